@@ -1,0 +1,203 @@
+/*
+ * numbskull_b200.h -- C ABI of the B200-native Gibbs / weight-learning hot path.
+ *
+ * This is the drop-in boundary.  In the reference the
+ * seam is FactorGraph (numbskull/factorgraph.py:27-208): its constructor takes
+ * the packed numpy record arrays declared in numbskull/numbskulltypes.py:11-39
+ * and its burnIn/inference/learn methods hand those arrays to the numba
+ * kernels through run_pool (factorgraph.py:13-24).  Every entry point below
+ * replaces one of those hand-offs; the comment above each names the reference
+ * lines it stands in for.  All pointers are plain host pointers unless a name
+ * says "dev"; no torch / C++ types cross this boundary.
+ *
+ * Every function returns NB_OK (0) or an NB_ERR_* code; nb_last_error()
+ * returns a human-readable message for the calling thread's last failure.
+ * There is NO CPU fallback: without a CUDA device nb_graph_create fails with
+ * NB_ERR_CUDA.
+ */
+#ifndef NUMBSKULL_B200_H
+#define NUMBSKULL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_ABI_VERSION 1
+
+enum {
+    NB_OK = 0,
+    NB_ERR_INVALID = 1,          /* malformed input (-> ValueError / AssertionError)        */
+    NB_ERR_NOT_IMPLEMENTED = 2,  /* unknown factorFunction (inference.py:410-413)           */
+    NB_ERR_CUDA = 3,             /* CUDA runtime failure or no device                        */
+    NB_ERR_UNSUPPORTED = 4,      /* valid for the reference, outside this build's limits     */
+    NB_ERR_NOMEM = 5
+};
+
+/* ---- host record layouts: numbskull/numbskulltypes.py:11-39, packed ---- */
+#pragma pack(push, 1)
+typedef struct { uint8_t isFixed; double initialValue; } nb_weight_rec;              /*  9 B */
+typedef struct { int8_t isEvidence; int64_t initialValue; int16_t dataType;
+                 int64_t cardinality; int64_t vtf_offset; } nb_variable_rec;          /* 27 B */
+typedef struct { int16_t factorFunction; int64_t weightId; double featureValue;
+                 int64_t arity; int64_t ftv_offset; } nb_factor_rec;                  /* 34 B */
+typedef struct { int64_t vid; int64_t dense_equal_to; } nb_ftv_rec;                   /* 16 B */
+typedef struct { int64_t value; int64_t factor_index_offset;
+                 int64_t factor_index_length; } nb_vtf_rec;                           /* 24 B */
+#pragma pack(pop)
+
+typedef struct nb_graph nb_graph; /* opaque, owns all device memory of one factor graph */
+
+/* What FactorGraph.__init__ receives (factorgraph.py:30-36) plus placement. */
+typedef struct {
+    const nb_weight_rec *weight;       int64_t n_weight;
+    const nb_variable_rec *variable;   int64_t n_variable;
+    const nb_factor_rec *factor;       int64_t n_factor;
+    const nb_ftv_rec *fmap;            int64_t n_fmap;
+    const nb_vtf_rec *vmap;            int64_t n_vmap;
+    const int64_t *factor_index;       int64_t n_factor_index;
+    int32_t device;                    /* CUDA ordinal                                     */
+    uint64_t color_seed;               /* Jones-Plassmann priority seed                    */
+    const int64_t *global_vid;         /* NULL, or per-variable global id (partitioned
+                                          graphs: priorities and RNG streams are functions
+                                          of the GLOBAL id so all ranks agree)             */
+    int32_t warp_row_words;            /* rows longer than this go one-per-warp; 0 = default */
+    int32_t sigma_shift;               /* SELL sorting window = 2^sigma_shift ids; 0 = default */
+    const int32_t *preset_color;       /* NULL, or a valid colouring to adopt (n_variable)  */
+} nb_graph_desc;
+
+typedef struct {
+    int64_t n_variable, n_factor, n_weight, n_edges; /* n_edges = sum of bucket lengths     */
+    int32_t n_colors;
+    int32_t wide_headers;              /* 0 = 1-word incidence headers, 1 = 2-word          */
+    int64_t n_thread_rows, n_warp_rows;
+    int64_t stream_words;              /* 32-bit words in the incidence streams (with pad)  */
+    int64_t device_bytes;              /* total device allocation                           */
+    int64_t count_entries;             /* == cstart[n_variable]                              */
+    int64_t jp_rounds;
+} nb_graph_info;
+
+const char *nb_last_error(void);
+int nb_abi_version(void);
+int nb_device_count(int *count);
+
+/* ---------------- host-side integer work (bit-exact) ---------------- */
+
+/* numbskull.py:219-227 / :309-317 -- the per-variable Python loop that assigns
+ * vtf_offset; returns the number of VarToFactor records through *n_vtf. */
+int nb_assign_vtf_offsets(nb_variable_rec *variable, int64_t n_variable, int64_t *n_vtf);
+
+/* dataloading.py:16-81 compute_var_map, in place, same outputs.  Unlike the
+ * reference it bounds-checks every index (the reference's factors_to_skip
+ * path overruns factor_index; here that returns NB_ERR_INVALID). */
+int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
+                       const nb_factor_rec *factor, int64_t n_factor,
+                       const nb_ftv_rec *fmap, int64_t n_fmap,
+                       nb_vtf_rec *vmap, int64_t n_vmap,
+                       int64_t *factor_index, int64_t n_factor_index,
+                       const uint8_t *domain_mask,
+                       const int64_t *factors_to_skip, int64_t n_skip);
+
+/* dataloading.py:103-123 / :126-156 / :159-187 / :190-237 -- big-endian
+ * DeepDive binary parsers (graph.weights 17 B/rec, graph.variables 27 B/rec,
+ * graph.domains, graph.factors variable-length). */
+int nb_load_weights(const uint8_t *data, int64_t n_bytes, int64_t n_weight, nb_weight_rec *out);
+int nb_load_variables(const uint8_t *data, int64_t n_bytes, int64_t n_variable,
+                      nb_variable_rec *out);
+int nb_load_domains(const uint8_t *data, int64_t n_bytes, uint8_t *domain_mask, nb_vtf_rec *vmap,
+                    int64_t n_vmap, nb_variable_rec *variable, int64_t n_variable);
+int nb_load_factors(const uint8_t *data, int64_t n_bytes, int64_t n_factor, nb_factor_rec *factor,
+                    nb_ftv_rec *fmap, int64_t n_fmap, const uint8_t *domain_mask,
+                    const nb_variable_rec *variable, int64_t n_variable, const nb_vtf_rec *vmap,
+                    int64_t n_vmap);
+
+/* -------------------------- graph lifecycle -------------------------- */
+
+/* FactorGraph.__init__ (factorgraph.py:30-73): builds the device-resident
+ * SoA/CSR form, colours the variable conflict graph (Jones-Plassmann on the
+ * GPU), reorders variables by (colour, row length) and lays the per-variable
+ * incidence streams out in HBM.  State starts as the reference's: var_value =
+ * var_value_evid = initialValue, weight_value = weight.initialValue, count = 0. */
+int nb_graph_create(const nb_graph_desc *desc, nb_graph **out);
+void nb_graph_destroy(nb_graph *g);          /* FactorGraph.clear (factorgraph.py:75-78) */
+int nb_graph_get_info(const nb_graph *g, nb_graph_info *info);
+
+/* Colour of every variable in ORIGINAL id order (-1 = not owned, isEvidence==4).
+ * Parity hook for "no two same-colour variables share a factor". */
+int nb_graph_get_colors(const nb_graph *g, int32_t *colors);
+/* Device-side validity check of the colouring in use: number of ordered pairs of
+ * owned variables that share a factor AND a colour (0 for a valid colouring). */
+int nb_graph_check_coloring(nb_graph *g, int64_t *conflicts);
+/* Bucket entries (factor-edge evaluations per sweep) owned by each colour; n_colors entries. */
+int nb_graph_color_edges(const nb_graph *g, int64_t *edges_per_color);
+
+/* ------------------- state exchange at call boundaries ------------------- */
+/* The arrays are the reference's public ones (factorgraph.py:46-52):
+ * chain 0 = var_value[var_copy], chain 1 = var_value_evid[var_copy] (int64, original
+ * variable order); weight_value[weight_copy] (float64); count (int64, cstart layout). */
+int nb_set_var_values(nb_graph *g, int chain, const int64_t *values);
+int nb_get_var_values(nb_graph *g, int chain, int64_t *values);
+int nb_set_weights(nb_graph *g, const double *weights);
+int nb_get_weights(nb_graph *g, double *weights);
+int nb_reset_counts(nb_graph *g);
+/* accumulate != 0: counts[i] += device tally (the reference's count is cumulative,
+ * factorgraph.py:172-173); else counts[i] = device tally. */
+int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate);
+
+/* ------------------------------ hot path ------------------------------ */
+
+/* inference.py:55-71 potential(), for parity tests: energies of every value of
+ * the listed variables under the current state of `chain`; variable var_ids[i]
+ * writes cardinality entries starting at out[out_offsets[i]]. */
+int nb_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
+                  const int64_t *out_offsets, double *out, int64_t n_out);
+
+/* run_pool(gibbsthread) x n_epochs (factorgraph.py:135-141 burnIn with
+ * burnin != 0, :156-163 inference with burnin == 0): one chromatic Gibbs sweep
+ * per epoch, one kernel launch per colour and row class.  Tallies into the
+ * device count unless burnin.  `seed` keys the Philox streams. */
+int nb_gibbs_sweeps(nb_graph *g, int64_t n_epochs, int burnin, int sample_evidence,
+                    uint64_t seed);
+
+/* run_pool(learnthread) x n_epochs with stepsize *= decay after each
+ * (factorgraph.py:188-206); *stepsize is updated to the final value.
+ * Both chains are sampled in one sweep; gradients are reduced by weight id
+ * and applied once per mini-batch of at most `batch_visits` visits per weight
+ * (0 = default policy, see DESIGN.md "learning"). */
+int nb_learn_sweeps(nb_graph *g, int64_t n_epochs, double *stepsize, double decay,
+                    int regularization, double reg_param, double truncation,
+                    int learn_non_evidence, uint64_t seed, int64_t batch_visits);
+
+/* ------------------------- measurement helpers ------------------------- */
+/* CUDA-event timer on the stream the sweeps are launched on. */
+int nb_timer_start(nb_graph *g);
+int nb_timer_stop(nb_graph *g, float *milliseconds);
+int nb_synchronize(nb_graph *g);
+/* Number of kernel launches issued by this graph's sweeps so far. */
+int nb_launch_count(const nb_graph *g, int64_t *launches);
+/* Write `bytes` of device memory to evict L2 between timed iterations. */
+int nb_flush_l2(nb_graph *g, int64_t bytes);
+
+/* --------------------- partitioned (multi-GPU) graphs --------------------- */
+/* Owner-computes partitioning (salt/src/numbskull_master.py:343,
+ * numbskull_minion.py:185): non-owned members are local variables with
+ * isEvidence == 4.  After each colour the owner's fresh values are shipped to
+ * the ranks that hold them as ghosts (messages.py:1308-1319).  These calls
+ * expose one colour phase at a time plus gather/scatter by local variable id
+ * on DEVICE buffers so the host layer can put NCCL between them. */
+int nb_gibbs_color_phase(nb_graph *g, int color, int burnin, int sample_evidence,
+                         uint64_t seed, int64_t epoch);
+/* values of `local_ids` (device int32, ORIGINAL local ids) of `chain` -> dev_out (uint8) */
+int nb_gather_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, int64_t n,
+                         uint8_t *dev_out);
+int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, int64_t n,
+                          const uint8_t *dev_in);
+/* run the sweeps on a caller-owned CUDA stream (cudaStream_t as void*) */
+int nb_set_stream(nb_graph *g, void *cuda_stream);
+int nb_begin_epoch(nb_graph *g, int64_t *epoch); /* returns and advances the sweep counter */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUMBSKULL_B200_H */

@@ -1,0 +1,348 @@
+// C-ABI entry points: graph lifecycle, state exchange at call boundaries,
+// sweep drivers and measurement helpers (include/numbskull_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "nb_common.cuh"
+
+static inline unsigned grid_for(int64_t n, int block = 256) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------
+extern "C" int nb_graph_create(const nb_graph_desc *desc, nb_graph **out)
+{
+    *out = nullptr;
+    if (!desc) NB_FAIL(NB_ERR_INVALID, "null descriptor");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        NB_FAIL(NB_ERR_CUDA, "no CUDA device available (%s); numbskull_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (desc->device < 0 || desc->device >= ndev) NB_FAIL(NB_ERR_INVALID, "device %d out of range [0, %d)", desc->device, ndev);
+    NB_CUDA(cudaSetDevice(desc->device));
+    nb_graph *g = new nb_graph();
+    g->device = desc->device;
+    int rc = NB_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) {
+            nb_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = NB_ERR_CUDA;
+            break;
+        }
+        rc = nb_build_device_graph(g, desc);
+    } while (0);
+    if (rc != NB_OK) { nb_graph_destroy(g); return rc; }
+    *out = g;
+    return NB_OK;
+}
+
+extern "C" void nb_graph_destroy(nb_graph *g)
+{
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    for (void *p : g->allocs) cudaFree(p);
+    if (g->d_xfer) cudaFree(g->d_xfer);
+    if (g->d_flush) cudaFree(g->d_flush);
+    if (g->h_pinned) cudaFreeHost(g->h_pinned);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->stream && g->own_stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+extern "C" int nb_graph_get_info(const nb_graph *g, nb_graph_info *info)
+{
+    memset(info, 0, sizeof(*info));
+    info->n_variable = g->V; info->n_factor = g->F; info->n_weight = g->W; info->n_edges = g->n_edges;
+    info->n_colors = g->n_colors; info->wide_headers = g->wide ? 1 : 0;
+    info->n_thread_rows = g->n_trows; info->n_warp_rows = g->n_wrows;
+    info->stream_words = g->n_twords + g->n_wwords;
+    info->device_bytes = g->device_bytes; info->count_entries = g->count_entries; info->jp_rounds = g->jp_rounds;
+    return NB_OK;
+}
+
+extern "C" int nb_graph_get_colors(const nb_graph *g, int32_t *colors)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaMemcpyAsync(colors, g->d_color, (size_t)g->V * 4, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    for (int64_t i = 0; i < g->V; i++) if (colors[i] < 0) colors[i] = -1;
+    return NB_OK;
+}
+
+extern "C" int nb_graph_color_edges(const nb_graph *g, int64_t *edges_per_color)
+{
+    for (int c = 0; c < g->n_colors; c++) edges_per_color[c] = g->colors[(size_t)c].edges;
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// state exchange
+// ---------------------------------------------------------------------------
+__global__ void k_scatter_values_i64(int64_t V, const int64_t *in, const int32_t *old2new, const int32_t *v_card,
+                                     nb_val_t *val, int *bad)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int64_t x = in[v];
+    if (x < 0 || x >= v_card[v]) { *bad = 1; x = 0; }
+    val[old2new[v]] = (nb_val_t)x;
+}
+
+__global__ void k_gather_values_i64(int64_t V, const nb_val_t *val, const int32_t *old2new, int64_t *out)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v < V) out[v] = (int64_t)val[old2new[v]];
+}
+
+extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
+{
+    if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    NB_CUDA(cudaSetDevice(g->device));
+    const int64_t V = g->V;
+    NB_TRY(nb_ensure_xfer(g, (size_t)V * 8 + 16));
+    int *d_bad = (int *)((char *)g->d_xfer + (size_t)V * 8);
+    NB_CUDA(cudaMemcpyAsync(g->d_xfer, values, (size_t)V * 8, cudaMemcpyHostToDevice, g->stream));
+    NB_CUDA(cudaMemsetAsync(d_bad, 0, 4, g->stream));
+    k_scatter_values_i64<<<grid_for(V), 256, 0, g->stream>>>(V, (const int64_t *)g->d_xfer, g->d_old2new, g->d_v_card,
+                                                             g->d_val[chain], d_bad);
+    int bad = 0;
+    NB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    if (bad) NB_FAIL(NB_ERR_INVALID, "var_value holds entries outside [0, cardinality)");
+    return NB_OK;
+}
+
+extern "C" int nb_get_var_values(nb_graph *g, int chain, int64_t *values)
+{
+    if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    NB_CUDA(cudaSetDevice(g->device));
+    const int64_t V = g->V;
+    NB_TRY(nb_ensure_xfer(g, (size_t)V * 8));
+    k_gather_values_i64<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_val[chain], g->d_old2new, (int64_t *)g->d_xfer);
+    NB_CUDA(cudaMemcpyAsync(values, g->d_xfer, (size_t)V * 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_set_weights(nb_graph *g, const double *weights)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaMemcpyAsync(g->d_weight, weights, (size_t)g->W * 8, cudaMemcpyHostToDevice, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_get_weights(nb_graph *g, double *weights)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaMemcpyAsync(weights, g->d_weight, (size_t)g->W * 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_reset_counts(nb_graph *g)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaMemsetAsync(g->d_count, 0, (size_t)g->count_entries * 4, g->stream));
+    return NB_OK;
+}
+
+// new-order int32 tallies -> reference cstart layout, int64
+__global__ void k_counts_to_old(int64_t V, const int32_t *count, const uint32_t *cstart_new, const int64_t *cstart_old,
+                                const int32_t *old2new, const int32_t *v_card, int64_t *out)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int n = v_card[v] == 2 ? 1 : v_card[v];
+    uint32_t s = cstart_new[old2new[v]];
+    int64_t d = cstart_old[v];
+    for (int j = 0; j < n; j++) out[d + j] = (int64_t)count[s + j];
+}
+
+extern "C" int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    const int64_t n = g->count_entries;
+    if (n == 0) return NB_OK;
+    NB_TRY(nb_ensure_xfer(g, (size_t)n * 8));
+    k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_cstart, g->d_cstart_old, g->d_old2new,
+                                                            g->d_v_card, (int64_t *)g->d_xfer);
+    if (!accumulate) {
+        NB_CUDA(cudaMemcpyAsync(counts, g->d_xfer, (size_t)n * 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        return NB_OK;
+    }
+    NB_TRY(nb_ensure_pinned(g, (size_t)n * 8));
+    NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)n * 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    const int64_t *src = (const int64_t *)g->h_pinned;
+    int nt = n > (1 << 20) ? (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::vector<std::thread> th;
+    int64_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        int64_t a = t * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([=] { for (int64_t i = a; i < b; i++) counts[i] += src[i]; });
+    }
+    for (auto &t : th) t.join();
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// hot path drivers
+// ---------------------------------------------------------------------------
+static int check_runnable(const nb_graph *g)
+{
+    if (g->has_unknown_func)
+        NB_FAIL(NB_ERR_NOT_IMPLEMENTED, "Error: Factor Function %d ( used in factor %lld ) is not implemented.",
+                g->unknown_func_id, (long long)g->unknown_func_factor);
+    return NB_OK;
+}
+
+extern "C" int nb_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n, const int64_t *out_offsets,
+                             double *out, int64_t n_out)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    return nb_run_potentials(g, chain, var_ids, n, out_offsets, out, n_out);
+}
+
+extern "C" int nb_begin_epoch(nb_graph *g, int64_t *epoch)
+{
+    *epoch = (int64_t)g->epoch_counter++;
+    return NB_OK;
+}
+
+extern "C" int nb_gibbs_color_phase(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed, int64_t epoch)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    return nb_launch_gibbs_color(g, color, burnin, sample_evidence, seed, (uint64_t)epoch);
+}
+
+extern "C" int nb_gibbs_sweeps(nb_graph *g, int64_t n_epochs, int burnin, int sample_evidence, uint64_t seed)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    for (int64_t ep = 0; ep < n_epochs; ep++) {
+        uint64_t epoch = g->epoch_counter++;
+        for (int c = 0; c < g->n_colors; c++) NB_TRY(nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch));
+    }
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_learn_sweeps(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, int regularization,
+                               double reg_param, double truncation, int learn_non_evidence, uint64_t seed,
+                               int64_t batch_visits)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    NB_TRY(nb_run_learn(g, n_epochs, stepsize, decay, regularization, reg_param, truncation, learn_non_evidence, seed,
+                        batch_visits));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------
+extern "C" int nb_timer_start(nb_graph *g)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaEventRecord(g->ev0, g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_timer_stop(nb_graph *g, float *ms)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaEventRecord(g->ev1, g->stream));
+    NB_CUDA(cudaEventSynchronize(g->ev1));
+    NB_CUDA(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+    return NB_OK;
+}
+
+extern "C" int nb_synchronize(nb_graph *g)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_launch_count(const nb_graph *g, int64_t *launches)
+{
+    *launches = g->launches;
+    return NB_OK;
+}
+
+__global__ void k_flush(uint4 *p, int64_t n, uint32_t tag)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_uint4(tag, tag, tag, tag);
+}
+
+extern "C" int nb_flush_l2(nb_graph *g, int64_t bytes)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    if ((size_t)bytes > g->flush_bytes) {
+        if (g->d_flush) cudaFree(g->d_flush);
+        g->d_flush = nullptr;
+        g->flush_bytes = 0;
+        NB_CUDA(cudaMalloc(&g->d_flush, (size_t)bytes));
+        g->flush_bytes = (size_t)bytes;
+    }
+    k_flush<<<148 * 8, 256, 0, g->stream>>>((uint4 *)g->d_flush, bytes / 16, (uint32_t)g->launches);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// partitioned graphs: gather / scatter by original local id on device buffers
+// ---------------------------------------------------------------------------
+__global__ void k_gather_u8(int64_t n, const int32_t *ids, const int32_t *old2new, const nb_val_t *val, uint8_t *out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = val[old2new[ids[i]]];
+}
+__global__ void k_scatter_u8(int64_t n, const int32_t *ids, const int32_t *old2new, nb_val_t *val, const uint8_t *in)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) val[old2new[ids[i]]] = in[i];
+}
+
+extern "C" int nb_gather_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, int64_t n, uint8_t *dev_out)
+{
+    if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    if (n == 0) return NB_OK;
+    NB_CUDA(cudaSetDevice(g->device));
+    k_gather_u8<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_old2new, g->d_val[chain], dev_out);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+extern "C" int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, int64_t n, const uint8_t *dev_in)
+{
+    if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    if (n == 0) return NB_OK;
+    NB_CUDA(cudaSetDevice(g->device));
+    k_scatter_u8<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_old2new, g->d_val[chain], dev_in);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+extern "C" int nb_set_stream(nb_graph *g, void *cuda_stream)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    g->stream = (cudaStream_t)cuda_stream;
+    g->own_stream = false;
+    return NB_OK;
+}

@@ -1,0 +1,741 @@
+// Device-graph construction: AoS records -> SoA upload -> Jones-Plassmann
+// colouring -> (colour, window, row length) ordering -> SELL-32 / contiguous
+// incidence streams resident in HBM.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <cub/cub.cuh>
+
+#include "nb_common.cuh"
+
+// ---------------------------------------------------------------------------
+// small host helpers
+// ---------------------------------------------------------------------------
+template <class F>
+static void parallel_for(int64_t n, F fn)
+{
+    int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 64);
+    if (n < (1 << 16)) nt = 1;
+    if (nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    int64_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        int64_t a = t * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([=] { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
+
+int nb_dev_alloc(nb_graph *g, void **p, size_t bytes, bool zero)
+{
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        nb_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? NB_ERR_NOMEM : NB_ERR_CUDA;
+    }
+    g->allocs.push_back(*p);
+    g->device_bytes += (int64_t)bytes;
+    if (zero) NB_CUDA(cudaMemsetAsync(*p, 0, bytes, g->stream));
+    return NB_OK;
+}
+
+int nb_ensure_xfer(nb_graph *g, size_t bytes)
+{
+    if (g->xfer_bytes >= bytes) return NB_OK;
+    if (g->d_xfer) cudaFree(g->d_xfer);
+    g->d_xfer = nullptr;
+    g->xfer_bytes = 0;
+    cudaError_t e = cudaMalloc(&g->d_xfer, bytes);
+    if (e != cudaSuccess) NB_FAIL(NB_ERR_NOMEM, "cudaMalloc(xfer %zu) failed: %s", bytes, cudaGetErrorString(e));
+    g->xfer_bytes = bytes;
+    return NB_OK;
+}
+
+int nb_ensure_pinned(nb_graph *g, size_t bytes)
+{
+    if (g->pinned_bytes >= bytes) return NB_OK;
+    if (g->h_pinned) cudaFreeHost(g->h_pinned);
+    g->h_pinned = nullptr;
+    g->pinned_bytes = 0;
+    cudaError_t e = cudaMallocHost(&g->h_pinned, bytes);
+    if (e != cudaSuccess) NB_FAIL(NB_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    g->pinned_bytes = bytes;
+    return NB_OK;
+}
+
+template <class T>
+static int upload(nb_graph *g, T **dst, const std::vector<T> &src)
+{
+    NB_TRY(nb_alloc(g, dst, src.size(), false));
+    if (!src.empty())
+        NB_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+struct RawGraph {
+    int64_t V;
+    const int8_t *v_evid;
+    const int32_t *v_card;
+    const int8_t *v_dtype;
+    const int64_t *v_vtf;
+    const int64_t *b_off;
+    const int32_t *b_len;
+    const int32_t *fi;
+    const uint8_t *f_code;
+    const int32_t *f_wid;
+    const double *f_feat;
+    const int32_t *f_arity;
+    const int64_t *f_off;
+    const int32_t *m_vid;
+    const int32_t *m_eq;
+    const int64_t *gid;
+    bool wide;
+};
+
+__device__ __forceinline__ int nbuckets(const RawGraph &G, int64_t v) { return G.v_dtype[v] == 0 ? 1 : G.v_card[v]; }
+
+// words and incidences of every row (ghost rows are empty: they are never sampled)
+__global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, int *overflow)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V) return;
+    if (G.v_evid[v] == 4) { rowlen[v] = 0; ninc[v] = 0; return; }
+    uint64_t words = 0, inc = 0;
+    int nb = nbuckets(G, v);
+    for (int b = 0; b < nb; b++) {
+        int64_t off = G.b_off[G.v_vtf[v] + b];
+        int len = G.b_len[G.v_vtf[v] + b];
+        if (G.v_dtype[v] == 1 && len > 0) words += G.wide ? 2 : 1;
+        for (int e = 0; e < len; e++) {
+            int f = G.fi[off + e];
+            words += nb_incidence_words(G.wide, G.f_code[f], G.f_arity[f], G.f_feat[f] != 1.0);
+        }
+        inc += len;
+    }
+    if (words > 0x7FFFFFFFull || inc > 0x7FFFFFFFull) { *overflow = 1; words = 0; inc = 0; }
+    rowlen[v] = (uint32_t)words;
+    ninc[v] = (uint32_t)inc;
+}
+
+__host__ __device__ inline uint64_t nb_mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// Jones-Plassmann priority: a pure function of the GLOBAL variable id
+__host__ __device__ inline uint64_t nb_jp_priority(uint64_t gid, uint64_t seed)
+{
+    return (nb_mix64(gid ^ nb_mix64(seed)) & 0xFFFFFFFF00000000ull) | (gid & 0xFFFFFFFFull);
+}
+
+// One Jones-Plassmann round.  A variable takes the smallest colour unused by its
+// neighbours once every neighbour of higher priority is coloured; the outcome
+// equals a sequential greedy colouring in priority order, whatever the schedule.
+// Colours are searched in windows of 64 (cbase); a full window defers to the next round.
+__global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *cbase, unsigned long long *remaining)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V) return;
+    if (color[v] != -1) return;  // coloured, or -2 = ghost
+    const uint64_t pv = nb_jp_priority(G.gid ? (uint64_t)G.gid[v] : (uint64_t)v, seed);
+    const int base = cbase[v];
+    uint64_t used = 0;
+    bool ready = true;
+    int nb = nbuckets(G, v);
+    for (int b = 0; b < nb && ready; b++) {
+        int64_t off = G.b_off[G.v_vtf[v] + b];
+        int len = G.b_len[G.v_vtf[v] + b];
+        for (int e = 0; e < len && ready; e++) {
+            int f = G.fi[off + e];
+            int64_t mo = G.f_off[f];
+            int a = G.f_arity[f];
+            for (int j = 0; j < a; j++) {
+                int u = G.m_vid[mo + j];
+                if (u == v) continue;
+                int cu = ((volatile int32_t *)color)[u];
+                if (cu == -2) continue;
+                if (cu == -1) {
+                    uint64_t pu = nb_jp_priority(G.gid ? (uint64_t)G.gid[u] : (uint64_t)u, seed);
+                    if (pu > pv) { ready = false; break; }
+                } else if (cu >= base && cu < base + 64) {
+                    used |= 1ull << (cu - base);
+                }
+            }
+        }
+    }
+    if (!ready) { atomicAdd(remaining, 1ull); return; }
+    if (used == ~0ull) { cbase[v] = base + 64; atomicAdd(remaining, 1ull); return; }
+    ((volatile int32_t *)color)[v] = base + (__ffsll((long long)~used) - 1);
+}
+
+__global__ void k_init_color(int64_t V, const int8_t *v_evid, int32_t *color)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v < V) color[v] = v_evid[v] == 4 ? -2 : -1;
+}
+
+// conflicts = ordered pairs (v, u) of owned variables that share a factor and a colour
+__global__ void k_check_coloring(RawGraph G, const int32_t *color, unsigned long long *conflicts)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || color[v] < 0) return;
+    unsigned long long bad = 0;
+    int nb = nbuckets(G, v);
+    for (int b = 0; b < nb; b++) {
+        int64_t off = G.b_off[G.v_vtf[v] + b];
+        int len = G.b_len[G.v_vtf[v] + b];
+        for (int e = 0; e < len; e++) {
+            int f = G.fi[off + e];
+            for (int j = 0; j < G.f_arity[f]; j++) {
+                int u = G.m_vid[G.f_off[f] + j];
+                if (u != v && color[u] == color[v]) bad++;
+            }
+        }
+    }
+    if (bad) atomicAdd(conflicts, bad);
+}
+
+__global__ void k_max_color(int64_t V, const int32_t *color, int *maxc)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v < V && color[v] >= 0) atomicMax(maxc, color[v]);
+}
+
+// sort key: path(1) | colour(15) | window(28) | row length(20); ghosts use colour = n_colors
+__global__ void k_sort_keys(int64_t V, const int32_t *color, const uint32_t *rowlen, int n_colors,
+                            int warp_row_words, int sigma_shift, uint64_t *keys, int32_t *ids,
+                            unsigned long long *group_count, unsigned long long *color_edges,
+                            const uint32_t *ninc)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int c = color[v] < 0 ? n_colors : color[v];
+    uint32_t len = rowlen[v];
+    int path = len > (uint32_t)warp_row_words ? 1 : 0;
+    uint64_t window = ((uint64_t)v >> sigma_shift) & ((1ull << 28) - 1);
+    uint64_t l = len < (1u << 20) ? len : (1u << 20) - 1;
+    keys[v] = ((uint64_t)path << 63) | ((uint64_t)c << 48) | (window << 20) | l;
+    ids[v] = (int32_t)v;
+    atomicAdd(&group_count[path * (n_colors + 1) + c], 1ull);
+    if (color[v] >= 0) atomicAdd(&color_edges[c], (unsigned long long)ninc[v]);
+}
+
+// sorted position -> new id, plus all per-variable arrays in the new order
+__global__ void k_assign_ids(int64_t V, const uint64_t *keys, const int32_t *sorted_ids, int n_colors,
+                             const int64_t *group_start, const int64_t *group_base, RawGraph G,
+                             const int32_t *v_init, const uint32_t *rowlen, int32_t *old2new,
+                             int32_t *new2old, uint32_t *vmeta, uint32_t *rowlen_new, nb_val_t *vinit,
+                             uint32_t *rng_id, nb_val_t *val0, nb_val_t *val1)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    uint64_t key = keys[i];
+    int path = (int)(key >> 63);
+    int c = (int)((key >> 48) & 0x7FFF);
+    int g = path * (n_colors + 1) + c;
+    int64_t nid = group_base[g] + (i - group_start[g]);
+    int v = sorted_ids[i];
+    old2new[v] = (int32_t)nid;
+    new2old[nid] = v;
+    vmeta[nid] = nb_pack_meta(G.v_card[v], G.v_evid[v], G.v_dtype[v], 1);
+    rowlen_new[nid] = rowlen[v];
+    nb_val_t init = (nb_val_t)v_init[v];
+    vinit[nid] = init;
+    val0[nid] = init;
+    val1[nid] = init;
+    rng_id[nid] = (uint32_t)(G.gid ? (uint64_t)G.gid[v] : (uint64_t)v);
+}
+
+__global__ void k_count_entries(int64_t Vn, const uint32_t *vmeta, uint32_t *entries)
+{
+    int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= Vn) return;
+    uint32_t m = vmeta[n];
+    int card = NB_META_CARD(m);
+    entries[n] = NB_META_VALID(m) ? (card == 2 ? 1u : (uint32_t)card) : 0u;
+}
+
+__global__ void k_count_entries_old(int64_t V, const int32_t *v_card, int64_t *entries)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v < V) entries[v] = v_card[v] == 2 ? 1 : v_card[v];
+}
+
+// SELL-32 slice width = longest row of the slice
+__global__ void k_slice_width(int64_t n_slices, const uint32_t *rowlen_new, int64_t *width32)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    uint32_t w = 0;
+    for (int l = 0; l < 32; l++) w = max(w, rowlen_new[s * 32 + l]);
+    width32[s] = (int64_t)w * 32;
+}
+
+__global__ void k_warp_row_sizes(int64_t n_wrows, int64_t n_trows, const uint32_t *rowlen_new,
+                                 const int32_t *new2old, const uint32_t *ninc, int64_t *wlen, int64_t *winc)
+{
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_wrows) return;
+    wlen[r] = rowlen_new[n_trows + r];
+    winc[r] = ninc[new2old[n_trows + r]];
+}
+
+// Write every row's incidence stream (member ids translated to new ids).
+__global__ void k_fill_rows(RawGraph G, const int32_t *old2new, int64_t n_trows, const int64_t *slice_ptr,
+                            uint32_t *twords, const int64_t *wrow_ptr, uint32_t *wwords,
+                            const int64_t *inc_ptr, uint2 *inc, const uint8_t *wfixed)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || G.v_evid[v] == 4) return;
+    int64_t nid = old2new[v];
+    uint32_t *base;
+    int64_t stride;
+    uint2 *incp = nullptr;
+    if (nid < n_trows) {
+        base = twords + slice_ptr[nid >> 5] + (nid & 31);
+        stride = 32;
+    } else {
+        base = wwords + wrow_ptr[nid - n_trows];
+        stride = 1;
+        incp = inc + inc_ptr[nid - n_trows];
+    }
+    int64_t pos = 0;
+    int nb = nbuckets(G, v);
+    const bool cat = G.v_dtype[v] == 1;
+    for (int b = 0; b < nb; b++) {
+        int64_t off = G.b_off[G.v_vtf[v] + b];
+        int len = G.b_len[G.v_vtf[v] + b];
+        if (cat && len > 0) {
+            if (G.wide) { base[pos * stride] = (uint32_t)b; base[(pos + 1) * stride] = nb_pack_wide_b(C_MARK, 0, 0, 0); pos += 2; }
+            else { base[pos * stride] = nb_pack_mark_compact((uint32_t)b); pos += 1; }
+        }
+        for (int e = 0; e < len; e++) {
+            int f = G.fi[off + e];
+            int code = G.f_code[f], a = G.f_arity[f];
+            uint32_t wid = (uint32_t)G.f_wid[f];
+            double feat = G.f_feat[f];
+            int hasfeat = feat != 1.0;
+            int fixed = wfixed[wid];
+            if (incp) { *incp++ = make_uint2((uint32_t)pos, (uint32_t)b); }
+            if (G.wide) {
+                base[pos * stride] = wid;
+                base[(pos + 1) * stride] = nb_pack_wide_b(code, hasfeat, fixed, a);
+                pos += 2;
+            } else {
+                base[pos * stride] = nb_pack_compact(code, hasfeat, fixed, a, wid);
+                pos += 1;
+            }
+            if (hasfeat) {
+                base[pos * stride] = (uint32_t)__double2loint(feat);
+                base[(pos + 1) * stride] = (uint32_t)__double2hiint(feat);
+                pos += 2;
+            }
+            int64_t mo = G.f_off[f];
+            bool eq = nb_code_has_eq(code);
+            for (int j = 0; j < a; j++) {
+                base[pos * stride] = (uint32_t)old2new[G.m_vid[mo + j]];
+                pos++;
+                if (eq) { base[pos * stride] = (uint32_t)G.m_eq[mo + j]; pos++; }
+            }
+            if (nb_code_has_extra(code)) {
+                uint32_t x;
+                if (code == C_IMPLY_MLN || code == C_IMPLY_NATURAL_CAT || code == C_IMPLY_MLN_CAT) {
+                    // the reference reads var_value[fmap slot of the head] (inference.py:243,277,292)
+                    int64_t slot = mo + a - 1;
+                    x = (a > 0 && slot < G.V) ? (uint32_t)old2new[slot] : 0xFFFFFFFFu;
+                } else {
+                    int m = nb_code_abstain_member(code);
+                    x = m < a ? (uint32_t)(G.v_card[G.m_vid[mo + m]] - 1) : 0u;
+                }
+                base[pos * stride] = x;
+                pos++;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+static RawGraph raw_view(const nb_graph *g)
+{
+    RawGraph G;
+    G.V = g->V;
+    G.v_evid = g->d_v_evid; G.v_card = g->d_v_card; G.v_dtype = g->d_v_dtype; G.v_vtf = g->d_v_vtf;
+    G.b_off = g->d_b_off; G.b_len = g->d_b_len; G.fi = g->d_fi;
+    G.f_code = g->d_f_code; G.f_wid = g->d_f_wid; G.f_feat = g->d_f_feat; G.f_arity = g->d_f_arity;
+    G.f_off = g->d_f_off; G.m_vid = g->d_m_vid; G.m_eq = g->d_m_eq; G.gid = g->d_gid; G.wide = g->wide;
+    return G;
+}
+
+static inline unsigned grid_for(int64_t n, int block = 256) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+
+template <class T>
+static int exclusive_scan(nb_graph *g, const T *in, T *out, int64_t n)
+{
+    size_t tmp = 0;
+    NB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, g->stream));
+    NB_TRY(nb_ensure_xfer(g, tmp));
+    NB_CUDA(cub::DeviceScan::ExclusiveSum(g->d_xfer, tmp, in, out, n, g->stream));
+    return NB_OK;
+}
+
+static int extract_and_upload(nb_graph *g, const nb_graph_desc *d)
+{
+    const int64_t V = d->n_variable, F = d->n_factor, W = d->n_weight;
+    const int64_t NF = d->n_fmap, NV = d->n_vmap, NFI = d->n_factor_index;
+    if (V < 0 || F < 0 || W < 0 || NF < 0 || NV < 0 || NFI < 0) NB_FAIL(NB_ERR_INVALID, "negative array length");
+    if (V >= (1ll << 31) - 64 || F >= (1ll << 31) || W >= (1ll << 31))
+        NB_FAIL(NB_ERR_UNSUPPORTED, "variables/factors/weights must stay below 2^31 per GPU (partition the graph)");
+    g->V = V; g->F = F; g->W = W; g->NFMAP = NF; g->NVMAP = NV; g->NFI = NFI;
+
+    std::atomic<int> bad(0);
+    std::atomic<int> maxcard(1), maxarity(0), anycat(0);
+    std::atomic<int64_t> unknown(-1);
+    char msg[256] = "";
+    auto fail = [&](const char *what, int64_t idx) {
+        int expected = 0;
+        if (bad.compare_exchange_strong(expected, 1)) snprintf(msg, sizeof(msg), "%s (index %lld)", what, (long long)idx);
+    };
+
+    // ---- variables ----
+    std::vector<int8_t> v_evid(V), v_dtype(V);
+    std::vector<int32_t> v_card(V), v_init(V);
+    std::vector<int64_t> v_vtf(V);
+    parallel_for(V, [&](int64_t a, int64_t b) {
+        int mc = 1, cat = 0;
+        for (int64_t i = a; i < b; i++) {
+            const nb_variable_rec &r = d->variable[i];
+            if (r.dataType != 0 && r.dataType != 1) { fail("variable dataType must be 0 or 1", i); continue; }
+            if (r.cardinality < 1 || r.cardinality > NB_MAX_CARD) { fail("variable cardinality outside [1, 255]", i); continue; }
+            if (r.initialValue < 0 || r.initialValue >= r.cardinality) { fail("variable initialValue outside [0, cardinality)", i); continue; }
+            int64_t nb = r.dataType == 0 ? 1 : r.cardinality;
+            if (r.vtf_offset < 0 || r.vtf_offset + nb > NV) { fail("variable vtf_offset out of range", i); continue; }
+            v_evid[i] = r.isEvidence; v_dtype[i] = (int8_t)r.dataType;
+            v_card[i] = (int32_t)r.cardinality; v_init[i] = (int32_t)r.initialValue; v_vtf[i] = r.vtf_offset;
+            mc = std::max(mc, (int)r.cardinality);
+            cat |= r.dataType == 1;
+        }
+        int cur = maxcard.load();
+        while (mc > cur && !maxcard.compare_exchange_weak(cur, mc)) {}
+        if (cat) anycat.store(1);
+    });
+    // ---- buckets ----
+    std::vector<int64_t> b_off(NV);
+    std::vector<int32_t> b_len(NV);
+    std::atomic<int64_t> edges(0);
+    parallel_for(NV, [&](int64_t a, int64_t b) {
+        int64_t sum = 0;
+        for (int64_t i = a; i < b; i++) {
+            const nb_vtf_rec &r = d->vmap[i];
+            if (r.factor_index_length < 0 || r.factor_index_offset < 0 ||
+                r.factor_index_offset + r.factor_index_length > NFI || r.factor_index_length > 0x7FFFFFFF) {
+                fail("vmap bucket outside factor_index", i);
+                continue;
+            }
+            b_off[i] = r.factor_index_offset;
+            b_len[i] = (int32_t)r.factor_index_length;
+            sum += r.factor_index_length;
+        }
+        edges += sum;
+    });
+    std::vector<int32_t> fi(NFI);
+    parallel_for(NFI, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            int64_t f = d->factor_index[i];
+            // entries beyond a bucket's de-duplicated length are scratch; clamp instead of failing
+            fi[i] = (f >= 0 && f < F) ? (int32_t)f : 0;
+        }
+    });
+    // ---- factors ----
+    std::vector<uint8_t> f_code(F);
+    std::vector<int32_t> f_wid(F), f_arity(F);
+    std::vector<double> f_feat(F);
+    std::vector<int64_t> f_off(F);
+    parallel_for(F, [&](int64_t a, int64_t b) {
+        int ma = 0, cat = 0;
+        for (int64_t i = a; i < b; i++) {
+            const nb_factor_rec &r = d->factor[i];
+            int code = nb_code_of_func(r.factorFunction);
+            if (code == C_UNKNOWN) {
+                int64_t cur = unknown.load();
+                while ((cur < 0 || i < cur) && !unknown.compare_exchange_weak(cur, i)) {}
+            }
+            if (r.weightId < 0 || r.weightId >= W) { fail("factor weightId out of range", i); continue; }
+            if (r.arity < 0 || r.arity >= (1 << 24) || r.ftv_offset < 0 || r.ftv_offset + r.arity > NF) { fail("factor fmap range out of bounds", i); continue; }
+            f_code[i] = (uint8_t)code; f_wid[i] = (int32_t)r.weightId; f_arity[i] = (int32_t)r.arity;
+            f_feat[i] = r.featureValue; f_off[i] = r.ftv_offset;
+            ma = std::max(ma, (int)r.arity);
+            cat |= nb_code_has_eq(code);
+        }
+        int cur = maxarity.load();
+        while (ma > cur && !maxarity.compare_exchange_weak(cur, ma)) {}
+        if (cat) anycat.store(1);
+    });
+    // ---- members ----
+    std::vector<int32_t> m_vid(NF), m_eq;
+    const bool need_eq = anycat.load() != 0;
+    if (need_eq) m_eq.resize(NF);
+    parallel_for(NF, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            const nb_ftv_rec &r = d->fmap[i];
+            if (r.vid < 0 || r.vid >= V) { fail("fmap vid out of range", i); continue; }
+            m_vid[i] = (int32_t)r.vid;
+            if (need_eq) m_eq[i] = (int32_t)std::min<int64_t>(std::max<int64_t>(r.dense_equal_to, -1), 0x7FFFFFFF);
+        }
+    });
+    if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+
+    g->n_edges = edges.load();
+    g->max_card = maxcard.load();
+    g->any_categorical = need_eq;
+    g->wide = (W > (int64_t)NB_COMPACT_MAX_WID + 1) || (maxarity.load() > NB_COMPACT_MAX_ARITY);
+    if (unknown.load() >= 0) {
+        g->has_unknown_func = true;
+        g->unknown_func_factor = unknown.load();
+        g->unknown_func_id = d->factor[unknown.load()].factorFunction;
+    }
+
+    NB_TRY(upload(g, &g->d_v_evid, v_evid));
+    NB_TRY(upload(g, &g->d_v_dtype, v_dtype));
+    NB_TRY(upload(g, &g->d_v_card, v_card));
+    NB_TRY(upload(g, &g->d_v_init, v_init));
+    NB_TRY(upload(g, &g->d_v_vtf, v_vtf));
+    NB_TRY(upload(g, &g->d_b_off, b_off));
+    NB_TRY(upload(g, &g->d_b_len, b_len));
+    NB_TRY(upload(g, &g->d_fi, fi));
+    NB_TRY(upload(g, &g->d_f_code, f_code));
+    NB_TRY(upload(g, &g->d_f_wid, f_wid));
+    NB_TRY(upload(g, &g->d_f_arity, f_arity));
+    NB_TRY(upload(g, &g->d_f_feat, f_feat));
+    NB_TRY(upload(g, &g->d_f_off, f_off));
+    NB_TRY(upload(g, &g->d_m_vid, m_vid));
+    if (need_eq) NB_TRY(upload(g, &g->d_m_eq, m_eq));
+    if (d->global_vid) {
+        std::vector<int64_t> gid(d->global_vid, d->global_vid + V);
+        NB_TRY(upload(g, &g->d_gid, gid));
+    }
+    // weights
+    std::vector<double> w(W);
+    std::vector<uint8_t> wf(W);
+    for (int64_t i = 0; i < W; i++) { w[i] = d->weight[i].initialValue; wf[i] = d->weight[i].isFixed ? 1 : 0; }
+    NB_TRY(upload(g, &g->d_weight, w));
+    NB_TRY(upload(g, &g->d_wfixed, wf));
+    return NB_OK;
+}
+
+static int color_graph(nb_graph *g, const nb_graph_desc *d)
+{
+    const int64_t V = g->V;
+    RawGraph G = raw_view(g);
+    NB_TRY(nb_alloc(g, &g->d_color, (size_t)V, false));
+    unsigned long long *d_cnt;
+    NB_TRY(nb_alloc(g, &d_cnt, 2));
+    if (d->preset_color) {
+        NB_CUDA(cudaMemcpyAsync(g->d_color, d->preset_color, (size_t)V * 4, cudaMemcpyHostToDevice, g->stream));
+        k_check_coloring<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_color, d_cnt);
+        unsigned long long bad = 0;
+        NB_CUDA(cudaMemcpyAsync(&bad, d_cnt, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        if (bad) NB_FAIL(NB_ERR_INVALID, "preset colouring has %llu conflicts", bad);
+    } else {
+        int32_t *d_cbase;
+        NB_TRY(nb_alloc(g, &d_cbase, (size_t)V));
+        k_init_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_v_evid, g->d_color);
+        for (int64_t round = 0;; round++) {
+            NB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, g->stream));
+            k_jp_round<<<grid_for(V), 256, 0, g->stream>>>(G, d->color_seed, g->d_color, d_cbase, d_cnt);
+            unsigned long long rem = 0;
+            NB_CUDA(cudaMemcpyAsync(&rem, d_cnt, 8, cudaMemcpyDeviceToHost, g->stream));
+            NB_CUDA(cudaStreamSynchronize(g->stream));
+            g->jp_rounds = round + 1;
+            if (rem == 0) break;
+            if (round > 1000000) NB_FAIL(NB_ERR_CUDA, "Jones-Plassmann colouring did not converge");
+        }
+    }
+    int *d_max;
+    NB_TRY(nb_alloc(g, &d_max, 1));
+    NB_CUDA(cudaMemsetAsync(d_max, 0xFF, 4, g->stream));  // -1
+    k_max_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_max);
+    int maxc = -1;
+    NB_CUDA(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    g->n_colors = maxc + 1;
+    if (g->n_colors >= 0x7FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 32766)", g->n_colors);
+    return NB_OK;
+}
+
+int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
+{
+    if (d->warp_row_words > 0) g->warp_row_words = d->warp_row_words;
+    if (d->sigma_shift > 0) g->sigma_shift = d->sigma_shift;
+    NB_TRY(extract_and_upload(g, d));
+    const int64_t V = g->V;
+    RawGraph G = raw_view(g);
+
+    // ---- row sizes ----
+    uint32_t *d_rowlen, *d_ninc;
+    int *d_overflow;
+    NB_TRY(nb_alloc(g, &d_rowlen, (size_t)V));
+    NB_TRY(nb_alloc(g, &d_ninc, (size_t)V));
+    NB_TRY(nb_alloc(g, &d_overflow, 1));
+    k_row_size<<<grid_for(V), 256, 0, g->stream>>>(G, d_rowlen, d_ninc, d_overflow);
+    int overflow = 0;
+    NB_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    if (overflow) NB_FAIL(NB_ERR_UNSUPPORTED, "a variable's incidence row exceeds 2^31 words");
+
+    // ---- colouring ----
+    NB_TRY(color_graph(g, d));
+    const int nc = g->n_colors, ng = 2 * (nc + 1);
+
+    // ---- ordering ----
+    uint64_t *d_keys, *d_keys_sorted;
+    int32_t *d_ids, *d_ids_sorted;
+    unsigned long long *d_group_count, *d_color_edges;
+    NB_TRY(nb_alloc(g, &d_keys, (size_t)V, false));
+    NB_TRY(nb_alloc(g, &d_keys_sorted, (size_t)V, false));
+    NB_TRY(nb_alloc(g, &d_ids, (size_t)V, false));
+    NB_TRY(nb_alloc(g, &d_ids_sorted, (size_t)V, false));
+    NB_TRY(nb_alloc(g, &d_group_count, (size_t)ng));
+    NB_TRY(nb_alloc(g, &d_color_edges, (size_t)nc + 1));
+    k_sort_keys<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_rowlen, nc, g->warp_row_words, g->sigma_shift,
+                                                    d_keys, d_ids, d_group_count, d_color_edges, d_ninc);
+    {
+        size_t tmp = 0;
+        NB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_keys, d_keys_sorted, d_ids, d_ids_sorted, V, 0, 64, g->stream));
+        NB_TRY(nb_ensure_xfer(g, tmp));
+        NB_CUDA(cub::DeviceRadixSort::SortPairs(g->d_xfer, tmp, d_keys, d_keys_sorted, d_ids, d_ids_sorted, V, 0, 64, g->stream));
+    }
+    std::vector<unsigned long long> gcount((size_t)ng), cedges((size_t)nc + 1);
+    NB_CUDA(cudaMemcpyAsync(gcount.data(), d_group_count, (size_t)ng * 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaMemcpyAsync(cedges.data(), d_color_edges, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+
+    // groups in sorted order: path 0 colours 0..nc (nc = ghosts), then path 1 colours 0..nc
+    std::vector<int64_t> gstart((size_t)ng), gbase((size_t)ng);
+    g->colors.assign((size_t)nc, NbColorRange());
+    int64_t pos = 0, nid = 0;
+    for (int c = 0; c <= nc; c++) {
+        gstart[(size_t)c] = pos;
+        nid = (nid + 31) & ~31ll;
+        gbase[(size_t)c] = nid;
+        if (c < nc) { g->colors[(size_t)c].t_beg = (int32_t)nid; g->colors[(size_t)c].t_end = (int32_t)(nid + (int64_t)gcount[(size_t)c]); }
+        pos += (int64_t)gcount[(size_t)c];
+        nid += (int64_t)gcount[(size_t)c];
+    }
+    g->n_trows = (nid + 31) & ~31ll;
+    int64_t wr = 0;
+    for (int c = 0; c <= nc; c++) {
+        size_t gi = (size_t)(nc + 1 + c);
+        gstart[gi] = pos;
+        gbase[gi] = g->n_trows + wr;
+        if (c < nc) { g->colors[(size_t)c].w_beg = (int32_t)wr; g->colors[(size_t)c].w_end = (int32_t)(wr + (int64_t)gcount[gi]); g->colors[(size_t)c].edges = (int64_t)cedges[(size_t)c]; }
+        pos += (int64_t)gcount[gi];
+        wr += (int64_t)gcount[gi];
+    }
+    g->n_wrows = wr;
+    g->Vn = g->n_trows + g->n_wrows;
+    if (g->Vn >= (1ll << 31)) NB_FAIL(NB_ERR_UNSUPPORTED, "padded variable id space exceeds 2^31");
+    const int64_t Vn = g->Vn;
+
+    int64_t *d_gstart, *d_gbase;
+    NB_TRY(upload(g, &d_gstart, gstart));
+    NB_TRY(upload(g, &d_gbase, gbase));
+    NB_TRY(nb_alloc(g, &g->d_old2new, (size_t)V, false));
+    NB_TRY(nb_alloc(g, &g->d_new2old, (size_t)Vn, false));
+    NB_CUDA(cudaMemsetAsync(g->d_new2old, 0xFF, (size_t)Vn * 4, g->stream));
+    NB_TRY(nb_alloc(g, &g->d_vmeta, (size_t)Vn));
+    NB_TRY(nb_alloc(g, &g->d_rowlen, (size_t)Vn));
+    NB_TRY(nb_alloc(g, &g->d_vinit, (size_t)Vn));
+    NB_TRY(nb_alloc(g, &g->d_rng_id, (size_t)Vn));
+    NB_TRY(nb_alloc(g, &g->d_val[0], (size_t)Vn));
+    NB_TRY(nb_alloc(g, &g->d_val[1], (size_t)Vn));
+    k_assign_ids<<<grid_for(V), 256, 0, g->stream>>>(V, d_keys_sorted, d_ids_sorted, nc, d_gstart, d_gbase, G,
+                                                     g->d_v_init, d_rowlen, g->d_old2new, g->d_new2old, g->d_vmeta,
+                                                     g->d_rowlen, g->d_vinit, g->d_rng_id, g->d_val[0], g->d_val[1]);
+
+    // ---- count layouts ----
+    {
+        uint32_t *d_entries;
+        NB_TRY(nb_alloc(g, &d_entries, (size_t)Vn + 1));
+        NB_TRY(nb_alloc(g, &g->d_cstart, (size_t)Vn + 1));
+        k_count_entries<<<grid_for(Vn), 256, 0, g->stream>>>(Vn, g->d_vmeta, d_entries);
+        NB_TRY(exclusive_scan(g, d_entries, g->d_cstart, Vn + 1));
+        int64_t *d_entries_old;
+        NB_TRY(nb_alloc(g, &d_entries_old, (size_t)V + 1));
+        NB_TRY(nb_alloc(g, &g->d_cstart_old, (size_t)V + 1));
+        k_count_entries_old<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_v_card, d_entries_old);
+        NB_TRY(exclusive_scan(g, d_entries_old, g->d_cstart_old, V + 1));
+        int64_t total = 0;
+        uint32_t total_new = 0;
+        NB_CUDA(cudaMemcpyAsync(&total, g->d_cstart_old + V, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaMemcpyAsync(&total_new, g->d_cstart + Vn, 4, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        if (total >= (1ll << 32) - 1 || total != (int64_t)total_new)
+            NB_FAIL(NB_ERR_UNSUPPORTED, "count array of %lld entries unsupported (new layout %u)", (long long)total, total_new);
+        g->count_entries = total;
+        NB_TRY(nb_alloc(g, &g->d_count, (size_t)total));
+    }
+
+    // ---- SELL-32 slices (thread path) ----
+    const int64_t n_slices = g->n_trows / 32;
+    {
+        int64_t *d_width;
+        NB_TRY(nb_alloc(g, &d_width, (size_t)n_slices + 1));
+        NB_TRY(nb_alloc(g, &g->d_slice_ptr, (size_t)n_slices + 1));
+        if (n_slices) k_slice_width<<<grid_for(n_slices), 256, 0, g->stream>>>(n_slices, g->d_rowlen, d_width);
+        NB_TRY(exclusive_scan(g, d_width, g->d_slice_ptr, n_slices + 1));
+        NB_CUDA(cudaMemcpyAsync(&g->n_twords, g->d_slice_ptr + n_slices, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        NB_TRY(nb_alloc(g, &g->d_twords, (size_t)g->n_twords));
+    }
+    // ---- contiguous rows (warp path) ----
+    {
+        const int64_t nw = g->n_wrows;
+        int64_t *d_wlen, *d_winc;
+        NB_TRY(nb_alloc(g, &d_wlen, (size_t)nw + 1));
+        NB_TRY(nb_alloc(g, &d_winc, (size_t)nw + 1));
+        NB_TRY(nb_alloc(g, &g->d_wrow_ptr, (size_t)nw + 1));
+        NB_TRY(nb_alloc(g, &g->d_inc_ptr, (size_t)nw + 1));
+        if (nw) k_warp_row_sizes<<<grid_for(nw), 256, 0, g->stream>>>(nw, g->n_trows, g->d_rowlen, g->d_new2old, d_ninc, d_wlen, d_winc);
+        NB_TRY(exclusive_scan(g, d_wlen, g->d_wrow_ptr, nw + 1));
+        NB_TRY(exclusive_scan(g, d_winc, g->d_inc_ptr, nw + 1));
+        NB_CUDA(cudaMemcpyAsync(&g->n_wwords, g->d_wrow_ptr + nw, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaMemcpyAsync(&g->n_inc, g->d_inc_ptr + nw, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        NB_TRY(nb_alloc(g, &g->d_wwords, (size_t)g->n_wwords));
+        NB_TRY(nb_alloc(g, &g->d_inc, (size_t)g->n_inc));
+    }
+    k_fill_rows<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_trows, g->d_slice_ptr, g->d_twords,
+                                                    g->d_wrow_ptr, g->d_wwords, g->d_inc_ptr, g->d_inc, g->d_wfixed);
+    NB_CUDA(cudaGetLastError());
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_graph_check_coloring(nb_graph *g, int64_t *conflicts)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    unsigned long long *d_cnt;
+    NB_CUDA(cudaMalloc(&d_cnt, 8));
+    cudaMemsetAsync(d_cnt, 0, 8, g->stream);
+    k_check_coloring<<<grid_for(g->V), 256, 0, g->stream>>>(raw_view(g), g->d_color, d_cnt);
+    unsigned long long bad = 0;
+    cudaMemcpyAsync(&bad, d_cnt, 8, cudaMemcpyDeviceToHost, g->stream);
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_cnt);
+    NB_CUDA(e);
+    *conflicts = (int64_t)bad;
+    return NB_OK;
+}

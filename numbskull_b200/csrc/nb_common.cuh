@@ -1,0 +1,274 @@
+// Internal declarations shared by the translation units of libnumbskull_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/numbskull_b200.h"
+
+// ----------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------
+void nb_set_error(const char *fmt, ...);
+
+#define NB_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            nb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__,  \
+                         __LINE__, cudaGetErrorString(e_));                             \
+            return NB_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define NB_TRY(call)                       \
+    do {                                   \
+        int rc_ = (call);                  \
+        if (rc_ != NB_OK) return rc_;      \
+    } while (0)
+
+#define NB_FAIL(code, ...)      \
+    do {                        \
+        nb_set_error(__VA_ARGS__); \
+        return (code);          \
+    } while (0)
+
+// ----------------------------------------------------------------------------
+// factor-function codes (dense 5-bit re-numbering of inference.py:74-146)
+// ----------------------------------------------------------------------------
+enum NbCode : int {
+    C_NOOP = 0, C_IMPLY_NATURAL = 1, C_OR = 2, C_AND = 3, C_EQUAL = 4, C_ISTRUE = 5,
+    C_LINEAR = 6, C_RATIO = 7, C_LOGICAL = 8, C_IMPLY_MLN = 9,
+    C_AND_CAT = 10, C_OR_CAT = 11, C_EQUAL_CAT_CONST = 12, C_IMPLY_NATURAL_CAT = 13,
+    C_IMPLY_MLN_CAT = 14,
+    C_DP_CLASS_PRIOR = 15, C_DP_LF_PRIOR = 16, C_DP_LF_PROPENSITY = 17, C_DP_LF_ACCURACY = 18,
+    C_DP_LF_CLASS_PROPENSITY = 19, C_DP_DEP_FIXING = 20, C_DP_DEP_REINFORCING = 21,
+    C_DP_DEP_EXCLUSIVE = 22, C_DP_DEP_SIMILAR = 23, C_UFO = 24,
+    C_UNKNOWN = 30,  // never emitted into a stream
+    C_MARK = 31      // categorical bucket marker
+};
+
+__host__ __device__ inline int nb_code_of_func(int func)
+{
+    switch (func) {
+    case -1: return C_NOOP;
+    case 0: return C_IMPLY_NATURAL;
+    case 1: return C_OR;
+    case 2: return C_AND;
+    case 3: return C_EQUAL;
+    case 4: return C_ISTRUE;
+    case 7: return C_LINEAR;
+    case 8: return C_RATIO;
+    case 9: return C_LOGICAL;
+    case 12: return C_AND_CAT;
+    case 13: return C_IMPLY_MLN;
+    case 14: return C_OR_CAT;
+    case 15: return C_EQUAL_CAT_CONST;
+    case 16: return C_IMPLY_NATURAL_CAT;
+    case 17: return C_IMPLY_MLN_CAT;
+    case 18: return C_DP_CLASS_PRIOR;
+    case 19: return C_DP_LF_PRIOR;
+    case 20: return C_DP_LF_PROPENSITY;
+    case 21: return C_DP_LF_ACCURACY;
+    case 22: return C_DP_LF_CLASS_PROPENSITY;
+    case 23: return C_DP_DEP_FIXING;
+    case 24: return C_DP_DEP_REINFORCING;
+    case 25: return C_DP_DEP_EXCLUSIVE;
+    case 26: return C_DP_DEP_SIMILAR;
+    case 30: return C_UFO;
+    default: return C_UNKNOWN;
+    }
+}
+
+// members carry a dense_equal_to word
+__host__ __device__ inline bool nb_code_has_eq(int c) { return c >= C_AND_CAT && c <= C_IMPLY_MLN_CAT; }
+// one extra trailing word: the as-coded "head alias" variable for the three
+// implication functions that index var_value by fmap slot (inference.py:243,277,292),
+// or the abstain value (cardinality - 1 of a fixed member) for the DP functions.
+__host__ __device__ inline bool nb_code_has_extra(int c)
+{
+    return c == C_IMPLY_MLN || c == C_IMPLY_NATURAL_CAT || c == C_IMPLY_MLN_CAT ||
+           (c >= C_DP_LF_PROPENSITY && c <= C_DP_DEP_EXCLUSIVE);
+}
+// member whose cardinality defines "abstain" (inference.py:319,327,342,356,373,387)
+__host__ __device__ inline int nb_code_abstain_member(int c) { return (c == C_DP_LF_PROPENSITY || c == C_DP_DEP_EXCLUSIVE) ? 0 : 1; }
+
+// ----------------------------------------------------------------------------
+// Incidence-stream word formats.  A row (one variable) is a sequence of
+// incidences, one per (variable, factor) pair of the reference's vmap bucket(s):
+//   header | [featureValue lo, hi]? | member words | [extra]?
+// compact header (1 word):  code:5 | feat:1 | fixed:1 | arity:5 | wid:20
+// wide header (2 words):    wid:32 ; code:5 | feat:1 | fixed:1 | 0:1 | arity:24
+// member word: NEW variable id; members of *_CAT functions are (id, dense_equal_to) pairs.
+// A categorical variable's row has a MARK before each non-empty bucket:
+//   compact: code=31 | value:27         wide: value ; code=31
+// ----------------------------------------------------------------------------
+#define NB_COMPACT_MAX_ARITY 31
+#define NB_COMPACT_MAX_WID ((1u << 20) - 1)
+
+struct NbHdr {
+    int code, arity, feat, fixed;
+    uint32_t wid;  // MARK: bucket value
+};
+
+__host__ __device__ inline uint32_t nb_pack_compact(int code, int feat, int fixed, int arity, uint32_t wid)
+{
+    return ((uint32_t)code << 27) | ((uint32_t)feat << 26) | ((uint32_t)fixed << 25) |
+           ((uint32_t)arity << 20) | wid;
+}
+__host__ __device__ inline uint32_t nb_pack_wide_b(int code, int feat, int fixed, int arity)
+{
+    return ((uint32_t)code << 27) | ((uint32_t)feat << 26) | ((uint32_t)fixed << 25) | (uint32_t)arity;
+}
+__host__ __device__ inline uint32_t nb_pack_mark_compact(uint32_t value) { return ((uint32_t)C_MARK << 27) | value; }
+
+// number of 32-bit words an incidence occupies
+__host__ __device__ inline int nb_incidence_words(bool wide, int code, int arity, int feat)
+{
+    return (wide ? 2 : 1) + (feat ? 2 : 0) + arity * (nb_code_has_eq(code) ? 2 : 1) +
+           (nb_code_has_extra(code) ? 1 : 0);
+}
+
+// vmeta word per (new) variable id
+#define NB_META_CARD(m) ((int)((m) & 0xFFFFu))
+#define NB_META_EVID(m) ((int)(((m) >> 16) & 0xFu))
+#define NB_META_DTYPE(m) ((int)(((m) >> 20) & 1u))
+#define NB_META_VALID(m) ((int)(((m) >> 21) & 1u))
+__host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, int valid)
+{
+    return (uint32_t)card | ((uint32_t)(evid & 0xF) << 16) | ((uint32_t)dtype << 20) | ((uint32_t)valid << 21);
+}
+
+typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
+#define NB_MAX_CARD 255
+
+// ----------------------------------------------------------------------------
+// device graph
+// ----------------------------------------------------------------------------
+struct NbColorRange {
+    int32_t t_beg, t_end;  // thread-path rows [t_beg, t_end) in new ids (t_beg % 32 == 0)
+    int32_t w_beg, w_end;  // warp-path rows, as indices into the warp-row arrays
+    int64_t edges;         // bucket entries owned by this colour
+    int64_t learn_visits_max;  // max over weights of gradient visits in this colour (dataType-0 upper bound)
+};
+
+struct nb_graph {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // sizes
+    int64_t V = 0, F = 0, W = 0, NFMAP = 0, NVMAP = 0, NFI = 0;
+    int64_t n_edges = 0;        // sum of bucket lengths
+    int64_t Vn = 0;             // padded new-id space (thread rows first, then warp rows)
+    int64_t n_trows = 0;        // padded thread-row id space [0, n_trows)
+    int64_t n_wrows = 0;        // warp rows occupy new ids [n_trows, n_trows + n_wrows)
+    int64_t count_entries = 0;
+    int n_colors = 0;
+    bool wide = false;
+    bool has_unknown_func = false;
+    int64_t unknown_func_factor = -1;
+    int unknown_func_id = 0;
+    bool any_categorical = false;
+    int max_card = 2;
+    int64_t jp_rounds = 0;
+    int64_t device_bytes = 0;
+    int64_t launches = 0;
+    uint64_t epoch_counter = 0;
+    int warp_row_words = 1024;
+    int sigma_shift = 12;
+
+    // ---- raw CSR in original ids (kept for the colouring / rebuilds) ----
+    int8_t *d_v_evid = nullptr;      // [V]
+    int32_t *d_v_card = nullptr;     // [V]
+    int8_t *d_v_dtype = nullptr;     // [V]
+    int32_t *d_v_init = nullptr;     // [V]
+    int64_t *d_v_vtf = nullptr;      // [V]
+    int64_t *d_b_off = nullptr;      // [NVMAP] bucket offset into factor_index
+    int32_t *d_b_len = nullptr;      // [NVMAP]
+    int32_t *d_fi = nullptr;         // [NFI] factor ids
+    uint8_t *d_f_code = nullptr;     // [F]
+    int32_t *d_f_wid = nullptr;      // [F]
+    double *d_f_feat = nullptr;      // [F]
+    int32_t *d_f_arity = nullptr;    // [F]
+    int64_t *d_f_off = nullptr;      // [F]
+    int32_t *d_m_vid = nullptr;      // [NFMAP]
+    int32_t *d_m_eq = nullptr;       // [NFMAP] (only if any_categorical)
+    int64_t *d_gid = nullptr;        // [V] global ids or null
+
+    // ---- ordering ----
+    int32_t *d_color = nullptr;      // [V] original ids
+    int32_t *d_old2new = nullptr;    // [V]
+    int32_t *d_new2old = nullptr;    // [Vn], -1 for padding
+    uint32_t *d_rng_id = nullptr;    // [Vn] low 32 bits of the global id (Philox counter)
+
+    // ---- per new-id variable data ----
+    uint32_t *d_vmeta = nullptr;     // [Vn]
+    uint32_t *d_rowlen = nullptr;    // [Vn] words
+    nb_val_t *d_vinit = nullptr;     // [Vn]
+    uint32_t *d_cstart = nullptr;    // [Vn + 1] new-order count layout
+    int64_t *d_cstart_old = nullptr; // [V + 1] reference count layout
+
+    // ---- streams ----
+    int64_t *d_slice_ptr = nullptr;  // [n_trows/32 + 1] word offsets into d_twords
+    uint32_t *d_twords = nullptr;    // SELL-32 column-major thread-path stream
+    int64_t n_twords = 0;
+    int64_t *d_wrow_ptr = nullptr;   // [n_wrows + 1] word offsets into d_wwords
+    uint32_t *d_wwords = nullptr;    // contiguous warp-path rows
+    int64_t n_wwords = 0;
+    int64_t *d_inc_ptr = nullptr;    // [n_wrows + 1] offsets into d_inc
+    uint2 *d_inc = nullptr;          // per incidence of a warp row: (word offset in row, bucket value)
+    int64_t n_inc = 0;
+
+    // ---- state ----
+    nb_val_t *d_val[2] = {nullptr, nullptr};  // [Vn] chain 0 = free, 1 = evidence
+    int32_t *d_count = nullptr;      // [count_entries] new-order layout
+    double *d_weight = nullptr;      // [W]
+    uint8_t *d_wfixed = nullptr;     // [W]
+
+    // ---- learning scratch ----
+    float *d_grad = nullptr;         // [W]
+    uint32_t *d_nvis = nullptr;      // [W] visits
+    uint32_t *d_ntrunc = nullptr;    // [W] truncating visits (L1)
+    float *d_gpart = nullptr;        // block partials
+    uint32_t *d_npart = nullptr;
+    uint32_t *d_tpart = nullptr;
+    int64_t part_blocks = 0;
+    uint32_t *d_done = nullptr;
+
+    // scratch for host transfers
+    void *d_xfer = nullptr;
+    size_t xfer_bytes = 0;
+    void *h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+
+    std::vector<NbColorRange> colors;
+    std::vector<void *> allocs;
+};
+
+// device allocation tracked by the graph
+int nb_dev_alloc(nb_graph *g, void **p, size_t bytes, bool zero);
+template <class T>
+inline int nb_alloc(nb_graph *g, T **p, size_t n, bool zero = true)
+{
+    return nb_dev_alloc(g, (void **)p, n * sizeof(T), zero);
+}
+int nb_ensure_xfer(nb_graph *g, size_t bytes);
+int nb_ensure_pinned(nb_graph *g, size_t bytes);
+
+// build steps (nb_build.cu)
+int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);
+
+// sweeps (nb_sweep.cu / nb_learn.cu)
+int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed,
+                          uint64_t epoch);
+int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, int regularization,
+                 double reg_param, double truncation, int learn_non_evidence, uint64_t seed,
+                 int64_t batch_visits);
+int nb_run_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
+                      const int64_t *out_offsets, double *out, int64_t n_out);

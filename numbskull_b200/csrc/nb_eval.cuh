@@ -1,0 +1,419 @@
+// Device-side incidence-stream reader, factor evaluation and sampling helpers.
+#pragma once
+#include "nb_common.cuh"
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy
+// as 1, 2, 3", SC'11).  Counter = (variable global id, epoch, stream tag, 0),
+// key = 64-bit seed: every (variable, sweep, purpose) has its own stream, so
+// results do not depend on the launch geometry, the colouring or the partition.
+// ---------------------------------------------------------------------------
+struct NbPhilox {
+    uint32_t c[4];
+    uint32_t k[2];
+};
+
+__host__ __device__ inline void nb_philox_round(uint32_t *c, const uint32_t *k)
+{
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1];
+    c[1] = (uint32_t)p1;
+    c[3] = (uint32_t)p0;
+    c[0] = n0;
+    c[2] = n2;
+}
+
+__host__ __device__ inline void nb_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint64_t seed, uint32_t out[4])
+{
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        nb_philox_round(c, k);
+        k[0] += 0x9E3779B9u;
+        k[1] += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// 53-bit uniform in [0, 1) from two 32-bit words
+__host__ __device__ inline double nb_u53(uint32_t hi, uint32_t lo)
+{
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// stream tags (third counter word): purpose << 24 | block
+#define NB_TAG_FREE 0u
+#define NB_TAG_EVID 1u
+#define NB_TAG_TRUNC 2u
+
+// Uniform stream of one (variable, epoch, purpose): two doubles per Philox call.
+struct NbUniforms {
+    uint32_t id, epoch_lo, epoch_hi_tag;
+    uint64_t seed;
+    uint32_t block;
+    double spare;
+    bool has_spare;
+    __device__ NbUniforms(uint32_t id_, uint64_t epoch, uint32_t tag, uint64_t seed_)
+        : id(id_), epoch_lo((uint32_t)epoch), epoch_hi_tag((uint32_t)((epoch >> 32) & 0xFFFFu) | (tag << 24)),
+          seed(seed_), block(0), spare(0.0), has_spare(false) {}
+    __device__ double next()
+    {
+        if (has_spare) { has_spare = false; return spare; }
+        uint32_t r[4];
+        nb_philox4x32(id, epoch_lo, epoch_hi_tag, block++, seed, r);
+        spare = nb_u53(r[2], r[3]);
+        has_spare = true;
+        return nb_u53(r[0], r[1]);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Row cursor: word i of a row lives at p[i * stride] (stride 32 for the SELL-32
+// thread-path stream, 1 for contiguous warp-path rows).
+// ---------------------------------------------------------------------------
+struct NbRow {
+    const uint32_t *p;
+    int stride;
+    __device__ __forceinline__ uint32_t w(int i) const { return __ldg(p + (size_t)i * (size_t)stride); }
+};
+
+template <bool WIDE>
+__device__ __forceinline__ NbHdr nb_read_hdr(const NbRow &r, int pos)
+{
+    NbHdr h;
+    if (WIDE) {
+        uint32_t a = r.w(pos), b = r.w(pos + 1);
+        h.wid = a;
+        h.code = (int)(b >> 27);
+        h.feat = (int)((b >> 26) & 1u);
+        h.fixed = (int)((b >> 25) & 1u);
+        h.arity = (int)(b & 0xFFFFFFu);
+    } else {
+        uint32_t a = r.w(pos);
+        h.code = (int)(a >> 27);
+        if (h.code == C_MARK) {
+            h.wid = a & 0x7FFFFFFu;
+            h.feat = h.fixed = h.arity = 0;
+        } else {
+            h.feat = (int)((a >> 26) & 1u);
+            h.fixed = (int)((a >> 25) & 1u);
+            h.arity = (int)((a >> 20) & 31u);
+            h.wid = a & 0xFFFFFu;
+        }
+    }
+    return h;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ int nb_hdr_words() { return WIDE ? 2 : 1; }
+
+// words of the incidence that starts with header h (header included); MARK = header only
+template <bool WIDE>
+__device__ __forceinline__ int nb_inc_words(const NbHdr &h)
+{
+    if (h.code == C_MARK) return nb_hdr_words<WIDE>();
+    return nb_incidence_words(WIDE, h.code, h.arity, h.feat);
+}
+
+__device__ __forceinline__ double nb_read_feature(const NbRow &r, int pos)
+{
+    uint32_t lo = r.w(pos), hi = r.w(pos + 1);
+    return __hiloint2double((int)hi, (int)lo);
+}
+
+// ---------------------------------------------------------------------------
+// eval_factor (inference.py:149-413) on one incidence.  `mpos` is the position
+// of the first member word, `self` the new id of the sampled variable, `k` the
+// value it is forced to; everything else is read from `vals`.  Loops run to the
+// end instead of returning early so the member gathers are independent loads.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int nb_member(const NbRow &r, int mpos, int step, int j, uint32_t self,
+                                         int k, const nb_val_t *__restrict__ vals)
+{
+    uint32_t vid = r.w(mpos + j * step);
+    return vid == self ? k : (int)vals[vid];
+}
+
+__device__ inline double nb_eval_incidence(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
+                                           int k, const nb_val_t *__restrict__ vals)
+{
+    const int a = h.arity;
+    const int step = nb_code_has_eq(h.code) ? 2 : 1;
+    switch (h.code) {
+    case C_NOOP:
+        return 0.0;
+    case C_IMPLY_NATURAL: {  // inference.py:162-176 (the -1 branch is unreachable)
+        bool all = true;
+        for (int j = 0; j < a; j++) all &= nb_member(r, mpos, 1, j, self, k, vals) != 0;
+        return all ? 1.0 : 0.0;
+    }
+    case C_OR: {  // :177-183
+        bool any = false;
+        for (int j = 0; j < a; j++) any |= nb_member(r, mpos, 1, j, self, k, vals) == 1;
+        return any ? 1.0 : -1.0;
+    }
+    case C_AND:
+    case C_ISTRUE: {  // :193-200
+        bool all = true;
+        for (int j = 0; j < a; j++) all &= nb_member(r, mpos, 1, j, self, k, vals) != 0;
+        return all ? 1.0 : -1.0;
+    }
+    case C_EQUAL: {  // :184-192
+        if (a == 0) return 1.0;
+        int first = nb_member(r, mpos, 1, 0, self, k, vals);
+        bool eq = true;
+        for (int j = 1; j < a; j++) eq &= nb_member(r, mpos, 1, j, self, k, vals) == first;
+        return eq ? 1.0 : -1.0;
+    }
+    case C_LINEAR:
+    case C_RATIO:
+    case C_LOGICAL: {  // :201-231
+        if (a == 0) return h.code == C_RATIO ? 0.0 : 0.0;
+        int head = nb_member(r, mpos, 1, a - 1, self, k, vals);
+        int cnt = 0;
+        for (int j = 0; j < a - 1; j++) cnt += nb_member(r, mpos, 1, j, self, k, vals) == head;
+        if (h.code == C_LINEAR) return (double)cnt;
+        if (h.code == C_RATIO) return log((double)(1 + cnt));
+        return cnt > 0 ? 1.0 : 0.0;
+    }
+    case C_IMPLY_MLN:
+    case C_IMPLY_NATURAL_CAT:
+    case C_IMPLY_MLN_CAT: {  // :232-246, :266-295 -- head read through the aliased slot, as coded
+        if (a == 0) return 0.0;
+        bool body = true;
+        for (int j = 0; j < a - 1; j++) {
+            int x = nb_member(r, mpos, step, j, self, k, vals);
+            if (h.code == C_IMPLY_MLN) body &= x != 0;
+            else body &= x == (int)r.w(mpos + j * step + 1);
+        }
+        uint32_t last = r.w(mpos + (a - 1) * step);
+        uint32_t alias = r.w(mpos + a * step);
+        int head = last == self ? k : (alias == 0xFFFFFFFFu ? 0 : (int)vals[alias]);
+        if (h.code == C_IMPLY_MLN) return !body ? 1.0 : (head ? 1.0 : 0.0);
+        bool hit = head == (int)r.w(mpos + (a - 1) * step + 1);
+        if (h.code == C_IMPLY_NATURAL_CAT) return !body ? 0.0 : (hit ? 1.0 : -1.0);
+        return !body ? 1.0 : (hit ? 1.0 : 0.0);
+    }
+    case C_AND_CAT:
+    case C_EQUAL_CAT_CONST: {  // :251-258
+        bool all = true;
+        for (int j = 0; j < a; j++)
+            all &= nb_member(r, mpos, 2, j, self, k, vals) == (int)r.w(mpos + 2 * j + 1);
+        return all ? 1.0 : 0.0;
+    }
+    case C_OR_CAT: {  // :259-265
+        bool any = false;
+        for (int j = 0; j < a; j++)
+            any |= nb_member(r, mpos, 2, j, self, k, vals) == (int)r.w(mpos + 2 * j + 1);
+        return any ? 1.0 : -1.0;
+    }
+    case C_DP_CLASS_PRIOR:  // :301-305
+        return nb_member(r, mpos, 1, 0, self, k, vals) == 1 ? 1.0 : -1.0;
+    case C_DP_LF_PRIOR: {  // :306-315
+        int l = nb_member(r, mpos, 1, 0, self, k, vals);
+        return l == 2 ? -1.0 : (l == 0 ? 0.0 : 1.0);
+    }
+    case C_DP_LF_PROPENSITY: {  // :316-320
+        int abstain = (int)r.w(mpos + a);
+        return nb_member(r, mpos, 1, 0, self, k, vals) == abstain ? 0.0 : 1.0;
+    }
+    case C_DP_LF_ACCURACY:
+    case C_DP_LF_CLASS_PROPENSITY: {  // :321-347
+        int y = nb_member(r, mpos, 1, 0, self, k, vals);
+        int l = nb_member(r, mpos, 1, 1, self, k, vals);
+        int abstain = (int)r.w(mpos + a);
+        if (l == abstain) return 0.0;
+        if (h.code == C_DP_LF_ACCURACY) return y == l ? 1.0 : -1.0;
+        return y == 1 ? 1.0 : -1.0;
+    }
+    case C_DP_DEP_FIXING:
+    case C_DP_DEP_REINFORCING: {  // :348-381
+        int y = nb_member(r, mpos, 1, 0, self, k, vals);
+        int l1 = nb_member(r, mpos, 1, 1, self, k, vals);
+        int l2 = nb_member(r, mpos, 1, 2, self, k, vals);
+        int abstain = (int)r.w(mpos + a);
+        if (l1 == abstain) return l2 != 1 ? -1.0 : 0.0;
+        if (h.code == C_DP_DEP_FIXING)
+            return ((l1 == 0 && l2 == 1 && y == 1) || (l1 == 1 && l2 == 0 && y == 0)) ? 1.0 : 0.0;
+        return ((l1 == 0 && l2 == 0 && y == 0) || (l1 == 1 && l2 == 1 && y == 1)) ? 1.0 : 0.0;
+    }
+    case C_DP_DEP_EXCLUSIVE: {  // :382-388
+        int l1 = nb_member(r, mpos, 1, 0, self, k, vals);
+        int l2 = nb_member(r, mpos, 1, 1, self, k, vals);
+        int abstain = (int)r.w(mpos + a);
+        return (l1 == abstain || l2 == abstain) ? 0.0 : -1.0;
+    }
+    case C_DP_DEP_SIMILAR:  // :389-394
+        return nb_member(r, mpos, 1, 0, self, k, vals) == nb_member(r, mpos, 1, 1, self, k, vals) ? 1.0 : 0.0;
+    case C_UFO: {  // :399-405; a selector beyond the factor's own members yields 0
+        int v0 = nb_member(r, mpos, 1, 0, self, k, vals);
+        if (v0 == 0 || v0 - 1 >= a) return 0.0;
+        return (double)nb_member(r, mpos, 1, v0 - 1, self, k, vals);
+    }
+    default:
+        return 0.0;
+    }
+}
+
+// position of the first member word of the incidence whose header is at `pos`
+template <bool WIDE>
+__device__ __forceinline__ int nb_member_pos(const NbHdr &h, int pos)
+{
+    return pos + nb_hdr_words<WIDE>() + (h.feat ? 2 : 0);
+}
+
+// p += w * f without FMA contraction: bit-identical to the reference's
+// double-precision `p += weight * eval_factor(...)` when summed in bucket order.
+__device__ __forceinline__ double nb_acc(double p, double w, double f) { return __dadd_rn(p, __dmul_rn(w, f)); }
+
+// ---------------------------------------------------------------------------
+// Streaming categorical sampler: P(pick = k) = exp(e_k) / sum_j exp(e_j) in
+// one pass (weighted reservoir with a running maximum for stability).
+// ---------------------------------------------------------------------------
+struct NbReservoir {
+    double m, s;
+    int pick;
+    bool empty;
+    __device__ NbReservoir() : m(0.0), s(0.0), pick(0), empty(true) {}
+    // add `mult` items of energy e; returns true when the pick moved to this group
+    __device__ bool add(double e, double mult, double u)
+    {
+        if (empty) { m = e; s = mult; empty = false; return true; }
+        double t;
+        if (e > m) { s = s * exp(m - e) + mult; m = e; t = mult; }
+        else { t = mult * exp(e - m); s += t; }
+        return u * s < t;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// energies of a dataType-0 row for k < card <= 4, all candidate values in one
+// pass over the row (sum order = bucket order = the reference's)
+// ---------------------------------------------------------------------------
+template <bool WIDE>
+__device__ __forceinline__ void nb_row_energies4(const NbRow &r, int len, uint32_t self, int card,
+                                                 const nb_val_t *__restrict__ vals,
+                                                 const double *__restrict__ weight, double e[4])
+{
+    int pos = 0;
+    while (pos < len) {
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        int mpos = nb_member_pos<WIDE>(h, pos);
+        double w = __ldg(weight + h.wid);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < card) e[k] = nb_acc(e[k], w, nb_eval_incidence(r, h, mpos, self, k, vals));
+        pos += nb_inc_words<WIDE>(h);
+    }
+}
+
+// energy of value k of a dataType-0 row (any cardinality)
+template <bool WIDE>
+__device__ __forceinline__ double nb_row_energy_k(const NbRow &r, int len, uint32_t self, int k,
+                                                  const nb_val_t *__restrict__ vals,
+                                                  const double *__restrict__ weight)
+{
+    double e = 0.0;
+    int pos = 0;
+    while (pos < len) {
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        e = nb_acc(e, __ldg(weight + h.wid), nb_eval_incidence(r, h, nb_member_pos<WIDE>(h, pos), self, k, vals));
+        pos += nb_inc_words<WIDE>(h);
+    }
+    return e;
+}
+
+// j-th value (ascending) of a categorical row that has no bucket marker
+template <bool WIDE>
+__device__ inline int nb_nth_empty_value(const NbRow &r, int len, int j)
+{
+    int cur = 0, pos = 0;
+    while (pos < len) {
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        if (h.code == C_MARK) {
+            int gap = (int)h.wid - cur;
+            if (j < gap) return cur + j;
+            j -= gap;
+            cur = (int)h.wid + 1;
+        }
+        pos += nb_inc_words<WIDE>(h);
+    }
+    return cur + j;
+}
+
+// inverse-CDF draw over k < card <= 4 energies (draw_sample, inference.py:36-52,
+// with the maximum subtracted before exp -- mathematically identical)
+__device__ __forceinline__ int nb_draw_small(const double e[4], int card, double u)
+{
+    if (card == 2) {
+        double p0 = 1.0 / (1.0 + exp(e[1] - e[0]));
+        return u <= p0 ? 0 : 1;
+    }
+    double m = e[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < card) m = fmax(m, e[k]);
+    double z[4], tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { z[k] = k < card ? exp(e[k] - m) : 0.0; tot += z[k]; z[k] = tot; }
+    double t = u * tot;
+    int pick = card - 1;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) if (k < card && z[k] >= t) pick = k;
+    return pick;
+}
+
+// Sample one variable whose row is `r` (thread path, or any row walked by one thread).
+template <bool WIDE>
+__device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint32_t meta,
+                                    const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
+                                    NbUniforms &rng)
+{
+    const int card = NB_META_CARD(meta);
+    if (NB_META_DTYPE(meta) == 0) {
+        if (card <= 4) {
+            double e[4] = {0.0, 0.0, 0.0, 0.0};
+            nb_row_energies4<WIDE>(r, len, self, card, vals, weight, e);
+            return nb_draw_small(e, card, rng.next());
+        }
+        NbReservoir res;
+        for (int k = 0; k < card; k++)
+            if (res.add(nb_row_energy_k<WIDE>(r, len, self, k, vals, weight), 1.0, rng.next())) res.pick = k;
+        return res.pick;
+    }
+    // categorical: buckets in ascending value order, each introduced by a MARK
+    NbReservoir res;
+    int pos = 0, cur = -1, nonempty = 0;
+    double e = 0.0;
+    while (pos < len) {
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        if (h.code == C_MARK) {
+            if (cur >= 0 && res.add(e, 1.0, rng.next())) res.pick = cur;
+            cur = (int)h.wid;
+            e = 0.0;
+            nonempty++;
+        } else {
+            e = nb_acc(e, __ldg(weight + h.wid), nb_eval_incidence(r, h, nb_member_pos<WIDE>(h, pos), self, cur, vals));
+        }
+        pos += nb_inc_words<WIDE>(h);
+    }
+    if (cur >= 0 && res.add(e, 1.0, rng.next())) res.pick = cur;
+    int n_empty = card - nonempty;
+    if (n_empty > 0 && res.add(0.0, (double)n_empty, rng.next())) {
+        int j = min(n_empty - 1, (int)(rng.next() * (double)n_empty));
+        res.pick = nb_nth_empty_value<WIDE>(r, len, j);
+    }
+    return res.pick;
+}
+
+
+__device__ __forceinline__ double nb_warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+    return x;
+}
+

@@ -1,0 +1,266 @@
+// Host-side integer work of the drop-in boundary: error strings, the DeepDive
+// binary parsers and the (bit-exact) variable-to-factor index builder.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "nb_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void nb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *nb_last_error(void) { return g_err; }
+extern "C" int nb_abi_version(void) { return NB_ABI_VERSION; }
+
+extern "C" int nb_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        NB_FAIL(NB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// numbskull.py:219-227 (and :309-317): vtf_offset = running count of
+// VarToFactor records; Boolean (dataType 0) variables take one record,
+// categorical ones `cardinality`.
+// ---------------------------------------------------------------------------
+extern "C" int nb_assign_vtf_offsets(nb_variable_rec *variable, int64_t n_variable, int64_t *n_vtf)
+{
+    int64_t n = 0;
+    for (int64_t i = 0; i < n_variable; i++) {
+        variable[i].vtf_offset = n;
+        if (variable[i].dataType == 0) n += 1;
+        else {
+            if (variable[i].cardinality < 0) NB_FAIL(NB_ERR_INVALID, "variable %lld: negative cardinality", (long long)i);
+            n += variable[i].cardinality;
+        }
+    }
+    *n_vtf = n;
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// dataloading.py:16-81 compute_var_map.  Same four steps and the same outputs:
+// (1) bucket lengths from every fmap entry, (2) exclusive scan -> offsets,
+// (3) scatter factor ids in factor order skipping factors_to_skip, (4) per
+// bucket sort + unique with the length shrunk and the offsets left alone.
+// Because step 3 visits factors in increasing id, buckets are already sorted;
+// the sort is kept only for inputs whose fmap order violates that.
+// ---------------------------------------------------------------------------
+static inline int64_t bucket_of(const nb_variable_rec *variable, const nb_ftv_rec &m)
+{
+    const nb_variable_rec &v = variable[m.vid];
+    return v.vtf_offset + (v.dataType == 1 ? m.dense_equal_to : 0);
+}
+
+extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
+                                  const nb_factor_rec *factor, int64_t n_factor,
+                                  const nb_ftv_rec *fmap, int64_t n_fmap, nb_vtf_rec *vmap,
+                                  int64_t n_vmap, int64_t *factor_index, int64_t n_factor_index,
+                                  const uint8_t *domain_mask, const int64_t *factors_to_skip,
+                                  int64_t n_skip)
+{
+    for (int64_t i = 0; i < n_variable; i++) {
+        const nb_variable_rec &v = variable[i];
+        if (v.dataType == 0) continue;
+        if (v.vtf_offset < 0 || v.vtf_offset + v.cardinality > n_vmap)
+            NB_FAIL(NB_ERR_INVALID, "variable %lld: vmap range out of bounds", (long long)i);
+        if (domain_mask && domain_mask[i]) continue;
+        for (int64_t k = 0; k < v.cardinality; k++) vmap[v.vtf_offset + k].value = k;
+    }
+    for (int64_t j = 0; j < n_fmap; j++) {
+        const nb_ftv_rec &m = fmap[j];
+        if (m.vid < 0 || m.vid >= n_variable)
+            NB_FAIL(NB_ERR_INVALID, "fmap[%lld].vid = %lld out of range", (long long)j, (long long)m.vid);
+        const nb_variable_rec &v = variable[m.vid];
+        if (v.dataType == 1 && (m.dense_equal_to < 0 || m.dense_equal_to >= v.cardinality))
+            NB_FAIL(NB_ERR_INVALID, "fmap[%lld].dense_equal_to = %lld outside cardinality %lld",
+                    (long long)j, (long long)m.dense_equal_to, (long long)v.cardinality);
+        int64_t b = bucket_of(variable, m);
+        if (b < 0 || b >= n_vmap) NB_FAIL(NB_ERR_INVALID, "fmap[%lld]: bucket out of range", (long long)j);
+        vmap[b].factor_index_length += 1;
+    }
+    // The reference counts the entries of skipped factors too and then never
+    // writes their slots, which leaves stale ids in the buckets (and overruns
+    // factor_index).  Here skipped factors simply do not occupy bucket space;
+    // with an empty skip list the result is identical to the reference's.
+    for (int64_t s = 0; s < n_skip; s++) {
+        int64_t i = factors_to_skip[s];
+        if (i < 0 || i >= n_factor || (s > 0 && factors_to_skip[s - 1] >= i))
+            NB_FAIL(NB_ERR_INVALID, "factors_to_skip must be sorted, unique and in range");
+        const nb_factor_rec &f = factor[i];
+        if (f.ftv_offset < 0 || f.arity < 0 || f.ftv_offset + f.arity > n_fmap)
+            NB_FAIL(NB_ERR_INVALID, "factor %lld: fmap range out of bounds", (long long)i);
+        for (int64_t j = f.ftv_offset; j < f.ftv_offset + f.arity; j++)
+            vmap[bucket_of(variable, fmap[j])].factor_index_length -= 1;
+    }
+    int64_t last_len = 0, last_off = 0;
+    for (int64_t i = 0; i < n_vmap; i++) {
+        vmap[i].factor_index_offset = last_off + last_len;
+        last_len = vmap[i].factor_index_length;
+        last_off = vmap[i].factor_index_offset;
+    }
+    if (last_off + last_len > n_factor_index)
+        NB_FAIL(NB_ERR_INVALID,
+                "factor_index holds %lld entries but the buckets need %lld (the reference overruns "
+                "here when factors_to_skip is non-empty)",
+                (long long)n_factor_index, (long long)(last_off + last_len));
+
+    std::vector<int64_t> cursor((size_t)n_vmap);
+    for (int64_t i = 0; i < n_vmap; i++) cursor[(size_t)i] = vmap[i].factor_index_offset;
+    int64_t fts = 0;
+    for (int64_t i = 0; i < n_factor; i++) {
+        if (fts < n_skip && factors_to_skip[fts] == i) { fts++; continue; }
+        const nb_factor_rec &f = factor[i];
+        if (f.ftv_offset < 0 || f.arity < 0 || f.ftv_offset + f.arity > n_fmap)
+            NB_FAIL(NB_ERR_INVALID, "factor %lld: fmap range out of bounds", (long long)i);
+        for (int64_t j = f.ftv_offset; j < f.ftv_offset + f.arity; j++)
+            factor_index[cursor[(size_t)bucket_of(variable, fmap[j])]++] = i;
+    }
+    for (int64_t i = 0; i < n_vmap; i++) {
+        int64_t off = vmap[i].factor_index_offset, len = vmap[i].factor_index_length;
+        int64_t *b = factor_index + off;
+        if (!std::is_sorted(b, b + len)) std::sort(b, b + len);
+        int64_t n = 0, last = -1;
+        for (int64_t k = 0; k < len; k++) {
+            if (b[k] == last) continue;
+            last = b[k];
+            b[n++] = last;
+        }
+        vmap[i].factor_index_length = n;
+    }
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Big-endian readers for the DeepDive binary graph files.
+// ---------------------------------------------------------------------------
+static inline uint64_t be64(const uint8_t *p)
+{
+    uint64_t x;
+    memcpy(&x, p, 8);
+    return __builtin_bswap64(x);
+}
+static inline uint16_t be16(const uint8_t *p) { return (uint16_t)((p[0] << 8) | p[1]); }
+static inline double be_f64(const uint8_t *p)
+{
+    uint64_t x = be64(p);
+    double d;
+    memcpy(&d, &x, 8);
+    return d;
+}
+
+// dataloading.py:103-123: 17-byte records (int64 weightId, u8 isFixed, f64 initialValue)
+extern "C" int nb_load_weights(const uint8_t *data, int64_t n_bytes, int64_t n_weight, nb_weight_rec *out)
+{
+    if (n_bytes < 17 * n_weight) NB_FAIL(NB_ERR_INVALID, "graph.weights: %lld bytes < %lld records", (long long)n_bytes, (long long)n_weight);
+    for (int64_t i = 0; i < n_weight; i++) {
+        const uint8_t *r = data + 17 * i;
+        int64_t id = (int64_t)be64(r);
+        if (id < 0 || id >= n_weight) NB_FAIL(NB_ERR_INVALID, "graph.weights: weightId %lld out of range", (long long)id);
+        out[id].isFixed = r[8];
+        out[id].initialValue = be_f64(r + 9);
+    }
+    return NB_OK;
+}
+
+// dataloading.py:126-156: 27-byte records (int64 id, i8 isEvidence, int64 initialValue,
+// int16 dataType, int64 cardinality)
+extern "C" int nb_load_variables(const uint8_t *data, int64_t n_bytes, int64_t n_variable, nb_variable_rec *out)
+{
+    if (n_bytes < 27 * n_variable) NB_FAIL(NB_ERR_INVALID, "graph.variables: %lld bytes < %lld records", (long long)n_bytes, (long long)n_variable);
+    for (int64_t i = 0; i < n_variable; i++) {
+        const uint8_t *r = data + 27 * i;
+        int64_t id = (int64_t)be64(r);
+        if (id < 0 || id >= n_variable) NB_FAIL(NB_ERR_INVALID, "graph.variables: variableId %lld out of range", (long long)id);
+        out[id].isEvidence = (int8_t)r[8];
+        out[id].initialValue = (int64_t)be64(r + 9);
+        out[id].dataType = (int16_t)be16(r + 17);
+        out[id].cardinality = (int64_t)be64(r + 19);
+    }
+    return NB_OK;
+}
+
+// dataloading.py:159-187: (int64 variableId, int64 cardinality, cardinality x int64 value);
+// marks the variable, stores the (sorted) domain in vmap[].value and rewrites
+// initialValue to its dense index.
+extern "C" int nb_load_domains(const uint8_t *data, int64_t n_bytes, uint8_t *domain_mask, nb_vtf_rec *vmap,
+                               int64_t n_vmap, nb_variable_rec *variable, int64_t n_variable)
+{
+    int64_t idx = 0;
+    while (idx < n_bytes) {
+        if (idx + 16 > n_bytes) NB_FAIL(NB_ERR_INVALID, "graph.domains: truncated header");
+        int64_t vid = (int64_t)be64(data + idx);
+        int64_t card = (int64_t)be64(data + idx + 8);
+        idx += 16;
+        if (vid < 0 || vid >= n_variable) NB_FAIL(NB_ERR_INVALID, "graph.domains: variableId %lld out of range", (long long)vid);
+        if (card < 0 || idx + 8 * card > n_bytes || variable[vid].vtf_offset + card > n_vmap)
+            NB_FAIL(NB_ERR_INVALID, "graph.domains: bad cardinality for variable %lld", (long long)vid);
+        domain_mask[vid] = 1;
+        for (int64_t j = 0; j < card; j++) {
+            int64_t val = (int64_t)be64(data + idx);
+            idx += 8;
+            vmap[variable[vid].vtf_offset + j].value = val;
+            if (val == variable[vid].initialValue) variable[vid].initialValue = j;
+        }
+    }
+    return NB_OK;
+}
+
+// dataloading.py:190-237: sequential variable-length records
+// (int16 func, int64 arity, arity x (int64 vid, int64 value), int64 weightId, f64 feature);
+// values of variables with an explicit domain are translated to dense indices by
+// binary search over vmap[].value (np.searchsorted, side='left').
+extern "C" int nb_load_factors(const uint8_t *data, int64_t n_bytes, int64_t n_factor, nb_factor_rec *factor,
+                               nb_ftv_rec *fmap, int64_t n_fmap, const uint8_t *domain_mask,
+                               const nb_variable_rec *variable, int64_t n_variable, const nb_vtf_rec *vmap,
+                               int64_t n_vmap)
+{
+    int64_t idx = 0, e = 0;
+    for (int64_t i = 0; i < n_factor; i++) {
+        if (idx + 10 > n_bytes) NB_FAIL(NB_ERR_INVALID, "graph.factors: truncated at factor %lld", (long long)i);
+        factor[i].factorFunction = (int16_t)be16(data + idx);
+        int64_t arity = (int64_t)be64(data + idx + 2);
+        idx += 10;
+        if (arity < 0 || idx + 16 * arity + 16 > n_bytes || e + arity > n_fmap)
+            NB_FAIL(NB_ERR_INVALID, "graph.factors: factor %lld has bad arity %lld", (long long)i, (long long)arity);
+        factor[i].arity = arity;
+        factor[i].ftv_offset = e;
+        for (int64_t k = 0; k < arity; k++) {
+            int64_t vid = (int64_t)be64(data + idx);
+            int64_t val = (int64_t)be64(data + idx + 8);
+            idx += 16;
+            if (vid < 0 || vid >= n_variable) NB_FAIL(NB_ERR_INVALID, "graph.factors: factor %lld references variable %lld", (long long)i, (long long)vid);
+            if (domain_mask && domain_mask[vid]) {
+                int64_t s = variable[vid].vtf_offset, n = variable[vid].cardinality;
+                if (s < 0 || s + n > n_vmap) NB_FAIL(NB_ERR_INVALID, "graph.factors: domain of variable %lld out of range", (long long)vid);
+                int64_t lo = 0, hi = n;
+                while (lo < hi) {
+                    int64_t mid = (lo + hi) / 2;
+                    if (vmap[s + mid].value < val) lo = mid + 1; else hi = mid;
+                }
+                val = lo;
+            }
+            fmap[e + k].vid = vid;
+            fmap[e + k].dense_equal_to = val;
+        }
+        e += arity;
+        factor[i].weightId = (int64_t)be64(data + idx);
+        factor[i].featureValue = be_f64(data + idx + 8);
+        idx += 16;
+    }
+    return NB_OK;
+}

@@ -1,0 +1,464 @@
+// Weight learning sweep (learning.py:12-125 learnthread / sample_and_sgd).
+//
+// Per colour (split into mini-batches, see DESIGN.md "learning"): every owned
+// variable samples the evidence chain and the free chain in the same pass over
+// its row, then walks the row again for the per-factor gradient
+// (f(proposal | free) - f(evidence | evid)) * featureValue.  Gradients and visit
+// counts are REDUCED BY WEIGHT ID -- block-private shared-memory tables, flushed
+// to per-block partials that the last block sums in block order -- and the
+// SGD / L2-shrink / L1-truncated-gradient update is applied once per mini-batch.
+// Graphs whose weight table does not fit in shared memory accumulate into a
+// global table instead and apply with a separate kernel.
+#include <algorithm>
+#include <cmath>
+
+#include "nb_eval.cuh"
+
+#define NB_LEARN_SMEM_W 4096
+#define NB_LEARN_MAX_BLOCKS (148 * 2)
+#define NB_LEARN_THREADS 256
+
+struct LearnArgs {
+    const uint32_t *vmeta;
+    const uint32_t *rowlen;
+    const int64_t *slice_ptr;
+    const uint32_t *twords;
+    const int64_t *wrow_ptr;
+    const uint32_t *wwords;
+    const int64_t *inc_ptr;
+    const uint2 *inc;
+    const uint32_t *rng_id;
+    const nb_val_t *vinit;
+    nb_val_t *val_free;
+    nb_val_t *val_evid;
+    double *weight;
+    const uint8_t *wfixed;
+    int64_t n_trows;
+    int W;
+    uint64_t seed, epoch;
+    double step, reg_param, truncation;
+    int regularization, learn_non_evidence;
+    // reduction targets
+    float *g_grad;        // [W] global table (large-W path) or unused
+    uint32_t *g_cnt;      // [W]
+    float *p_grad;        // [blocks][W] per-block partials (shared-memory path)
+    uint32_t *p_cnt;
+    uint32_t *done;       // completion counter
+};
+
+// ---------------------------------------------------------------------------
+// closed-form application of n per-visit updates (learning.py:110-125):
+//   L2: each visit does w = w * s - step * g_i, s = 1 / (1 + reg_param * step),
+//       so n visits give w * s^n - step * sum_i g_i s^(n-i); the g_i are spread
+//       evenly over the batch, i.e. sum_i g_i s^(n-i) ~= G * (1 - s^n) / (n (1 - s)).
+//   L1: w -= step * G, then the m truncating visits' soft-threshold, merged.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double nb_apply_update(double w, double G, uint32_t cnt, int regularization, double step,
+                                                  double reg_param, double truncation)
+{
+    if (regularization == 2) {
+        if (cnt == 0) return w - step * G;
+        double s = 1.0 / (1.0 + reg_param * step);
+        double sn = pow(s, (double)cnt);
+        double geo = (s < 1.0) ? (1.0 - sn) / ((double)cnt * (1.0 - s)) : 1.0;
+        return w * sn - step * G * geo;
+    }
+    w -= step * G;
+    if (regularization == 1 && cnt > 0) {
+        double l1 = reg_param * step * truncation * (double)cnt;
+        w = w > 0.0 ? fmax(0.0, w - l1) : fmin(0.0, w + l1);
+    }
+    return w;
+}
+
+template <bool SMEM>
+struct GradSink {
+    float *grad;
+    uint32_t *cnt;
+    __device__ __forceinline__ void add(uint32_t wid, float g, uint32_t c)
+    {
+        if (g != 0.0f) atomicAdd(grad + wid, g);
+        if (c) atomicAdd(cnt + wid, c);
+    }
+};
+
+// second pass over a row: gradient of every visited incidence with a learnable weight
+template <bool WIDE, bool SMEM>
+__device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, uint32_t meta, int ev, int prop,
+                                       const LearnArgs &a, uint32_t cnt_inc, GradSink<SMEM> &sink,
+                                       int first_inc, int inc_stride, const uint2 *inc_list, int n_inc)
+{
+    const bool cat = NB_META_DTYPE(meta) == 1;
+    if (inc_list == nullptr) {
+        int pos = 0, cur = -1;
+        while (pos < len) {
+            NbHdr h = nb_read_hdr<WIDE>(r, pos);
+            if (h.code == C_MARK) cur = (int)h.wid;
+            else if (!h.fixed && (!cat || cur == ev || cur == prop)) {
+                int mpos = nb_member_pos<WIDE>(h, pos);
+                double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
+                double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
+                double feat = h.feat ? nb_read_feature(r, pos + nb_hdr_words<WIDE>()) : 1.0;
+                sink.add(h.wid, (float)((f1 - f0) * feat), cnt_inc);
+            }
+            pos += nb_inc_words<WIDE>(h);
+        }
+    } else {
+        for (int i = first_inc; i < n_inc; i += inc_stride) {
+            uint2 ent = inc_list[i];
+            int pos = (int)ent.x, cur = (int)ent.y;
+            NbHdr h = nb_read_hdr<WIDE>(r, pos);
+            if (h.fixed || (cat && cur != ev && cur != prop)) continue;
+            int mpos = nb_member_pos<WIDE>(h, pos);
+            double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
+            double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
+            double feat = h.feat ? nb_read_feature(r, pos + nb_hdr_words<WIDE>()) : 1.0;
+            sink.add(h.wid, (float)((f1 - f0) * feat), cnt_inc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// block epilogue of the shared-memory path: flush the block's table, and let
+// the last block to finish sum the partials in block order and apply the update
+// ---------------------------------------------------------------------------
+__device__ inline void nb_flush_and_apply(const LearnArgs &a, float *s_grad, uint32_t *s_cnt)
+{
+    __shared__ bool s_last;
+    __syncthreads();
+    float *pg = a.p_grad + (size_t)blockIdx.x * a.W;
+    uint32_t *pc = a.p_cnt + (size_t)blockIdx.x * a.W;
+    for (int w = threadIdx.x; w < a.W; w += blockDim.x) { pg[w] = s_grad[w]; pc[w] = s_cnt[w]; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int w = threadIdx.x; w < a.W; w += blockDim.x) {
+        if (a.wfixed[w]) continue;
+        double G = 0.0;
+        uint32_t n = 0;
+        for (unsigned b = 0; b < gridDim.x; b++) {
+            G += (double)__ldcg(a.p_grad + (size_t)b * a.W + w);
+            n += __ldcg(a.p_cnt + (size_t)b * a.W + w);
+        }
+        if (G != 0.0 || n != 0)
+            a.weight[w] = nb_apply_update(a.weight[w], G, n, a.regularization, a.step, a.reg_param, a.truncation);
+    }
+    if (threadIdx.x == 0) *a.done = 0;
+}
+
+// ---------------------------------------------------------------------------
+// thread path
+// ---------------------------------------------------------------------------
+template <bool WIDE, bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, int beg, int end)
+{
+    extern __shared__ unsigned char s_raw[];
+    float *s_grad = (float *)s_raw;
+    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(float) * (size_t)(SMEM ? a.W : 0));
+    if (SMEM) {
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0.0f; s_cnt[w] = 0u; }
+        __syncthreads();
+    }
+    GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
+
+    for (int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; nid < end;
+         nid += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t meta = a.vmeta[nid];
+        const int evid = NB_META_EVID(meta);
+        if (!NB_META_VALID(meta) || evid == 4) continue;                   // learning.py:24-26
+        NbRow r{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32};
+        const int len = (int)a.rowlen[nid];
+        const uint32_t self = (uint32_t)nid, id = a.rng_id[nid];
+        int ev;
+        if (evid != 1) {                                                    // :53-57
+            NbUniforms rng(id, a.epoch, NB_TAG_EVID, a.seed);
+            ev = nb_sample_row<WIDE>(r, len, self, meta, a.val_evid, a.weight, rng);
+        } else {
+            ev = (int)a.vinit[nid];                                         // :60-61
+        }
+        a.val_evid[nid] = (nb_val_t)ev;                                     // :63
+        NbUniforms rng(id, a.epoch, NB_TAG_FREE, a.seed);
+        int prop = nb_sample_row<WIDE>(r, len, self, meta, a.val_free, a.weight, rng);   // :65-67
+        a.val_free[nid] = (nb_val_t)prop;                                   // :69
+        if (!a.learn_non_evidence && evid != 1) continue;                   // :70-71
+        uint32_t cnt_inc = 1;
+        if (a.regularization == 1) {                                        // :90
+            NbUniforms tr(id, a.epoch, NB_TAG_TRUNC, a.seed);
+            cnt_inc = tr.next() < 1.0 / a.truncation ? 1u : 0u;
+        } else if (a.regularization != 2) cnt_inc = 0;
+        nb_row_gradient<WIDE, SMEM>(r, len, self, meta, ev, prop, a, cnt_inc, sink, 0, 1, nullptr, 0);
+    }
+    if (SMEM) nb_flush_and_apply(a, s_grad, s_cnt);
+}
+
+// ---------------------------------------------------------------------------
+// warp path: one long row per warp
+// ---------------------------------------------------------------------------
+// per-value energies of a warp row into e[4] (dataType 0, card <= 4) or the shared array se
+template <bool WIDE>
+__device__ inline void nb_warp_energies_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
+                                          const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
+                                          double e[4], double *se)
+{
+    const int lane = threadIdx.x & 31, card = NB_META_CARD(meta);
+    const bool small = NB_META_DTYPE(meta) == 0 && card <= 4;
+    if (!small) {
+        for (int k = lane; k < card; k += 32) se[k] = 0.0;
+        __syncwarp();
+    }
+    for (int i = lane; i < n_inc; i += 32) {
+        uint2 ent = inc[i];
+        int pos = (int)ent.x;
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        int mpos = nb_member_pos<WIDE>(h, pos);
+        double w = weight[h.wid];
+        if (small) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < card) e[k] += w * nb_eval_incidence(r, h, mpos, self, k, vals);
+        } else if (NB_META_DTYPE(meta) == 0) {
+            for (int k = 0; k < card; k++) atomicAdd(&se[k], w * nb_eval_incidence(r, h, mpos, self, k, vals));
+        } else {
+            atomicAdd(&se[(int)ent.y], w * nb_eval_incidence(r, h, mpos, self, (int)ent.y, vals));
+        }
+    }
+    if (small) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] = nb_warp_sum(e[k]);
+    } else {
+        __syncwarp();
+    }
+}
+
+template <bool WIDE>
+__device__ inline int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
+                                       const nb_val_t *__restrict__ vals, const double *__restrict__ weight, double *se,
+                                       NbUniforms &rng)
+{
+    const int card = NB_META_CARD(meta);
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    nb_warp_energies_l<WIDE>(r, inc, n_inc, self, meta, vals, weight, e, se);
+    int k;
+    if (NB_META_DTYPE(meta) == 0 && card <= 4) k = nb_draw_small(e, card, rng.next());
+    else {
+        NbReservoir res;
+        for (int j = 0; j < card; j++)
+            if (res.add(se[j], 1.0, rng.next())) res.pick = j;
+        k = res.pick;
+    }
+    __syncwarp();
+    return k;
+}
+
+#define NB_LWARPS (NB_LEARN_THREADS / 32)
+
+template <bool WIDE, bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, int wbeg, int wend)
+{
+    extern __shared__ unsigned char s_raw[];
+    __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
+    float *s_grad = (float *)s_raw;
+    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(float) * (size_t)(SMEM ? a.W : 0));
+    if (SMEM) {
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0.0f; s_cnt[w] = 0u; }
+        __syncthreads();
+    }
+    GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int64_t wr = (int64_t)wbeg + blockIdx.x * (int64_t)NB_LWARPS + warp; wr < wend;
+         wr += (int64_t)gridDim.x * NB_LWARPS) {
+        const int64_t nid = a.n_trows + wr;
+        const uint32_t meta = a.vmeta[nid];
+        const int evid = NB_META_EVID(meta);
+        if (!NB_META_VALID(meta) || evid == 4) continue;
+        NbRow r{a.wwords + a.wrow_ptr[wr], 1};
+        const uint2 *inc = a.inc + a.inc_ptr[wr];
+        const int n_inc = (int)(a.inc_ptr[wr + 1] - a.inc_ptr[wr]);
+        const uint32_t self = (uint32_t)nid, id = a.rng_id[nid];
+        int ev;
+        if (evid != 1) {
+            NbUniforms rng(id, a.epoch, NB_TAG_EVID, a.seed);
+            ev = nb_warp_sample_l<WIDE>(r, inc, n_inc, self, meta, a.val_evid, a.weight, s_e[warp], rng);
+        } else {
+            ev = (int)a.vinit[nid];
+        }
+        NbUniforms rng(id, a.epoch, NB_TAG_FREE, a.seed);
+        int prop = nb_warp_sample_l<WIDE>(r, inc, n_inc, self, meta, a.val_free, a.weight, s_e[warp], rng);
+        if (lane == 0) { a.val_evid[nid] = (nb_val_t)ev; a.val_free[nid] = (nb_val_t)prop; }
+        if (!a.learn_non_evidence && evid != 1) continue;
+        uint32_t cnt_inc = 1;
+        if (a.regularization == 1) {
+            NbUniforms tr(id, a.epoch, NB_TAG_TRUNC, a.seed);
+            cnt_inc = tr.next() < 1.0 / a.truncation ? 1u : 0u;
+        } else if (a.regularization != 2) cnt_inc = 0;
+        nb_row_gradient<WIDE, SMEM>(r, 0, self, meta, ev, prop, a, cnt_inc, sink, lane, 32, inc, n_inc);
+    }
+    if (SMEM) nb_flush_and_apply(a, s_grad, s_cnt);
+}
+
+// large-W path: apply the global table and clear it
+__global__ void k_apply_global(LearnArgs a)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.W) return;
+    float G = a.g_grad[w];
+    uint32_t n = a.g_cnt[w];
+    if (G == 0.0f && n == 0u) return;
+    a.g_grad[w] = 0.0f;
+    a.g_cnt[w] = 0u;
+    if (a.wfixed[w]) return;
+    a.weight[w] = nb_apply_update(a.weight[w], (double)G, n, a.regularization, a.step, a.reg_param, a.truncation);
+}
+
+// visits per weight of one colour (upper bound: every incidence of a learnable row)
+template <bool WIDE>
+__global__ void k_visit_histogram(LearnArgs a, int beg, int end, int wbeg, int wend, uint32_t *hist)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t nt = end - beg, nw = wend - wbeg;
+    if (i >= nt + nw) return;
+    int64_t nid = i < nt ? beg + i : a.n_trows + wbeg + (i - nt);
+    const uint32_t meta = a.vmeta[nid];
+    const int evid = NB_META_EVID(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;
+    if (!a.learn_non_evidence && evid != 1) return;
+    NbRow r = nid < a.n_trows ? NbRow{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32}
+                              : NbRow{a.wwords + a.wrow_ptr[nid - a.n_trows], 1};
+    int len = (int)a.rowlen[nid], pos = 0;
+    while (pos < len) {
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        if (h.code != C_MARK && !h.fixed) atomicAdd(hist + h.wid, 1u);
+        pos += nb_inc_words<WIDE>(h);
+    }
+}
+
+__global__ void k_max_u32(const uint32_t *x, int n, uint32_t *out)
+{
+    uint32_t m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, x[i]);
+    atomicMax(out, m);
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+static LearnArgs learn_args(nb_graph *g)
+{
+    LearnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vmeta = g->d_vmeta; a.rowlen = g->d_rowlen; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
+    a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
+    a.rng_id = g->d_rng_id; a.vinit = g->d_vinit; a.val_free = g->d_val[0]; a.val_evid = g->d_val[1];
+    a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
+    a.g_grad = g->d_grad; a.g_cnt = g->d_nvis; a.p_grad = g->d_gpart; a.p_cnt = g->d_npart; a.done = g->d_done;
+    return a;
+}
+
+static int ensure_learn_buffers(nb_graph *g, bool smem)
+{
+    if (!g->d_done) NB_TRY(nb_alloc(g, &g->d_done, 4));
+    if (!g->d_grad) {
+        NB_TRY(nb_alloc(g, &g->d_grad, (size_t)g->W));
+        NB_TRY(nb_alloc(g, &g->d_nvis, (size_t)g->W));
+    }
+    if (smem && !g->d_gpart) {
+        NB_TRY(nb_alloc(g, &g->d_gpart, (size_t)NB_LEARN_MAX_BLOCKS * (size_t)g->W));
+        NB_TRY(nb_alloc(g, &g->d_npart, (size_t)NB_LEARN_MAX_BLOCKS * (size_t)g->W));
+    }
+    return NB_OK;
+}
+
+// max over weights of the gradient visits one sweep of colour c can make
+static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &out)
+{
+    out.assign((size_t)g->n_colors, 0);
+    uint32_t *d_max;
+    NB_TRY(nb_alloc(g, &d_max, 1));
+    for (int c = 0; c < g->n_colors; c++) {
+        const NbColorRange &cr = g->colors[(size_t)c];
+        int64_t n = (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
+        if (n == 0) continue;
+        NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
+        NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
+        unsigned grid = (unsigned)((n + 255) / 256);
+        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        k_max_u32<<<64, 256, 0, g->stream>>>(g->d_nvis, (int)g->W, d_max);
+        uint32_t m = 0;
+        NB_CUDA(cudaMemcpyAsync(&m, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        out[(size_t)c] = m;
+    }
+    NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
+    return NB_OK;
+}
+
+template <bool WIDE, bool SMEM>
+static int launch_learn_range(nb_graph *g, const LearnArgs &a, int tb, int te, int wb, int we)
+{
+    size_t smem = SMEM ? (size_t)g->W * 8 : 0;
+    if (te > tb) {
+        int64_t need = ((int64_t)(te - tb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
+        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
+        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, tb, te);
+        g->launches++;
+        if (!SMEM) { k_apply_global<<<(unsigned)((g->W + 255) / 256), 256, 0, g->stream>>>(a); g->launches++; }
+    }
+    if (we > wb) {
+        int64_t need = ((int64_t)(we - wb) + NB_LWARPS - 1) / NB_LWARPS;
+        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
+        k_learn_warp<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, wb, we);
+        g->launches++;
+        if (!SMEM) { k_apply_global<<<(unsigned)((g->W + 255) / 256), 256, 0, g->stream>>>(a); g->launches++; }
+    }
+    return NB_OK;
+}
+
+int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, int regularization, double reg_param,
+                 double truncation, int learn_non_evidence, uint64_t seed, int64_t batch_visits)
+{
+    if (n_epochs <= 0) return NB_OK;
+    const bool smem = g->W <= NB_LEARN_SMEM_W;
+    NB_TRY(ensure_learn_buffers(g, smem));
+    LearnArgs a = learn_args(g);
+    a.seed = seed; a.reg_param = reg_param; a.truncation = truncation;
+    a.regularization = regularization; a.learn_non_evidence = learn_non_evidence;
+
+    std::vector<int64_t> vmax;
+    NB_TRY(color_visit_bounds(g, a, vmax));
+
+    double step = *stepsize;
+    for (int64_t ep = 0; ep < n_epochs; ep++) {
+        a.step = step;
+        a.epoch = g->epoch_counter++;
+        // mini-batch size: at most `bv` visits of any one weight between two applications
+        int64_t bv = batch_visits > 0 ? batch_visits
+                                      : (int64_t)std::max(1.0, std::floor(0.5 / std::max(std::fabs(step), 1e-12)));
+        for (int c = 0; c < g->n_colors; c++) {
+            const NbColorRange &cr = g->colors[(size_t)c];
+            int64_t chunks = std::max<int64_t>(1, (vmax[(size_t)c] + bv - 1) / bv);
+            int64_t nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
+            chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(nt, nw)));
+            for (int64_t k = 0; k < chunks; k++) {
+                int tb = cr.t_beg + (int)((nt * k / chunks) & ~31ll), te = cr.t_beg + (int)((nt * (k + 1) / chunks) & ~31ll);
+                if (k == chunks - 1) te = cr.t_end;
+                int wb = cr.w_beg + (int)(nw * k / chunks), we = cr.w_beg + (int)(nw * (k + 1) / chunks);
+                if (g->wide) {
+                    if (smem) NB_TRY((launch_learn_range<true, true>(g, a, tb, te, wb, we)));
+                    else NB_TRY((launch_learn_range<true, false>(g, a, tb, te, wb, we)));
+                } else {
+                    if (smem) NB_TRY((launch_learn_range<false, true>(g, a, tb, te, wb, we)));
+                    else NB_TRY((launch_learn_range<false, false>(g, a, tb, te, wb, we)));
+                }
+            }
+        }
+        NB_CUDA(cudaGetLastError());
+        step *= decay;   // factorgraph.py:206
+    }
+    *stepsize = step;
+    return NB_OK;
+}

@@ -1,0 +1,228 @@
+// Chromatic Gibbs sweep (inference.py:10-71 gibbsthread / draw_sample /
+// potential) and the potential() parity hook.
+//
+// One launch per (colour, row class).  Thread path: one variable per thread,
+// rows read from the SELL-32 stream so that the 32 lanes of a warp load 32
+// consecutive words at every step.  Warp path: one long row per warp, lanes
+// stride over its incidences and the per-value energies are reduced with
+// shuffles (shared memory for categorical rows).
+#include "nb_eval.cuh"
+
+struct SweepArgs {
+    const uint32_t *vmeta;
+    const uint32_t *rowlen;
+    const int64_t *slice_ptr;
+    const uint32_t *twords;
+    const int64_t *wrow_ptr;
+    const uint32_t *wwords;
+    const int64_t *inc_ptr;
+    const uint2 *inc;
+    const uint32_t *rng_id;
+    const uint32_t *cstart;
+    int32_t *count;
+    nb_val_t *val;
+    const double *weight;
+    int64_t n_trows;
+    uint64_t seed, epoch;
+    int burnin, sample_evidence;
+};
+
+static SweepArgs sweep_args(nb_graph *g, int chain, int burnin, int sample_evidence, uint64_t seed, uint64_t epoch)
+{
+    SweepArgs a;
+    a.vmeta = g->d_vmeta; a.rowlen = g->d_rowlen; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
+    a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
+    a.rng_id = g->d_rng_id; a.cstart = g->d_cstart; a.count = g->d_count; a.val = g->d_val[chain];
+    a.weight = g->d_weight; a.n_trows = g->n_trows; a.seed = seed; a.epoch = epoch;
+    a.burnin = burnin; a.sample_evidence = sample_evidence;
+    return a;
+}
+
+__device__ __forceinline__ void nb_tally(const SweepArgs &a, int64_t nid, int card, int k)
+{
+    if (a.burnin) return;
+    uint32_t cs = a.cstart[nid];
+    if (card == 2) a.count[cs] += k;       // inference.py:30-31
+    else a.count[cs + k] += 1;             // :32-33
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int end)
+{
+    int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (nid >= end) return;
+    const uint32_t meta = a.vmeta[nid];
+    const int evid = NB_META_EVID(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
+    if (!(evid == 0 || a.sample_evidence)) return;          // :24
+    NbRow r{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32};
+    NbUniforms rng(a.rng_id[nid], a.epoch, NB_TAG_FREE, a.seed);
+    int k = nb_sample_row<WIDE>(r, (int)a.rowlen[nid], (uint32_t)nid, meta, a.val, a.weight, rng);
+    a.val[nid] = (nb_val_t)k;
+    nb_tally(a, nid, NB_META_CARD(meta), k);
+}
+
+// ---------------------------------------------------------------------------
+// warp path
+// ---------------------------------------------------------------------------
+#define NB_WARPS_PER_BLOCK 8
+
+// Energies of every value of the warp row `wr`, lanes striding over incidences.
+// dataType 0, card <= 4: returned in e[] on all lanes.  Otherwise the per-value
+// energies land in the warp's shared array se[0..card).
+template <bool WIDE>
+__device__ inline void nb_warp_row_energies(const uint32_t *__restrict__ wwords, const int64_t *__restrict__ wrow_ptr,
+                                            const int64_t *__restrict__ inc_ptr, const uint2 *__restrict__ inc,
+                                            int64_t wr, uint32_t self, uint32_t meta,
+                                            const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
+                                            double e[4], double *se)
+{
+    const int lane = threadIdx.x & 31;
+    const int card = NB_META_CARD(meta);
+    const bool small = NB_META_DTYPE(meta) == 0 && card <= 4;
+    NbRow r{wwords + wrow_ptr[wr], 1};
+    const int64_t i0 = inc_ptr[wr], i1 = inc_ptr[wr + 1];
+    if (!small) {
+        for (int k = lane; k < card; k += 32) se[k] = 0.0;
+        __syncwarp();
+    }
+    for (int64_t i = i0 + lane; i < i1; i += 32) {
+        uint2 ent = inc[i];
+        int pos = (int)ent.x;
+        NbHdr h = nb_read_hdr<WIDE>(r, pos);
+        int mpos = nb_member_pos<WIDE>(h, pos);
+        double w = __ldg(weight + h.wid);
+        if (small) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < card) e[k] += w * nb_eval_incidence(r, h, mpos, self, k, vals);
+        } else if (NB_META_DTYPE(meta) == 0) {
+            for (int k = 0; k < card; k++) atomicAdd(&se[k], w * nb_eval_incidence(r, h, mpos, self, k, vals));
+        } else {
+            int k = (int)ent.y;
+            atomicAdd(&se[k], w * nb_eval_incidence(r, h, mpos, self, k, vals));
+        }
+    }
+    if (small) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[k] = nb_warp_sum(e[k]);
+    } else {
+        __syncwarp();
+    }
+}
+
+// draw from the shared per-value energies (uniform on all lanes; lane 0's result is used)
+__device__ inline int nb_draw_shared(const double *se, int card, NbUniforms &rng)
+{
+    NbReservoir res;
+    for (int k = 0; k < card; k++)
+        if (res.add(se[k], 1.0, rng.next())) res.pick = k;
+    return res.pick;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp(SweepArgs a, int wbeg, int wend)
+{
+    __shared__ double s_e[NB_WARPS_PER_BLOCK][NB_MAX_CARD + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t wr = (int64_t)wbeg + blockIdx.x * (int64_t)NB_WARPS_PER_BLOCK + warp;
+    if (wr >= wend) return;
+    const int64_t nid = a.n_trows + wr;
+    const uint32_t meta = a.vmeta[nid];
+    const int evid = NB_META_EVID(meta), card = NB_META_CARD(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;
+    if (!(evid == 0 || a.sample_evidence)) return;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    nb_warp_row_energies<WIDE>(a.wwords, a.wrow_ptr, a.inc_ptr, a.inc, wr, (uint32_t)nid, meta, a.val, a.weight, e, s_e[warp]);
+    NbUniforms rng(a.rng_id[nid], a.epoch, NB_TAG_FREE, a.seed);
+    int k;
+    if (NB_META_DTYPE(meta) == 0 && card <= 4) k = nb_draw_small(e, card, rng.next());
+    else k = nb_draw_shared(s_e[warp], card, rng);
+    if (lane == 0) {
+        a.val[nid] = (nb_val_t)k;
+        nb_tally(a, nid, card, k);
+    }
+}
+
+int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed, uint64_t epoch)
+{
+    if (color < 0 || color >= g->n_colors) NB_FAIL(NB_ERR_INVALID, "colour %d out of range [0, %d)", color, g->n_colors);
+    const NbColorRange &c = g->colors[(size_t)color];
+    SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
+    if (c.t_end > c.t_beg) {
+        unsigned grid = (unsigned)((c.t_end - c.t_beg + 255) / 256);
+        if (g->wide) k_gibbs_thread<true><<<grid, 256, 0, g->stream>>>(a, c.t_beg, c.t_end);
+        else k_gibbs_thread<false><<<grid, 256, 0, g->stream>>>(a, c.t_beg, c.t_end);
+        g->launches++;
+    }
+    if (c.w_end > c.w_beg) {
+        unsigned grid = (unsigned)((c.w_end - c.w_beg + NB_WARPS_PER_BLOCK - 1) / NB_WARPS_PER_BLOCK);
+        if (g->wide) k_gibbs_warp<true><<<grid, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, c.w_beg, c.w_end);
+        else k_gibbs_warp<false><<<grid, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, c.w_beg, c.w_end);
+        g->launches++;
+    }
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// potential() parity hook (inference.py:55-71): one thread per requested
+// variable walks its row once per value, summing in bucket order.
+// ---------------------------------------------------------------------------
+template <bool WIDE>
+__global__ void k_potentials(SweepArgs a, const int32_t *old2new, const int64_t *var_ids, int64_t n,
+                             const int64_t *out_offsets, double *out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t nid = old2new[var_ids[i]];
+    const uint32_t meta = a.vmeta[nid];
+    const int card = NB_META_CARD(meta);
+    const int len = (int)a.rowlen[nid];
+    NbRow r = nid < a.n_trows ? NbRow{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32}
+                              : NbRow{a.wwords + a.wrow_ptr[nid - a.n_trows], 1};
+    double *o = out + out_offsets[i];
+    for (int k = 0; k < card; k++) {
+        double e = 0.0;
+        if (NB_META_DTYPE(meta) == 0) {
+            e = nb_row_energy_k<WIDE>(r, len, (uint32_t)nid, k, a.val, a.weight);
+        } else {
+            int pos = 0, cur = -1;
+            while (pos < len) {
+                NbHdr h = nb_read_hdr<WIDE>(r, pos);
+                if (h.code == C_MARK) cur = (int)h.wid;
+                else if (cur == k)
+                    e = nb_acc(e, a.weight[h.wid], nb_eval_incidence(r, h, nb_member_pos<WIDE>(h, pos), (uint32_t)nid, k, a.val));
+                pos += nb_inc_words<WIDE>(h);
+            }
+        }
+        o[k] = e;
+    }
+}
+
+int nb_run_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n, const int64_t *out_offsets,
+                      double *out, int64_t n_out)
+{
+    if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    if (n == 0) return NB_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (var_ids[i] < 0 || var_ids[i] >= g->V) NB_FAIL(NB_ERR_INVALID, "variable id %lld out of range", (long long)var_ids[i]);
+    int64_t *d_ids, *d_off;
+    double *d_out;
+    NB_CUDA(cudaMalloc(&d_ids, (size_t)n * 8));
+    NB_CUDA(cudaMalloc(&d_off, (size_t)n * 8));
+    NB_CUDA(cudaMalloc(&d_out, (size_t)std::max<int64_t>(n_out, 1) * 8));
+    cudaMemcpyAsync(d_ids, var_ids, (size_t)n * 8, cudaMemcpyHostToDevice, g->stream);
+    cudaMemcpyAsync(d_off, out_offsets, (size_t)n * 8, cudaMemcpyHostToDevice, g->stream);
+    cudaMemsetAsync(d_out, 0, (size_t)n_out * 8, g->stream);
+    SweepArgs a = sweep_args(g, chain, 1, 1, 0, 0);
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (g->wide) k_potentials<true><<<grid, 128, 0, g->stream>>>(a, g->d_old2new, d_ids, n, d_off, d_out);
+    else k_potentials<false><<<grid, 128, 0, g->stream>>>(a, g->d_old2new, d_ids, n, d_off, d_out);
+    cudaMemcpyAsync(out, d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost, g->stream);
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_ids); cudaFree(d_off); cudaFree(d_out);
+    NB_CUDA(e);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}

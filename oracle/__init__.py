@@ -5,3 +5,4 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 package ``numbskull_b200`` never does.
 """
 from .oracle import OracleGraph, build, lib, exact_marginals, compute_var_map  # noqa: F401
+from . import coloring  # noqa: F401,E402

@@ -1,0 +1,58 @@
+"""CPU checker for the GPU Jones-Plassmann colouring (TEST INFRASTRUCTURE ONLY).
+
+Jones-Plassmann with "smallest free colour" and fixed priorities is
+schedule-independent: it equals a sequential greedy colouring that visits the
+variables in decreasing priority.  This module computes that greedy colouring
+with the same priority function as ``csrc/nb_build.cu`` (``nb_jp_priority``)
+so the device result can be checked bit-exactly, and verifies validity (no two
+same-colour variables share a factor)."""
+import numpy as np
+
+M64 = (1 << 64) - 1
+
+
+def _mix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+    return x ^ (x >> 31)
+
+
+def jp_priority(gid, seed):
+    return (_mix64(gid ^ _mix64(seed)) & 0xFFFFFFFF00000000) | (gid & 0xFFFFFFFF)
+
+
+def neighbours(variable, factor, fmap):
+    nvar = len(variable)
+    adj = [set() for _ in range(nvar)]
+    owned = variable["isEvidence"] != 4
+    for f in factor:
+        mem = fmap["vid"][f["ftv_offset"]:f["ftv_offset"] + f["arity"]]
+        mem = [int(m) for m in mem if owned[m]]
+        for a in mem:
+            for b in mem:
+                if a != b:
+                    adj[a].add(b)
+    return adj
+
+
+def greedy_coloring(variable, factor, fmap, seed, global_vid=None):
+    nvar = len(variable)
+    adj = neighbours(variable, factor, fmap)
+    gid = np.arange(nvar) if global_vid is None else np.asarray(global_vid)
+    prio = [jp_priority(int(gid[v]), seed) for v in range(nvar)]
+    color = np.full(nvar, -1, np.int32)
+    for v in sorted(range(nvar), key=lambda i: -prio[i]):
+        if variable["isEvidence"][v] == 4:
+            continue
+        used = {int(color[u]) for u in adj[v] if color[u] >= 0}
+        c = 0
+        while c in used:
+            c += 1
+        color[v] = c
+    return color
+
+
+def conflicts(variable, factor, fmap, color):
+    adj = neighbours(variable, factor, fmap)
+    return sum(1 for v in range(len(variable)) for u in adj[v] if color[v] >= 0 and color[u] == color[v])
