@@ -7,7 +7,7 @@
 #include <thread>
 #include <cub/cub.cuh>
 
-#include "nb_common.cuh"
+#include "nb_eval.cuh"
 
 // ---------------------------------------------------------------------------
 // small host helpers
@@ -102,27 +102,36 @@ struct RawGraph {
 
 __device__ __forceinline__ int nbuckets(const RawGraph &G, int64_t v) { return G.v_dtype[v] == 0 ? 1 : G.v_card[v]; }
 
-// words and incidences of every row (ghost rows are empty: they are never sampled)
-__global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, int *overflow)
+// words and incidences of every row (ghost rows are empty: they are never sampled), and whether
+// the row qualifies for the single-pass Boolean kernel (NB_CLASS_FAST)
+__global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t *fast, int *overflow)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= G.V) return;
-    if (G.v_evid[v] == 4) { rowlen[v] = 0; ninc[v] = 0; return; }
+    if (G.v_evid[v] == 4) { rowlen[v] = 0; ninc[v] = 0; fast[v] = 0; return; }
     uint64_t words = 0, inc = 0;
     int nb = nbuckets(G, v);
+    bool ok = G.v_dtype[v] == 0 && G.v_card[v] == 2;
     for (int b = 0; b < nb; b++) {
         int64_t off = G.b_off[G.v_vtf[v] + b];
         int len = G.b_len[G.v_vtf[v] + b];
         if (G.v_dtype[v] == 1 && len > 0) words += G.wide ? 2 : 1;
         for (int e = 0; e < len; e++) {
             int f = G.fi[off + e];
-            words += nb_incidence_words(G.wide, G.f_code[f], G.f_arity[f], G.f_feat[f] != 1.0);
+            int code = G.f_code[f], a = G.f_arity[f];
+            words += nb_incidence_words(G.wide, code, a, G.f_feat[f] != 1.0);
+            if (ok) {   // truth-table class: arity <= 3, integer-valued function, small member domains
+                if (!nb_code_tt_ok(code) || a > 3) ok = false;
+                else if (!nb_code_tt_const_compare(code))
+                    for (int j = 0; j < a; j++) ok &= G.v_card[G.m_vid[G.f_off[f] + j]] <= 3;
+            }
         }
         inc += len;
     }
     if (words > 0x7FFFFFFFull || inc > 0x7FFFFFFFull) { *overflow = 1; words = 0; inc = 0; }
     rowlen[v] = (uint32_t)words;
     ninc[v] = (uint32_t)inc;
+    fast[v] = ok ? 1 : 0;
 }
 
 __host__ __device__ inline uint64_t nb_mix64(uint64_t x)
@@ -211,8 +220,8 @@ __global__ void k_max_color(int64_t V, const int32_t *color, int *maxc)
     if (v < V && color[v] >= 0) atomicMax(maxc, color[v]);
 }
 
-// sort key: path(1) | colour(15) | window(28) | row length(20); ghosts use colour = n_colors
-__global__ void k_sort_keys(int64_t V, const int32_t *color, const uint32_t *rowlen, int n_colors,
+// sort key: class(2) | colour(14) | window(28) | row length(20); ghosts use colour = n_colors
+__global__ void k_sort_keys(int64_t V, const int32_t *color, const uint32_t *rowlen, const uint8_t *fast, int n_colors,
                             int warp_row_words, int sigma_shift, uint64_t *keys, int32_t *ids,
                             unsigned long long *group_count, unsigned long long *color_edges,
                             const uint32_t *ninc)
@@ -221,33 +230,34 @@ __global__ void k_sort_keys(int64_t V, const int32_t *color, const uint32_t *row
     if (v >= V) return;
     int c = color[v] < 0 ? n_colors : color[v];
     uint32_t len = rowlen[v];
-    int path = len > (uint32_t)warp_row_words ? 1 : 0;
+    int cls = len > (uint32_t)warp_row_words ? NB_CLASS_WARP : (fast[v] ? NB_CLASS_FAST : NB_CLASS_GEN);
+    if (color[v] < 0) cls = NB_CLASS_GEN;
     uint64_t window = ((uint64_t)v >> sigma_shift) & ((1ull << 28) - 1);
     uint64_t l = len < (1u << 20) ? len : (1u << 20) - 1;
-    keys[v] = ((uint64_t)path << 63) | ((uint64_t)c << 48) | (window << 20) | l;
+    keys[v] = ((uint64_t)cls << 62) | ((uint64_t)c << 48) | (window << 20) | l;
     ids[v] = (int32_t)v;
-    atomicAdd(&group_count[path * (n_colors + 1) + c], 1ull);
+    atomicAdd(&group_count[cls * (n_colors + 1) + c], 1ull);
     if (color[v] >= 0) atomicAdd(&color_edges[c], (unsigned long long)ninc[v]);
 }
 
 // sorted position -> new id, plus all per-variable arrays in the new order
 __global__ void k_assign_ids(int64_t V, const uint64_t *keys, const int32_t *sorted_ids, int n_colors,
                              const int64_t *group_start, const int64_t *group_base, RawGraph G,
-                             const int32_t *v_init, const uint32_t *rowlen, int32_t *old2new,
+                             const int32_t *v_init, const uint32_t *rowlen, const uint8_t *fast, int32_t *old2new,
                              int32_t *new2old, uint32_t *vmeta, uint32_t *rowlen_new, nb_val_t *vinit,
                              uint32_t *rng_id, nb_val_t *val0, nb_val_t *val1)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= V) return;
     uint64_t key = keys[i];
-    int path = (int)(key >> 63);
-    int c = (int)((key >> 48) & 0x7FFF);
-    int g = path * (n_colors + 1) + c;
+    int cls = (int)(key >> 62);
+    int c = (int)((key >> 48) & 0x3FFF);
+    int g = cls * (n_colors + 1) + c;
     int64_t nid = group_base[g] + (i - group_start[g]);
     int v = sorted_ids[i];
     old2new[v] = (int32_t)nid;
     new2old[nid] = v;
-    vmeta[nid] = nb_pack_meta(G.v_card[v], G.v_evid[v], G.v_dtype[v], 1);
+    vmeta[nid] = nb_pack_meta(G.v_card[v], G.v_evid[v], G.v_dtype[v], 1, cls == NB_CLASS_FAST, rowlen[v]);
     rowlen_new[nid] = rowlen[v];
     nb_val_t init = (nb_val_t)v_init[v];
     vinit[nid] = init;
@@ -271,14 +281,14 @@ __global__ void k_count_entries_old(int64_t V, const int32_t *v_card, int64_t *e
     if (v < V) entries[v] = v_card[v] == 2 ? 1 : v_card[v];
 }
 
-// SELL-32 slice width = longest row of the slice
-__global__ void k_slice_width(int64_t n_slices, const uint32_t *rowlen_new, int64_t *width32)
+// SELL-32 slice size in quads (16 B): 32 lanes x ceil(longest row / 4)
+__global__ void k_slice_width(int64_t n_slices, const uint32_t *rowlen_new, int64_t *quads)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_slices) return;
     uint32_t w = 0;
     for (int l = 0; l < 32; l++) w = max(w, rowlen_new[s * 32 + l]);
-    width32[s] = (int64_t)w * 32;
+    quads[s] = (int64_t)((w + 3) / 4) * 32;
 }
 
 __global__ void k_warp_row_sizes(int64_t n_wrows, int64_t n_trows, const uint32_t *rowlen_new,
@@ -299,16 +309,17 @@ __global__ void k_fill_rows(RawGraph G, const int32_t *old2new, int64_t n_trows,
     if (v >= G.V || G.v_evid[v] == 4) return;
     int64_t nid = old2new[v];
     uint32_t *base;
-    int64_t stride;
+    bool quad;
     uint2 *incp = nullptr;
     if (nid < n_trows) {
-        base = twords + slice_ptr[nid >> 5] + (nid & 31);
-        stride = 32;
+        base = twords + ((slice_ptr[nid >> 5] + (nid & 31)) << 2);
+        quad = true;
     } else {
         base = wwords + wrow_ptr[nid - n_trows];
-        stride = 1;
+        quad = false;
         incp = inc + inc_ptr[nid - n_trows];
     }
+#define ROW_W(i) base[quad ? ((((i) >> 2) << 7) + ((i) & 3)) : (i)]
     int64_t pos = 0;
     int nb = nbuckets(G, v);
     const bool cat = G.v_dtype[v] == 1;
@@ -316,8 +327,8 @@ __global__ void k_fill_rows(RawGraph G, const int32_t *old2new, int64_t n_trows,
         int64_t off = G.b_off[G.v_vtf[v] + b];
         int len = G.b_len[G.v_vtf[v] + b];
         if (cat && len > 0) {
-            if (G.wide) { base[pos * stride] = (uint32_t)b; base[(pos + 1) * stride] = nb_pack_wide_b(C_MARK, 0, 0, 0); pos += 2; }
-            else { base[pos * stride] = nb_pack_mark_compact((uint32_t)b); pos += 1; }
+            if (G.wide) { ROW_W(pos) = (uint32_t)b; ROW_W(pos + 1) = nb_pack_wide_b(C_MARK, 0, 0, 0); pos += 2; }
+            else { ROW_W(pos) = nb_pack_mark_compact((uint32_t)b); pos += 1; }
         }
         for (int e = 0; e < len; e++) {
             int f = G.fi[off + e];
@@ -328,24 +339,19 @@ __global__ void k_fill_rows(RawGraph G, const int32_t *old2new, int64_t n_trows,
             int fixed = wfixed[wid];
             if (incp) { *incp++ = make_uint2((uint32_t)pos, (uint32_t)b); }
             if (G.wide) {
-                base[pos * stride] = wid;
-                base[(pos + 1) * stride] = nb_pack_wide_b(code, hasfeat, fixed, a);
+                ROW_W(pos) = wid;
+                ROW_W(pos + 1) = nb_pack_wide_b(code, hasfeat, fixed, a);
                 pos += 2;
             } else {
-                base[pos * stride] = nb_pack_compact(code, hasfeat, fixed, a, wid);
+                ROW_W(pos) = nb_pack_compact(code, hasfeat, fixed, a, wid);
                 pos += 1;
-            }
-            if (hasfeat) {
-                base[pos * stride] = (uint32_t)__double2loint(feat);
-                base[(pos + 1) * stride] = (uint32_t)__double2hiint(feat);
-                pos += 2;
             }
             int64_t mo = G.f_off[f];
             bool eq = nb_code_has_eq(code);
             for (int j = 0; j < a; j++) {
-                base[pos * stride] = (uint32_t)old2new[G.m_vid[mo + j]];
+                ROW_W(pos) = (uint32_t)old2new[G.m_vid[mo + j]];
                 pos++;
-                if (eq) { base[pos * stride] = (uint32_t)G.m_eq[mo + j]; pos++; }
+                if (eq) { ROW_W(pos) = (uint32_t)G.m_eq[mo + j]; pos++; }
             }
             if (nb_code_has_extra(code)) {
                 uint32_t x;
@@ -357,10 +363,78 @@ __global__ void k_fill_rows(RawGraph G, const int32_t *old2new, int64_t n_trows,
                     int m = nb_code_abstain_member(code);
                     x = m < a ? (uint32_t)(G.v_card[G.m_vid[mo + m]] - 1) : 0u;
                 }
-                base[pos * stride] = x;
+                ROW_W(pos) = x;
                 pos++;
             }
+            if (hasfeat) {
+                ROW_W(pos) = (uint32_t)__double2loint(feat);
+                ROW_W(pos + 1) = (uint32_t)__double2hiint(feat);
+                pos += 2;
+            }
         }
+    }
+#undef ROW_W
+}
+
+// ---- truth-table stream of the FAST rows --------------------------------------------------
+__global__ void k_tt_slice_width(int64_t n_slices, const int32_t *new2old, const uint32_t *ninc, int64_t *quads)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    uint32_t w = 0;
+    for (int l = 0; l < 32; l++) {
+        int v = new2old[s * 32 + l];
+        if (v >= 0) w = max(w, ninc[v]);
+    }
+    quads[s] = (int64_t)w * 32;
+}
+
+__global__ void k_tt_pad(uint4 *tt, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) tt[i] = make_uint4(0u, 0u, NB_TT_NEUTRAL, 0u);
+}
+
+__global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, const int64_t *tt_ptr, uint4 *tt,
+                          const uint8_t *wfixed)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || G.v_evid[v] == 4) return;
+    const int64_t nid = old2new[v];
+    if (nid >= n_frows) return;
+    uint4 *row = tt + tt_ptr[nid >> 5] + (nid & 31);
+    const int64_t off = G.b_off[G.v_vtf[v]];
+    const int len = G.b_len[G.v_vtf[v]];
+    for (int e = 0; e < len; e++) {
+        const int f = G.fi[off + e];
+        const int code = G.f_code[f], a = G.f_arity[f];
+        const int64_t mo = G.f_off[f];
+        // which "other" slot (0 = A, 1 = B) each member reads; -1 = the variable itself
+        int slot[3] = {-1, -1, -1};
+        uint32_t other[2] = {(uint32_t)nid, (uint32_t)nid};
+        int n_other = 0;
+        for (int j = 0; j < a; j++) {
+            int u = G.m_vid[mo + j];
+            if (u != v) { slot[j] = n_other; other[n_other++] = (uint32_t)old2new[u]; }
+        }
+        int extra = 0;
+        if (nb_code_has_extra(code)) {
+            int m = nb_code_abstain_member(code);
+            extra = m < a ? G.v_card[G.m_vid[mo + m]] - 1 : 0;
+        }
+        uint32_t table = 0;
+        for (int xa = 0; xa < 3; xa++)
+            for (int xb = 0; xb < 3; xb++) {
+                NbFastStats st;
+                st.reset();
+                st.extra = extra;
+                for (int j = 0; j < a; j++) st.member(j, a, slot[j] < 0, slot[j] < 0 ? 0 : (slot[j] == 0 ? xa : xb));
+                int d = (int)(st.value(code, 1) - st.value(code, 0));
+                table |= (uint32_t)(d + 2) << (3 * (3 * xa + xb));
+            }
+        const uint32_t wid = (uint32_t)G.f_wid[f];
+        if (wfixed[wid]) table |= NB_TT_FIXED_BIT;
+        row[(size_t)e * 32] = make_uint4(other[0], other[1], table, wid);
     }
 }
 
@@ -585,11 +659,13 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
 
     // ---- row sizes ----
     uint32_t *d_rowlen, *d_ninc;
+    uint8_t *d_fast;
     int *d_overflow;
     NB_TRY(nb_alloc(g, &d_rowlen, (size_t)V));
     NB_TRY(nb_alloc(g, &d_ninc, (size_t)V));
+    NB_TRY(nb_alloc(g, &d_fast, (size_t)V));
     NB_TRY(nb_alloc(g, &d_overflow, 1));
-    k_row_size<<<grid_for(V), 256, 0, g->stream>>>(G, d_rowlen, d_ninc, d_overflow);
+    k_row_size<<<grid_for(V), 256, 0, g->stream>>>(G, d_rowlen, d_ninc, d_fast, d_overflow);
     int overflow = 0;
     NB_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
@@ -597,7 +673,8 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
 
     // ---- colouring ----
     NB_TRY(color_graph(g, d));
-    const int nc = g->n_colors, ng = 2 * (nc + 1);
+    const int nc = g->n_colors, ng = 3 * (nc + 1);
+    if (nc >= 0x3FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 16382)", nc);
 
     // ---- ordering ----
     uint64_t *d_keys, *d_keys_sorted;
@@ -609,7 +686,7 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
     NB_TRY(nb_alloc(g, &d_ids_sorted, (size_t)V, false));
     NB_TRY(nb_alloc(g, &d_group_count, (size_t)ng));
     NB_TRY(nb_alloc(g, &d_color_edges, (size_t)nc + 1));
-    k_sort_keys<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_rowlen, nc, g->warp_row_words, g->sigma_shift,
+    k_sort_keys<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_rowlen, d_fast, nc, g->warp_row_words, g->sigma_shift,
                                                     d_keys, d_ids, d_group_count, d_color_edges, d_ninc);
     {
         size_t tmp = 0;
@@ -622,22 +699,30 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
     NB_CUDA(cudaMemcpyAsync(cedges.data(), d_color_edges, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
 
-    // groups in sorted order: path 0 colours 0..nc (nc = ghosts), then path 1 colours 0..nc
+    // groups in sorted order: FAST colours 0..nc, GEN colours 0..nc (nc = ghosts), WARP colours 0..nc
     std::vector<int64_t> gstart((size_t)ng), gbase((size_t)ng);
     g->colors.assign((size_t)nc, NbColorRange());
     int64_t pos = 0, nid = 0;
-    for (int c = 0; c <= nc; c++) {
-        gstart[(size_t)c] = pos;
-        nid = (nid + 31) & ~31ll;
-        gbase[(size_t)c] = nid;
-        if (c < nc) { g->colors[(size_t)c].t_beg = (int32_t)nid; g->colors[(size_t)c].t_end = (int32_t)(nid + (int64_t)gcount[(size_t)c]); }
-        pos += (int64_t)gcount[(size_t)c];
-        nid += (int64_t)gcount[(size_t)c];
+    for (int cls = 0; cls < 2; cls++) {
+        for (int c = 0; c <= nc; c++) {
+            size_t gi = (size_t)(cls * (nc + 1) + c);
+            gstart[gi] = pos;
+            nid = (nid + 31) & ~31ll;
+            gbase[gi] = nid;
+            if (c < nc) {
+                NbColorRange &cr = g->colors[(size_t)c];
+                if (cls == NB_CLASS_FAST) { cr.f_beg = (int32_t)nid; cr.f_end = (int32_t)(nid + (int64_t)gcount[gi]); }
+                else { cr.t_beg = (int32_t)nid; cr.t_end = (int32_t)(nid + (int64_t)gcount[gi]); }
+            }
+            pos += (int64_t)gcount[gi];
+            nid += (int64_t)gcount[gi];
+        }
+        if (cls == NB_CLASS_FAST) { nid = (nid + 31) & ~31ll; g->n_frows = nid; }
     }
     g->n_trows = (nid + 31) & ~31ll;
     int64_t wr = 0;
     for (int c = 0; c <= nc; c++) {
-        size_t gi = (size_t)(nc + 1 + c);
+        size_t gi = (size_t)(2 * (nc + 1) + c);
         gstart[gi] = pos;
         gbase[gi] = g->n_trows + wr;
         if (c < nc) { g->colors[(size_t)c].w_beg = (int32_t)wr; g->colors[(size_t)c].w_end = (int32_t)(wr + (int64_t)gcount[gi]); g->colors[(size_t)c].edges = (int64_t)cedges[(size_t)c]; }
@@ -656,14 +741,15 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
     NB_TRY(nb_alloc(g, &g->d_new2old, (size_t)Vn, false));
     NB_CUDA(cudaMemsetAsync(g->d_new2old, 0xFF, (size_t)Vn * 4, g->stream));
     NB_TRY(nb_alloc(g, &g->d_vmeta, (size_t)Vn));
-    NB_TRY(nb_alloc(g, &g->d_rowlen, (size_t)Vn));
+    uint32_t *d_rowlen_new;
+    NB_TRY(nb_alloc(g, &d_rowlen_new, (size_t)Vn));
     NB_TRY(nb_alloc(g, &g->d_vinit, (size_t)Vn));
     NB_TRY(nb_alloc(g, &g->d_rng_id, (size_t)Vn));
     NB_TRY(nb_alloc(g, &g->d_val[0], (size_t)Vn));
     NB_TRY(nb_alloc(g, &g->d_val[1], (size_t)Vn));
     k_assign_ids<<<grid_for(V), 256, 0, g->stream>>>(V, d_keys_sorted, d_ids_sorted, nc, d_gstart, d_gbase, G,
-                                                     g->d_v_init, d_rowlen, g->d_old2new, g->d_new2old, g->d_vmeta,
-                                                     g->d_rowlen, g->d_vinit, g->d_rng_id, g->d_val[0], g->d_val[1]);
+                                                     g->d_v_init, d_rowlen, d_fast, g->d_old2new, g->d_new2old, g->d_vmeta,
+                                                     d_rowlen_new, g->d_vinit, g->d_rng_id, g->d_val[0], g->d_val[1]);
 
     // ---- count layouts ----
     {
@@ -694,11 +780,13 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
         int64_t *d_width;
         NB_TRY(nb_alloc(g, &d_width, (size_t)n_slices + 1));
         NB_TRY(nb_alloc(g, &g->d_slice_ptr, (size_t)n_slices + 1));
-        if (n_slices) k_slice_width<<<grid_for(n_slices), 256, 0, g->stream>>>(n_slices, g->d_rowlen, d_width);
+        if (n_slices) k_slice_width<<<grid_for(n_slices), 256, 0, g->stream>>>(n_slices, d_rowlen_new, d_width);
         NB_TRY(exclusive_scan(g, d_width, g->d_slice_ptr, n_slices + 1));
-        NB_CUDA(cudaMemcpyAsync(&g->n_twords, g->d_slice_ptr + n_slices, 8, cudaMemcpyDeviceToHost, g->stream));
+        int64_t n_quads = 0;
+        NB_CUDA(cudaMemcpyAsync(&n_quads, g->d_slice_ptr + n_slices, 8, cudaMemcpyDeviceToHost, g->stream));
         NB_CUDA(cudaStreamSynchronize(g->stream));
-        NB_TRY(nb_alloc(g, &g->d_twords, (size_t)g->n_twords));
+        g->n_twords = n_quads * 4;
+        NB_TRY(nb_alloc(g, &g->d_twords, (size_t)g->n_twords + 4));
     }
     // ---- contiguous rows (warp path) ----
     {
@@ -708,7 +796,7 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
         NB_TRY(nb_alloc(g, &d_winc, (size_t)nw + 1));
         NB_TRY(nb_alloc(g, &g->d_wrow_ptr, (size_t)nw + 1));
         NB_TRY(nb_alloc(g, &g->d_inc_ptr, (size_t)nw + 1));
-        if (nw) k_warp_row_sizes<<<grid_for(nw), 256, 0, g->stream>>>(nw, g->n_trows, g->d_rowlen, g->d_new2old, d_ninc, d_wlen, d_winc);
+        if (nw) k_warp_row_sizes<<<grid_for(nw), 256, 0, g->stream>>>(nw, g->n_trows, d_rowlen_new, g->d_new2old, d_ninc, d_wlen, d_winc);
         NB_TRY(exclusive_scan(g, d_wlen, g->d_wrow_ptr, nw + 1));
         NB_TRY(exclusive_scan(g, d_winc, g->d_inc_ptr, nw + 1));
         NB_CUDA(cudaMemcpyAsync(&g->n_wwords, g->d_wrow_ptr + nw, 8, cudaMemcpyDeviceToHost, g->stream));
@@ -719,6 +807,23 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
     }
     k_fill_rows<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_trows, g->d_slice_ptr, g->d_twords,
                                                     g->d_wrow_ptr, g->d_wwords, g->d_inc_ptr, g->d_inc, g->d_wfixed);
+    NB_CUDA(cudaGetLastError());
+    // ---- truth-table stream (FAST rows = new ids [0, n_frows)) ----
+    {
+        const int64_t nfs = g->n_frows / 32;
+        int64_t *d_q;
+        NB_TRY(nb_alloc(g, &d_q, (size_t)nfs + 1));
+        NB_TRY(nb_alloc(g, &g->d_tt_ptr, (size_t)nfs + 1));
+        if (nfs) k_tt_slice_width<<<grid_for(nfs), 256, 0, g->stream>>>(nfs, g->d_new2old, d_ninc, d_q);
+        NB_TRY(exclusive_scan(g, d_q, g->d_tt_ptr, nfs + 1));
+        NB_CUDA(cudaMemcpyAsync(&g->n_tt_quads, g->d_tt_ptr + nfs, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        NB_TRY(nb_alloc(g, &g->d_tt, (size_t)g->n_tt_quads + 1, false));
+        if (g->n_tt_quads) {
+            k_tt_pad<<<grid_for(g->n_tt_quads), 256, 0, g->stream>>>(g->d_tt, g->n_tt_quads);
+            k_fill_tt<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_tt_ptr, g->d_tt, g->d_wfixed);
+        }
+    }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaStreamSynchronize(g->stream));
     return NB_OK;

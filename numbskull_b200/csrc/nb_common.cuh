@@ -98,7 +98,7 @@ __host__ __device__ inline int nb_code_abstain_member(int c) { return (c == C_DP
 // ----------------------------------------------------------------------------
 // Incidence-stream word formats.  A row (one variable) is a sequence of
 // incidences, one per (variable, factor) pair of the reference's vmap bucket(s):
-//   header | [featureValue lo, hi]? | member words | [extra]?
+//   header | member words | [extra]? | [featureValue lo, hi]?
 // compact header (1 word):  code:5 | feat:1 | fixed:1 | arity:5 | wid:20
 // wide header (2 words):    wid:32 ; code:5 | feat:1 | fixed:1 | 0:1 | arity:24
 // member word: NEW variable id; members of *_CAT functions are (id, dense_equal_to) pairs.
@@ -131,15 +131,28 @@ __host__ __device__ inline int nb_incidence_words(bool wide, int code, int arity
            (nb_code_has_extra(code) ? 1 : 0);
 }
 
-// vmeta word per (new) variable id
-#define NB_META_CARD(m) ((int)((m) & 0xFFFFu))
-#define NB_META_EVID(m) ((int)(((m) >> 16) & 0xFu))
-#define NB_META_DTYPE(m) ((int)(((m) >> 20) & 1u))
-#define NB_META_VALID(m) ((int)(((m) >> 21) & 1u))
-__host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, int valid)
+// vmeta word per (new) variable id: card:8 | isEvidence:4 | dataType:1 | valid:1 | fast:1 | row words:17
+// (row words saturate at 2^17-1; warp-path rows take their length from wrow_ptr)
+#define NB_META_CARD(m) ((int)((m) & 0xFFu))
+#define NB_META_EVID(m) ((int)(((m) >> 8) & 0xFu))
+#define NB_META_DTYPE(m) ((int)(((m) >> 12) & 1u))
+#define NB_META_VALID(m) ((int)(((m) >> 13) & 1u))
+#define NB_META_FAST(m) ((int)(((m) >> 14) & 1u))
+#define NB_META_ROWLEN(m) ((int)((m) >> 15))
+#define NB_META_MAX_ROWLEN ((1u << 17) - 1)
+__host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, int valid, int fast, uint32_t rowlen)
 {
-    return (uint32_t)card | ((uint32_t)(evid & 0xF) << 16) | ((uint32_t)dtype << 20) | ((uint32_t)valid << 21);
+    if (rowlen > NB_META_MAX_ROWLEN) rowlen = NB_META_MAX_ROWLEN;
+    return (uint32_t)card | ((uint32_t)(evid & 0xF) << 8) | ((uint32_t)dtype << 12) | ((uint32_t)valid << 13) |
+           ((uint32_t)fast << 14) | (rowlen << 15);
 }
+
+// Row classes.  FAST: Boolean variable (dataType 0, cardinality 2) whose incidences all have
+// arity <= 3 and a tabulable function -- sampled from the truth-table stream by k_gibbs_tt;
+// GEN: any other row short enough for one thread; WARP: long rows, one per warp.
+#define NB_CLASS_FAST 0
+#define NB_CLASS_GEN 1
+#define NB_CLASS_WARP 2
 
 typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
 #define NB_MAX_CARD 255
@@ -148,7 +161,8 @@ typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
 // device graph
 // ----------------------------------------------------------------------------
 struct NbColorRange {
-    int32_t t_beg, t_end;  // thread-path rows [t_beg, t_end) in new ids (t_beg % 32 == 0)
+    int32_t f_beg, f_end;  // FAST thread rows [f_beg, f_end) in new ids (f_beg % 32 == 0)
+    int32_t t_beg, t_end;  // GEN thread rows [t_beg, t_end) in new ids (t_beg % 32 == 0)
     int32_t w_beg, w_end;  // warp-path rows, as indices into the warp-row arrays
     int64_t edges;         // bucket entries owned by this colour
     int64_t learn_visits_max;  // max over weights of gradient visits in this colour (dataType-0 upper bound)
@@ -206,16 +220,19 @@ struct nb_graph {
     uint32_t *d_rng_id = nullptr;    // [Vn] low 32 bits of the global id (Philox counter)
 
     // ---- per new-id variable data ----
-    uint32_t *d_vmeta = nullptr;     // [Vn]
-    uint32_t *d_rowlen = nullptr;    // [Vn] words
+    uint32_t *d_vmeta = nullptr;     // [Vn] packed meta incl. row length
     nb_val_t *d_vinit = nullptr;     // [Vn]
     uint32_t *d_cstart = nullptr;    // [Vn + 1] new-order count layout
     int64_t *d_cstart_old = nullptr; // [V + 1] reference count layout
 
     // ---- streams ----
-    int64_t *d_slice_ptr = nullptr;  // [n_trows/32 + 1] word offsets into d_twords
-    uint32_t *d_twords = nullptr;    // SELL-32 column-major thread-path stream
+    int64_t *d_slice_ptr = nullptr;  // [n_trows/32 + 1] QUAD (16-byte) offsets into d_twords
+    uint32_t *d_twords = nullptr;    // SELL-32 thread-path stream: quad q of lane l at quad index ptr + q*32 + l
     int64_t n_twords = 0;
+    int64_t n_frows = 0;             // FAST rows occupy new ids [0, n_frows)
+    int64_t *d_tt_ptr = nullptr;     // [n_frows/32 + 1] quad offsets into d_tt
+    uint4 *d_tt = nullptr;           // truth-table stream of the FAST rows (SELL-32, one quad per incidence)
+    int64_t n_tt_quads = 0;
     int64_t *d_wrow_ptr = nullptr;   // [n_wrows + 1] word offsets into d_wwords
     uint32_t *d_wwords = nullptr;    // contiguous warp-path rows
     int64_t n_wwords = 0;

@@ -77,9 +77,22 @@ struct NbUniforms {
 // ---------------------------------------------------------------------------
 struct NbRow {
     const uint32_t *p;
-    int stride;
-    __device__ __forceinline__ uint32_t w(int i) const { return __ldg(p + (size_t)i * (size_t)stride); }
+    int quad;  // 1: SELL-32 quad layout (word i at p[(i / 4) * 128 + i % 4]); 0: contiguous row
+    __device__ __forceinline__ uint32_t w(int i) const
+    {
+        return quad ? __ldg(p + (((size_t)(i >> 2)) << 7) + (i & 3)) : __ldg(p + i);
+    }
 };
+
+// row of thread-path variable nid (new id) / of warp row wr
+__device__ __forceinline__ NbRow nb_thread_row(const uint32_t *twords, const int64_t *slice_ptr, int64_t nid)
+{
+    return NbRow{twords + ((slice_ptr[nid >> 5] + (nid & 31)) << 2), 1};
+}
+__device__ __forceinline__ NbRow nb_warp_row(const uint32_t *wwords, const int64_t *wrow_ptr, int64_t wr)
+{
+    return NbRow{wwords + wrow_ptr[wr], 0};
+}
 
 template <bool WIDE>
 __device__ __forceinline__ NbHdr nb_read_hdr(const NbRow &r, int pos)
@@ -119,9 +132,12 @@ __device__ __forceinline__ int nb_inc_words(const NbHdr &h)
     return nb_incidence_words(WIDE, h.code, h.arity, h.feat);
 }
 
-__device__ __forceinline__ double nb_read_feature(const NbRow &r, int pos)
+// featureValue of the incidence whose header is at `pos` (stored after members and extra)
+template <bool WIDE>
+__device__ __forceinline__ double nb_read_feature(const NbRow &r, const NbHdr &h, int pos)
 {
-    uint32_t lo = r.w(pos), hi = r.w(pos + 1);
+    int fpos = pos + (WIDE ? 2 : 1) + h.arity * (nb_code_has_eq(h.code) ? 2 : 1) + (nb_code_has_extra(h.code) ? 1 : 0);
+    uint32_t lo = r.w(fpos), hi = r.w(fpos + 1);
     return __hiloint2double((int)hi, (int)lo);
 }
 
@@ -263,7 +279,7 @@ __device__ inline double nb_eval_incidence(const NbRow &r, const NbHdr &h, int m
 template <bool WIDE>
 __device__ __forceinline__ int nb_member_pos(const NbHdr &h, int pos)
 {
-    return pos + nb_hdr_words<WIDE>() + (h.feat ? 2 : 0);
+    return pos + nb_hdr_words<WIDE>();
 }
 
 // p += w * f without FMA contraction: bit-identical to the reference's
@@ -417,3 +433,127 @@ __device__ __forceinline__ double nb_warp_sum(double x)
     return x;
 }
 
+
+// ---------------------------------------------------------------------------
+// Philox2x32-10 (same family, 64-bit counter, 32-bit key): one 53-bit uniform
+// per call, used where a variable needs a single draw per sweep.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline double nb_philox2x32_u53(uint32_t c0, uint32_t c1, uint32_t key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p = (uint64_t)0xD256D193u * c0;
+        c0 = (uint32_t)(p >> 32) ^ key ^ c1;
+        c1 = (uint32_t)p;
+        key += 0x9E3779B9u;
+    }
+    return nb_u53(c0, c1);
+}
+
+__host__ __device__ inline uint32_t nb_fold_key(uint64_t seed, uint64_t epoch, uint32_t tag)
+{
+    uint64_t x = seed ^ ((epoch >> 32) * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)tag << 56);
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33;
+    return (uint32_t)x ^ (uint32_t)(x >> 32);
+}
+
+// ---------------------------------------------------------------------------
+// Running statistics over the members of one incidence from which f(k = 0) and
+// f(k = 1) of every Boolean / data-programming function follow.  Used at build
+// time to tabulate the functions for the truth-table (TT) stream.
+// ---------------------------------------------------------------------------
+struct NbFastStats {
+    int any0, any1, alleq, first, cnt0, cnt1, nself, selfbody, lastself, lastval;
+    int m0, m1, m2, s0, s1, s2, extra;
+    __device__ __forceinline__ void reset()
+    {
+        any0 = any1 = 0; alleq = 1; first = -1; cnt0 = cnt1 = 0; nself = selfbody = 0; lastself = 0; lastval = 0;
+        m0 = m1 = m2 = 0; s0 = s1 = s2 = 0; extra = 0;
+    }
+    __device__ __forceinline__ void member(int j, int arity, bool isself, int x)
+    {
+        const bool last = j == arity - 1;
+        if (isself) {
+            nself++;
+            if (!last) selfbody++;
+        } else {
+            any0 |= x == 0;
+            any1 |= x == 1;
+            if (first < 0) first = x; else alleq &= x == first;
+            if (!last) { cnt0 += x == 0; cnt1 += x == 1; }
+        }
+        if (last) { lastself = isself; lastval = x; }
+        if (j == 0) { m0 = x; s0 = isself; }
+        else if (j == 1) { m1 = x; s1 = isself; }
+        else if (j == 2) { m2 = x; s2 = isself; }
+    }
+    // factor value with the variable forced to k (k in {0, 1})
+    __device__ __forceinline__ double value(int code, int k) const
+    {
+        switch (code) {
+        case C_IMPLY_NATURAL: return (!any0 && (nself == 0 || k != 0)) ? 1.0 : 0.0;
+        case C_OR: return (any1 || (nself > 0 && k == 1)) ? 1.0 : -1.0;
+        case C_AND:
+        case C_ISTRUE: return (!any0 && (nself == 0 || k != 0)) ? 1.0 : -1.0;
+        case C_EQUAL:
+            if (first < 0) return 1.0;
+            if (!alleq) return -1.0;
+            return (nself == 0 || k == first) ? 1.0 : -1.0;
+        case C_LINEAR:
+        case C_RATIO:
+        case C_LOGICAL: {
+            int head = lastself ? k : lastval;
+            int cnt = (head == 0 ? cnt0 : (head == 1 ? cnt1 : 0)) + (head == k ? selfbody : 0);
+            if (code == C_LINEAR) return (double)cnt;
+            if (code == C_RATIO) return log((double)(1 + cnt));
+            return cnt > 0 ? 1.0 : 0.0;
+        }
+        case C_DP_CLASS_PRIOR: return (s0 ? k : m0) == 1 ? 1.0 : -1.0;
+        case C_DP_LF_PRIOR: { int l = s0 ? k : m0; return l == 2 ? -1.0 : (l == 0 ? 0.0 : 1.0); }
+        case C_DP_LF_PROPENSITY: return (s0 ? k : m0) == extra ? 0.0 : 1.0;
+        case C_DP_LF_ACCURACY:
+        case C_DP_LF_CLASS_PROPENSITY: {
+            int y = s0 ? k : m0, l = s1 ? k : m1;
+            if (l == extra) return 0.0;
+            if (code == C_DP_LF_ACCURACY) return y == l ? 1.0 : -1.0;
+            return y == 1 ? 1.0 : -1.0;
+        }
+        case C_DP_DEP_FIXING:
+        case C_DP_DEP_REINFORCING: {
+            int y = s0 ? k : m0, l1 = s1 ? k : m1, l2 = s2 ? k : m2;
+            if (l1 == extra) return l2 != 1 ? -1.0 : 0.0;
+            if (code == C_DP_DEP_FIXING)
+                return ((l1 == 0 && l2 == 1 && y == 1) || (l1 == 1 && l2 == 0 && y == 0)) ? 1.0 : 0.0;
+            return ((l1 == 0 && l2 == 0 && y == 0) || (l1 == 1 && l2 == 1 && y == 1)) ? 1.0 : 0.0;
+        }
+        case C_DP_DEP_EXCLUSIVE: { int l1 = s0 ? k : m0, l2 = s1 ? k : m1; return (l1 == extra || l2 == extra) ? 0.0 : -1.0; }
+        case C_DP_DEP_SIMILAR: return (s0 ? k : m0) == (s1 ? k : m1) ? 1.0 : 0.0;
+        default: return 0.0;  // C_NOOP
+        }
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// Truth-table (TT) stream of the FAST row class.  A FAST row belongs to a
+// Boolean variable whose incidences all have arity <= 3 and an integer-valued
+// function; each incidence is ONE 16-byte quad
+//     { other member A (new id), other member B (new id), table, weight id }
+// where table holds, for the 3 x 3 combinations of (min(xA, 2), min(xB, 2)),
+// the 3-bit code of f(self = 1) - f(self = 0) + 2 at bit 3 * (3 * a + b); bit 27
+// = weight is fixed.  Unused member slots point at the variable itself, padding
+// quads carry the all-zero-difference table, so every lane of a warp runs the
+// same trip count with no parsing at all.
+// ---------------------------------------------------------------------------
+#define NB_TT_NEUTRAL 0x2492492u   /* 9 x code 2 (difference 0) */
+#define NB_TT_FIXED_BIT (1u << 27)
+
+__host__ __device__ inline bool nb_code_tt_const_compare(int c)
+{
+    return c == C_NOOP || c == C_IMPLY_NATURAL || c == C_OR || c == C_AND || c == C_ISTRUE;
+}
+__host__ __device__ inline bool nb_code_tt_ok(int c)
+{
+    return nb_code_tt_const_compare(c) || c == C_EQUAL || c == C_LINEAR || c == C_LOGICAL ||
+           (c >= C_DP_CLASS_PRIOR && c <= C_DP_DEP_SIMILAR);
+}

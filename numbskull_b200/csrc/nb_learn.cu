@@ -20,7 +20,6 @@
 
 struct LearnArgs {
     const uint32_t *vmeta;
-    const uint32_t *rowlen;
     const int64_t *slice_ptr;
     const uint32_t *twords;
     const int64_t *wrow_ptr;
@@ -98,7 +97,7 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
                 int mpos = nb_member_pos<WIDE>(h, pos);
                 double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
                 double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
-                double feat = h.feat ? nb_read_feature(r, pos + nb_hdr_words<WIDE>()) : 1.0;
+                double feat = h.feat ? nb_read_feature<WIDE>(r, h, pos) : 1.0;
                 sink.add(h.wid, (float)((f1 - f0) * feat), cnt_inc);
             }
             pos += nb_inc_words<WIDE>(h);
@@ -112,7 +111,7 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
             int mpos = nb_member_pos<WIDE>(h, pos);
             double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
             double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
-            double feat = h.feat ? nb_read_feature(r, pos + nb_hdr_words<WIDE>()) : 1.0;
+            double feat = h.feat ? nb_read_feature<WIDE>(r, h, pos) : 1.0;
             sink.add(h.wid, (float)((f1 - f0) * feat), cnt_inc);
         }
     }
@@ -153,7 +152,7 @@ __device__ inline void nb_flush_and_apply(const LearnArgs &a, float *s_grad, uin
 // thread path
 // ---------------------------------------------------------------------------
 template <bool WIDE, bool SMEM>
-__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, int beg, int end)
+__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, int beg0, int end0, int beg1, int end1)
 {
     extern __shared__ unsigned char s_raw[];
     float *s_grad = (float *)s_raw;
@@ -164,13 +163,15 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, 
     }
     GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
 
-    for (int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; nid < end;
-         nid += (int64_t)gridDim.x * blockDim.x) {
+    // two id ranges per launch: the colour's FAST-class rows and its GEN-class rows
+    const int64_t n0 = end0 - beg0, ntot = n0 + (end1 - beg1);
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < ntot; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nid = it < n0 ? beg0 + it : beg1 + (it - n0);
         const uint32_t meta = a.vmeta[nid];
         const int evid = NB_META_EVID(meta);
         if (!NB_META_VALID(meta) || evid == 4) continue;                   // learning.py:24-26
-        NbRow r{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32};
-        const int len = (int)a.rowlen[nid];
+        NbRow r = nb_thread_row(a.twords, a.slice_ptr, nid);
+        const int len = NB_META_ROWLEN(meta);
         const uint32_t self = (uint32_t)nid, id = a.rng_id[nid];
         int ev;
         if (evid != 1) {                                                    // :53-57
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, in
         const uint32_t meta = a.vmeta[nid];
         const int evid = NB_META_EVID(meta);
         if (!NB_META_VALID(meta) || evid == 4) continue;
-        NbRow r{a.wwords + a.wrow_ptr[wr], 1};
+        NbRow r = nb_warp_row(a.wwords, a.wrow_ptr, wr);
         const uint2 *inc = a.inc + a.inc_ptr[wr];
         const int n_inc = (int)(a.inc_ptr[wr + 1] - a.inc_ptr[wr]);
         const uint32_t self = (uint32_t)nid, id = a.rng_id[nid];
@@ -316,19 +317,20 @@ __global__ void k_apply_global(LearnArgs a)
 
 // visits per weight of one colour (upper bound: every incidence of a learnable row)
 template <bool WIDE>
-__global__ void k_visit_histogram(LearnArgs a, int beg, int end, int wbeg, int wend, uint32_t *hist)
+__global__ void k_visit_histogram(LearnArgs a, int beg0, int end0, int beg, int end, int wbeg, int wend, uint32_t *hist)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t nt = end - beg, nw = wend - wbeg;
-    if (i >= nt + nw) return;
-    int64_t nid = i < nt ? beg + i : a.n_trows + wbeg + (i - nt);
+    int64_t nf = end0 - beg0, nt = end - beg, nw = wend - wbeg;
+    if (i >= nf + nt + nw) return;
+    int64_t nid = i < nf ? beg0 + i : (i < nf + nt ? beg + (i - nf) : a.n_trows + wbeg + (i - nf - nt));
     const uint32_t meta = a.vmeta[nid];
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;
     if (!a.learn_non_evidence && evid != 1) return;
-    NbRow r = nid < a.n_trows ? NbRow{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32}
-                              : NbRow{a.wwords + a.wrow_ptr[nid - a.n_trows], 1};
-    int len = (int)a.rowlen[nid], pos = 0;
+    NbRow r = nid < a.n_trows ? nb_thread_row(a.twords, a.slice_ptr, nid) : nb_warp_row(a.wwords, a.wrow_ptr, nid - a.n_trows);
+    int len = nid < a.n_trows ? NB_META_ROWLEN(meta)
+                              : (int)(a.wrow_ptr[nid - a.n_trows + 1] - a.wrow_ptr[nid - a.n_trows]);
+    int pos = 0;
     while (pos < len) {
         NbHdr h = nb_read_hdr<WIDE>(r, pos);
         if (h.code != C_MARK && !h.fixed) atomicAdd(hist + h.wid, 1u);
@@ -350,7 +352,7 @@ static LearnArgs learn_args(nb_graph *g)
 {
     LearnArgs a;
     memset(&a, 0, sizeof(a));
-    a.vmeta = g->d_vmeta; a.rowlen = g->d_rowlen; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
+    a.vmeta = g->d_vmeta; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
     a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
     a.rng_id = g->d_rng_id; a.vinit = g->d_vinit; a.val_free = g->d_val[0]; a.val_evid = g->d_val[1];
     a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
@@ -380,13 +382,13 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
     NB_TRY(nb_alloc(g, &d_max, 1));
     for (int c = 0; c < g->n_colors; c++) {
         const NbColorRange &cr = g->colors[(size_t)c];
-        int64_t n = (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
+        int64_t n = (cr.f_end - cr.f_beg) + (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
         if (n == 0) continue;
         NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
         NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
         unsigned grid = (unsigned)((n + 255) / 256);
-        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
-        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, cr.f_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, cr.f_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
         k_max_u32<<<64, 256, 0, g->stream>>>(g->d_nvis, (int)g->W, d_max);
         uint32_t m = 0;
         NB_CUDA(cudaMemcpyAsync(&m, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
@@ -398,13 +400,13 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
 }
 
 template <bool WIDE, bool SMEM>
-static int launch_learn_range(nb_graph *g, const LearnArgs &a, int tb, int te, int wb, int we)
+static int launch_learn_range(nb_graph *g, const LearnArgs &a, int fb, int fe, int tb, int te, int wb, int we)
 {
     size_t smem = SMEM ? (size_t)g->W * 8 : 0;
-    if (te > tb) {
-        int64_t need = ((int64_t)(te - tb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
+    if (te > tb || fe > fb) {
+        int64_t need = ((int64_t)(te - tb) + (fe - fb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
         unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
-        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, tb, te);
+        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, fb, fe, tb, te);
         g->launches++;
         if (!SMEM) { k_apply_global<<<(unsigned)((g->W + 255) / 256), 256, 0, g->stream>>>(a); g->launches++; }
     }
@@ -441,18 +443,21 @@ int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, 
         for (int c = 0; c < g->n_colors; c++) {
             const NbColorRange &cr = g->colors[(size_t)c];
             int64_t chunks = std::max<int64_t>(1, (vmax[(size_t)c] + bv - 1) / bv);
-            int64_t nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
-            chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(nt, nw)));
+            int64_t nf = cr.f_end - cr.f_beg, nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
+            chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(nf, std::max(nt, nw))));
+            auto cut = [](int beg, int64_t n, int64_t k, int64_t parts, int end) {
+                return k >= parts ? end : beg + (int)((n * k / parts) & ~31ll);
+            };
             for (int64_t k = 0; k < chunks; k++) {
-                int tb = cr.t_beg + (int)((nt * k / chunks) & ~31ll), te = cr.t_beg + (int)((nt * (k + 1) / chunks) & ~31ll);
-                if (k == chunks - 1) te = cr.t_end;
+                int fb = cut(cr.f_beg, nf, k, chunks, cr.f_end), fe = cut(cr.f_beg, nf, k + 1, chunks, cr.f_end);
+                int tb = cut(cr.t_beg, nt, k, chunks, cr.t_end), te = cut(cr.t_beg, nt, k + 1, chunks, cr.t_end);
                 int wb = cr.w_beg + (int)(nw * k / chunks), we = cr.w_beg + (int)(nw * (k + 1) / chunks);
                 if (g->wide) {
-                    if (smem) NB_TRY((launch_learn_range<true, true>(g, a, tb, te, wb, we)));
-                    else NB_TRY((launch_learn_range<true, false>(g, a, tb, te, wb, we)));
+                    if (smem) NB_TRY((launch_learn_range<true, true>(g, a, fb, fe, tb, te, wb, we)));
+                    else NB_TRY((launch_learn_range<true, false>(g, a, fb, fe, tb, te, wb, we)));
                 } else {
-                    if (smem) NB_TRY((launch_learn_range<false, true>(g, a, tb, te, wb, we)));
-                    else NB_TRY((launch_learn_range<false, false>(g, a, tb, te, wb, we)));
+                    if (smem) NB_TRY((launch_learn_range<false, true>(g, a, fb, fe, tb, te, wb, we)));
+                    else NB_TRY((launch_learn_range<false, false>(g, a, fb, fe, tb, te, wb, we)));
                 }
             }
         }

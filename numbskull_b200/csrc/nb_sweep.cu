@@ -10,7 +10,6 @@
 
 struct SweepArgs {
     const uint32_t *vmeta;
-    const uint32_t *rowlen;
     const int64_t *slice_ptr;
     const uint32_t *twords;
     const int64_t *wrow_ptr;
@@ -30,7 +29,7 @@ struct SweepArgs {
 static SweepArgs sweep_args(nb_graph *g, int chain, int burnin, int sample_evidence, uint64_t seed, uint64_t epoch)
 {
     SweepArgs a;
-    a.vmeta = g->d_vmeta; a.rowlen = g->d_rowlen; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
+    a.vmeta = g->d_vmeta; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
     a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
     a.rng_id = g->d_rng_id; a.cstart = g->d_cstart; a.count = g->d_count; a.val = g->d_val[chain];
     a.weight = g->d_weight; a.n_trows = g->n_trows; a.seed = seed; a.epoch = epoch;
@@ -55,11 +54,59 @@ __global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int 
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
     if (!(evid == 0 || a.sample_evidence)) return;          // :24
-    NbRow r{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32};
+    NbRow r = nb_thread_row(a.twords, a.slice_ptr, nid);
     NbUniforms rng(a.rng_id[nid], a.epoch, NB_TAG_FREE, a.seed);
-    int k = nb_sample_row<WIDE>(r, (int)a.rowlen[nid], (uint32_t)nid, meta, a.val, a.weight, rng);
+    int k = nb_sample_row<WIDE>(r, NB_META_ROWLEN(meta), (uint32_t)nid, meta, a.val, a.weight, rng);
     a.val[nid] = (nb_val_t)k;
     nb_tally(a, nid, NB_META_CARD(meta), k);
+}
+
+// FAST rows: truth-table stream, one 16-byte quad per incidence, uniform trip count per warp.
+#define NB_TT_UNROLL 4
+__global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__restrict__ tt_ptr,
+                                                  const uint4 *__restrict__ tt, int beg, int end, uint32_t key)
+{
+    const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (nid >= end) return;
+    // independent loads first: they overlap with the stream
+    const uint32_t meta = a.vmeta[nid];
+    const uint32_t rid = a.rng_id[nid];
+    const uint32_t cs = a.cstart[nid];
+    const int64_t q0 = tt_ptr[nid >> 5], q1 = tt_ptr[(nid >> 5) + 1];
+    const int n = (int)((q1 - q0) >> 5);                      // incidences of the longest row of this slice
+    const uint4 *qp = tt + q0 + (nid & 31);
+    const nb_val_t *__restrict__ vals = a.val;
+    const double *__restrict__ weight = a.weight;
+    double d = 0.0;                                           // e1 - e0
+    for (int j = 0; j < n; j += NB_TT_UNROLL) {
+        uint4 q[NB_TT_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT_UNROLL; t++)
+            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4((uint32_t)nid, (uint32_t)nid, NB_TT_NEUTRAL, 0u);
+        int xa[NB_TT_UNROLL], xb[NB_TT_UNROLL];
+        double w[NB_TT_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT_UNROLL; t++) {
+            xa[t] = (int)vals[q[t].x];
+            xb[t] = (int)vals[q[t].y];
+            w[t] = __ldg(weight + q[t].w);
+        }
+#pragma unroll
+        for (int t = 0; t < NB_TT_UNROLL; t++) {
+            const int idx = min(xa[t], 2) * 3 + min(xb[t], 2);
+            const int df = (int)((q[t].z >> (3 * idx)) & 7u) - 2;
+            d = fma(w[t], (double)df, d);
+        }
+    }
+    const int evid = NB_META_EVID(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
+    if (!(evid == 0 || a.sample_evidence)) return;          // :24
+    const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, key);
+    // P(0) = 1 / (1 + exp(e1 - e0)): draw_sample (inference.py:36-52) for cardinality 2
+    const float p0 = 1.0f / (1.0f + __expf((float)d));
+    const int k = u <= (double)p0 ? 0 : 1;
+    a.val[nid] = (nb_val_t)k;
+    if (!a.burnin) a.count[cs] += k;                         // inference.py:30-31
 }
 
 // ---------------------------------------------------------------------------
@@ -80,7 +127,7 @@ __device__ inline void nb_warp_row_energies(const uint32_t *__restrict__ wwords,
     const int lane = threadIdx.x & 31;
     const int card = NB_META_CARD(meta);
     const bool small = NB_META_DTYPE(meta) == 0 && card <= 4;
-    NbRow r{wwords + wrow_ptr[wr], 1};
+    NbRow r = nb_warp_row(wwords, wrow_ptr, wr);
     const int64_t i0 = inc_ptr[wr], i1 = inc_ptr[wr + 1];
     if (!small) {
         for (int k = lane; k < card; k += 32) se[k] = 0.0;
@@ -149,6 +196,12 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     if (color < 0 || color >= g->n_colors) NB_FAIL(NB_ERR_INVALID, "colour %d out of range [0, %d)", color, g->n_colors);
     const NbColorRange &c = g->colors[(size_t)color];
     SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
+    if (c.f_end > c.f_beg) {
+        unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
+        uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
+        k_gibbs_tt<<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
+        g->launches++;
+    }
     if (c.t_end > c.t_beg) {
         unsigned grid = (unsigned)((c.t_end - c.t_beg + 255) / 256);
         if (g->wide) k_gibbs_thread<true><<<grid, 256, 0, g->stream>>>(a, c.t_beg, c.t_end);
@@ -178,9 +231,9 @@ __global__ void k_potentials(SweepArgs a, const int32_t *old2new, const int64_t 
     const int64_t nid = old2new[var_ids[i]];
     const uint32_t meta = a.vmeta[nid];
     const int card = NB_META_CARD(meta);
-    const int len = (int)a.rowlen[nid];
-    NbRow r = nid < a.n_trows ? NbRow{a.twords + a.slice_ptr[nid >> 5] + (nid & 31), 32}
-                              : NbRow{a.wwords + a.wrow_ptr[nid - a.n_trows], 1};
+    NbRow r = nid < a.n_trows ? nb_thread_row(a.twords, a.slice_ptr, nid) : nb_warp_row(a.wwords, a.wrow_ptr, nid - a.n_trows);
+    const int len = nid < a.n_trows ? NB_META_ROWLEN(meta)
+                                    : (int)(a.wrow_ptr[nid - a.n_trows + 1] - a.wrow_ptr[nid - a.n_trows]);
     double *o = out + out_offsets[i];
     for (int k = 0; k < card; k++) {
         double e = 0.0;
