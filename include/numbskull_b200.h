@@ -65,6 +65,9 @@ typedef struct {
     int32_t warp_row_words;            /* rows longer than this go one-per-warp; 0 = default */
     int32_t sigma_shift;               /* SELL sorting window = 2^sigma_shift ids; 0 = default */
     const int32_t *preset_color;       /* NULL, or a valid colouring to adopt (n_variable)  */
+    int32_t deferred_coloring;         /* != 0: stop after the upload; the caller drives
+                                          nb_color_round (+ ghost colour exchange) and then
+                                          nb_graph_finalize -- partitioned graphs             */
 } nb_graph_desc;
 
 typedef struct {
@@ -193,6 +196,19 @@ int nb_gather_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, i
                          uint8_t *dev_out);
 int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, int64_t n,
                           const uint8_t *dev_in);
+/* One colour of a learning sweep (both chains + gradient reduction + weight update for the
+ * colour's mini-batches); the caller exchanges both chains' boundary values afterwards. */
+int nb_learn_color_phase(nb_graph *g, int color, double stepsize, int regularization, double reg_param,
+                         double truncation, int learn_non_evidence, uint64_t seed, int64_t epoch,
+                         int64_t batch_visits);
+/* Distributed Jones-Plassmann (graphs created with deferred_coloring): one round over the
+ * owned, still uncoloured variables; ghosts are consulted through the colours last scattered
+ * in.  *remaining = owned variables still uncoloured after the round. */
+int nb_color_round(nb_graph *g, int64_t *remaining);
+int nb_gather_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, int32_t *dev_out);
+int nb_scatter_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, const int32_t *dev_in);
+/* Orders the variables and lays out the streams once every variable has its colour. */
+int nb_graph_finalize(nb_graph *g);
 /* run the sweeps on a caller-owned CUDA stream (cudaStream_t as void*) */
 int nb_set_stream(nb_graph *g, void *cuda_stream);
 int nb_begin_epoch(nb_graph *g, int64_t *epoch); /* returns and advances the sweep counter */

@@ -30,6 +30,7 @@ class GraphDesc(C.Structure):
         ("warp_row_words", C.c_int32),
         ("sigma_shift", C.c_int32),
         ("preset_color", C.c_void_p),
+        ("deferred_coloring", C.c_int32),
     ]
 
 
@@ -80,6 +81,11 @@ SIGNATURES = {
     "nb_gibbs_color_phase": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _U64, _I64]),
     "nb_gather_values_dev": (C.c_int, [_P, C.c_int, _P, _I64, _P]),
     "nb_scatter_values_dev": (C.c_int, [_P, C.c_int, _P, _I64, _P]),
+    "nb_learn_color_phase": (C.c_int, [_P, C.c_int, _DBL, C.c_int, _DBL, _DBL, C.c_int, _U64, _I64, _I64]),
+    "nb_color_round": (C.c_int, [_P, C.POINTER(_I64)]),
+    "nb_gather_colors_dev": (C.c_int, [_P, _P, _I64, _P]),
+    "nb_scatter_colors_dev": (C.c_int, [_P, _P, _I64, _P]),
+    "nb_graph_finalize": (C.c_int, [_P]),
     "nb_set_stream": (C.c_int, [_P, _P]),
     "nb_begin_epoch": (C.c_int, [_P, C.POINTER(_I64)]),
 }

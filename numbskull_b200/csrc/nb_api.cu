@@ -70,7 +70,7 @@ extern "C" int nb_graph_get_colors(const nb_graph *g, int32_t *colors)
     NB_CUDA(cudaSetDevice(g->device));
     NB_CUDA(cudaMemcpyAsync(colors, g->d_color, (size_t)g->V * 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
-    for (int64_t i = 0; i < g->V; i++) if (colors[i] < 0) colors[i] = -1;
+    for (int64_t i = 0; i < g->V; i++) if (colors[i] < 0) colors[i] = -1;   /* -2 (ignored ghost) -> -1 */
     return NB_OK;
 }
 
@@ -198,6 +198,7 @@ extern "C" int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate)
 // ---------------------------------------------------------------------------
 static int check_runnable(const nb_graph *g)
 {
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized: colour it (nb_color_round) and call nb_graph_finalize first");
     if (g->has_unknown_func)
         NB_FAIL(NB_ERR_NOT_IMPLEMENTED, "Error: Factor Function %d ( used in factor %lld ) is not implemented.",
                 g->unknown_func_id, (long long)g->unknown_func_factor);
@@ -333,6 +334,58 @@ extern "C" int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_
     if (n == 0) return NB_OK;
     NB_CUDA(cudaSetDevice(g->device));
     k_scatter_u8<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_old2new, g->d_val[chain], dev_in);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+extern "C" int nb_learn_color_phase(nb_graph *g, int color, double stepsize, int regularization, double reg_param,
+                                    double truncation, int learn_non_evidence, uint64_t seed, int64_t epoch,
+                                    int64_t batch_visits)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    return nb_learn_color(g, color, stepsize, regularization, reg_param, truncation, learn_non_evidence, seed,
+                          (uint64_t)epoch, batch_visits);
+}
+
+extern "C" int nb_color_round(nb_graph *g, int64_t *remaining)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    if (g->finalized) { *remaining = 0; return NB_OK; }
+    return nb_build_color_round(g, remaining);
+}
+
+extern "C" int nb_graph_finalize(nb_graph *g)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    return nb_build_finalize(g);
+}
+
+__global__ void k_gather_i32(int64_t n, const int32_t *ids, const int32_t *src, int32_t *out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[ids[i]];
+}
+__global__ void k_scatter_i32(int64_t n, const int32_t *ids, int32_t *dst, const int32_t *in)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[ids[i]] = in[i];
+}
+
+extern "C" int nb_gather_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, int32_t *dev_out)
+{
+    if (n == 0) return NB_OK;
+    NB_CUDA(cudaSetDevice(g->device));
+    k_gather_i32<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_color, dev_out);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+extern "C" int nb_scatter_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, const int32_t *dev_in)
+{
+    if (n == 0) return NB_OK;
+    NB_CUDA(cudaSetDevice(g->device));
+    k_scatter_i32<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_color, dev_in);
     NB_CUDA(cudaGetLastError());
     return NB_OK;
 }

@@ -155,7 +155,8 @@ __global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *c
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= G.V) return;
-    if (color[v] != -1) return;  // coloured, or -2 = ghost
+    if (G.v_evid[v] == 4) return;   // ghosts are coloured by their owner
+    if (color[v] != -1) return;     // already coloured
     const uint64_t pv = nb_jp_priority(G.gid ? (uint64_t)G.gid[v] : (uint64_t)v, seed);
     const int base = cbase[v];
     uint64_t used = 0;
@@ -187,10 +188,11 @@ __global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *c
     ((volatile int32_t *)color)[v] = base + (__ffsll((long long)~used) - 1);
 }
 
-__global__ void k_init_color(int64_t V, const int8_t *v_evid, int32_t *color)
+// single-GPU graphs ignore ghosts (-2); partitioned graphs wait for the owner's colour (-1)
+__global__ void k_init_color(int64_t V, const int8_t *v_evid, int32_t *color, int deferred)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (v < V) color[v] = v_evid[v] == 4 ? -2 : -1;
+    if (v < V) color[v] = (v_evid[v] == 4 && !deferred) ? -2 : -1;
 }
 
 // conflicts = ordered pairs (v, u) of owned variables that share a factor and a colour
@@ -221,23 +223,24 @@ __global__ void k_max_color(int64_t V, const int32_t *color, int *maxc)
 }
 
 // sort key: class(2) | colour(14) | window(28) | row length(20); ghosts use colour = n_colors
-__global__ void k_sort_keys(int64_t V, const int32_t *color, const uint32_t *rowlen, const uint8_t *fast, int n_colors,
+__global__ void k_sort_keys(int64_t V, const int32_t *color, const int8_t *v_evid, const uint32_t *rowlen, const uint8_t *fast, int n_colors,
                             int warp_row_words, int sigma_shift, uint64_t *keys, int32_t *ids,
                             unsigned long long *group_count, unsigned long long *color_edges,
                             const uint32_t *ninc)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= V) return;
-    int c = color[v] < 0 ? n_colors : color[v];
+    const bool ghost = v_evid[v] == 4 || color[v] < 0;
+    int c = ghost ? n_colors : color[v];
     uint32_t len = rowlen[v];
     int cls = len > (uint32_t)warp_row_words ? NB_CLASS_WARP : (fast[v] ? NB_CLASS_FAST : NB_CLASS_GEN);
-    if (color[v] < 0) cls = NB_CLASS_GEN;
+    if (ghost) cls = NB_CLASS_GEN;
     uint64_t window = ((uint64_t)v >> sigma_shift) & ((1ull << 28) - 1);
     uint64_t l = len < (1u << 20) ? len : (1u << 20) - 1;
     keys[v] = ((uint64_t)cls << 62) | ((uint64_t)c << 48) | (window << 20) | l;
     ids[v] = (int32_t)v;
     atomicAdd(&group_count[cls * (n_colors + 1) + c], 1ull);
-    if (color[v] >= 0) atomicAdd(&color_edges[c], (unsigned long long)ninc[v]);
+    if (!ghost) atomicAdd(&color_edges[c], (unsigned long long)ninc[v]);
 }
 
 // sorted position -> new id, plus all per-variable arrays in the new order
@@ -608,44 +611,44 @@ static int extract_and_upload(nb_graph *g, const nb_graph_desc *d)
     return NB_OK;
 }
 
+int nb_build_color_round(nb_graph *g, int64_t *remaining)
+{
+    RawGraph G = raw_view(g);
+    NB_CUDA(cudaMemsetAsync(g->d_jpcnt, 0, 8, g->stream));
+    k_jp_round<<<grid_for(g->V), 256, 0, g->stream>>>(G, g->color_seed, g->d_color, g->d_cbase, g->d_jpcnt);
+    unsigned long long rem = 0;
+    NB_CUDA(cudaMemcpyAsync(&rem, g->d_jpcnt, 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    g->jp_rounds++;
+    *remaining = (int64_t)rem;
+    return NB_OK;
+}
+
 static int color_graph(nb_graph *g, const nb_graph_desc *d)
 {
     const int64_t V = g->V;
     RawGraph G = raw_view(g);
     NB_TRY(nb_alloc(g, &g->d_color, (size_t)V, false));
-    unsigned long long *d_cnt;
-    NB_TRY(nb_alloc(g, &d_cnt, 2));
+    NB_TRY(nb_alloc(g, &g->d_jpcnt, 2));
+    NB_TRY(nb_alloc(g, &g->d_cbase, (size_t)V));
+    g->color_seed = d->color_seed;
     if (d->preset_color) {
         NB_CUDA(cudaMemcpyAsync(g->d_color, d->preset_color, (size_t)V * 4, cudaMemcpyHostToDevice, g->stream));
-        k_check_coloring<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_color, d_cnt);
+        k_check_coloring<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_color, g->d_jpcnt);
         unsigned long long bad = 0;
-        NB_CUDA(cudaMemcpyAsync(&bad, d_cnt, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaMemcpyAsync(&bad, g->d_jpcnt, 8, cudaMemcpyDeviceToHost, g->stream));
         NB_CUDA(cudaStreamSynchronize(g->stream));
         if (bad) NB_FAIL(NB_ERR_INVALID, "preset colouring has %llu conflicts", bad);
-    } else {
-        int32_t *d_cbase;
-        NB_TRY(nb_alloc(g, &d_cbase, (size_t)V));
-        k_init_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_v_evid, g->d_color);
-        for (int64_t round = 0;; round++) {
-            NB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, g->stream));
-            k_jp_round<<<grid_for(V), 256, 0, g->stream>>>(G, d->color_seed, g->d_color, d_cbase, d_cnt);
-            unsigned long long rem = 0;
-            NB_CUDA(cudaMemcpyAsync(&rem, d_cnt, 8, cudaMemcpyDeviceToHost, g->stream));
-            NB_CUDA(cudaStreamSynchronize(g->stream));
-            g->jp_rounds = round + 1;
-            if (rem == 0) break;
-            if (round > 1000000) NB_FAIL(NB_ERR_CUDA, "Jones-Plassmann colouring did not converge");
-        }
+        return NB_OK;
     }
-    int *d_max;
-    NB_TRY(nb_alloc(g, &d_max, 1));
-    NB_CUDA(cudaMemsetAsync(d_max, 0xFF, 4, g->stream));  // -1
-    k_max_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_max);
-    int maxc = -1;
-    NB_CUDA(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
-    NB_CUDA(cudaStreamSynchronize(g->stream));
-    g->n_colors = maxc + 1;
-    if (g->n_colors >= 0x7FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 32766)", g->n_colors);
+    k_init_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_v_evid, g->d_color, g->deferred ? 1 : 0);
+    if (g->deferred) return NB_OK;   // the caller drives nb_color_round + the ghost exchange
+    for (;;) {
+        int64_t rem = 0;
+        NB_TRY(nb_build_color_round(g, &rem));
+        if (rem == 0) break;
+        if (g->jp_rounds > 1000000) NB_FAIL(NB_ERR_CUDA, "Jones-Plassmann colouring did not converge");
+    }
     return NB_OK;
 }
 
@@ -653,19 +656,18 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
 {
     if (d->warp_row_words > 0) g->warp_row_words = d->warp_row_words;
     if (d->sigma_shift > 0) g->sigma_shift = d->sigma_shift;
+    g->deferred = d->deferred_coloring != 0;
     NB_TRY(extract_and_upload(g, d));
     const int64_t V = g->V;
     RawGraph G = raw_view(g);
 
     // ---- row sizes ----
-    uint32_t *d_rowlen, *d_ninc;
-    uint8_t *d_fast;
     int *d_overflow;
-    NB_TRY(nb_alloc(g, &d_rowlen, (size_t)V));
-    NB_TRY(nb_alloc(g, &d_ninc, (size_t)V));
-    NB_TRY(nb_alloc(g, &d_fast, (size_t)V));
+    NB_TRY(nb_alloc(g, &g->d_rowlen0, (size_t)V));
+    NB_TRY(nb_alloc(g, &g->d_ninc0, (size_t)V));
+    NB_TRY(nb_alloc(g, &g->d_fast0, (size_t)V));
     NB_TRY(nb_alloc(g, &d_overflow, 1));
-    k_row_size<<<grid_for(V), 256, 0, g->stream>>>(G, d_rowlen, d_ninc, d_fast, d_overflow);
+    k_row_size<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_rowlen0, g->d_ninc0, g->d_fast0, d_overflow);
     int overflow = 0;
     NB_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
@@ -673,6 +675,27 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
 
     // ---- colouring ----
     NB_TRY(color_graph(g, d));
+    if (g->deferred) return NB_OK;
+    return nb_build_finalize(g);
+}
+
+int nb_build_finalize(nb_graph *g)
+{
+    if (g->finalized) return NB_OK;
+    const int64_t V = g->V;
+    RawGraph G = raw_view(g);
+    uint32_t *d_rowlen = g->d_rowlen0, *d_ninc = g->d_ninc0;
+    uint8_t *d_fast = g->d_fast0;
+    {
+        int *d_max;
+        NB_TRY(nb_alloc(g, &d_max, 1));
+        NB_CUDA(cudaMemsetAsync(d_max, 0xFF, 4, g->stream));  // -1
+        k_max_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_max);
+        int maxc = -1;
+        NB_CUDA(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        g->n_colors = maxc + 1;
+    }
     const int nc = g->n_colors, ng = 3 * (nc + 1);
     if (nc >= 0x3FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 16382)", nc);
 
@@ -686,7 +709,7 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
     NB_TRY(nb_alloc(g, &d_ids_sorted, (size_t)V, false));
     NB_TRY(nb_alloc(g, &d_group_count, (size_t)ng));
     NB_TRY(nb_alloc(g, &d_color_edges, (size_t)nc + 1));
-    k_sort_keys<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, d_rowlen, d_fast, nc, g->warp_row_words, g->sigma_shift,
+    k_sort_keys<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_color, g->d_v_evid, d_rowlen, d_fast, nc, g->warp_row_words, g->sigma_shift,
                                                     d_keys, d_ids, d_group_count, d_color_edges, d_ninc);
     {
         size_t tmp = 0;
@@ -826,6 +849,7 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
     }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaStreamSynchronize(g->stream));
+    g->finalized = true;
     return NB_OK;
 }
 

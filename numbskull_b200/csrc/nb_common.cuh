@@ -213,6 +213,16 @@ struct nb_graph {
     int32_t *d_m_eq = nullptr;       // [NFMAP] (only if any_categorical)
     int64_t *d_gid = nullptr;        // [V] global ids or null
 
+    // ---- build intermediates (original ids) ----
+    uint32_t *d_rowlen0 = nullptr;   // [V] row words
+    uint32_t *d_ninc0 = nullptr;     // [V] incidences
+    uint8_t *d_fast0 = nullptr;      // [V] FAST-class flag
+    int32_t *d_cbase = nullptr;      // [V] JP colour window
+    unsigned long long *d_jpcnt = nullptr;
+    uint64_t color_seed = 0;
+    bool finalized = false;
+    bool deferred = false;
+
     // ---- ordering ----
     int32_t *d_color = nullptr;      // [V] original ids
     int32_t *d_old2new = nullptr;    // [V]
@@ -264,6 +274,8 @@ struct nb_graph {
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
 
+    std::vector<int64_t> learn_vmax;   // per colour: max gradient visits of one weight
+    int learn_vmax_flag = -1;
     std::vector<NbColorRange> colors;
     std::vector<void *> allocs;
 };
@@ -280,6 +292,10 @@ int nb_ensure_pinned(nb_graph *g, size_t bytes);
 
 // build steps (nb_build.cu)
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);
+int nb_build_color_round(nb_graph *g, int64_t *remaining);
+int nb_build_finalize(nb_graph *g);
+int nb_learn_color(nb_graph *g, int color, double step, int regularization, double reg_param, double truncation,
+                   int learn_non_evidence, uint64_t seed, uint64_t epoch, int64_t batch_visits);
 
 // sweeps (nb_sweep.cu / nb_learn.cu)
 int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed,

@@ -420,47 +420,80 @@ static int launch_learn_range(nb_graph *g, const LearnArgs &a, int fb, int fe, i
     return NB_OK;
 }
 
+// per-graph cache of the visit bounds (depends on learn_non_evidence)
+static int learn_prepare(nb_graph *g, LearnArgs &a, std::vector<int64_t> &vmax, int learn_non_evidence)
+{
+    const bool smem = g->W <= NB_LEARN_SMEM_W;
+    NB_TRY(ensure_learn_buffers(g, smem));
+    a = learn_args(g);
+    a.learn_non_evidence = learn_non_evidence;
+    if (g->learn_vmax_flag != learn_non_evidence || (int)g->learn_vmax.size() != g->n_colors) {
+        NB_TRY(color_visit_bounds(g, a, g->learn_vmax));
+        g->learn_vmax_flag = learn_non_evidence;
+    }
+    vmax = g->learn_vmax;
+    return NB_OK;
+}
+
+static int learn_one_color(nb_graph *g, const LearnArgs &a, int c, int64_t vmax_c, int64_t bv)
+{
+    const bool smem = g->W <= NB_LEARN_SMEM_W;
+    const NbColorRange &cr = g->colors[(size_t)c];
+    int64_t chunks = std::max<int64_t>(1, (vmax_c + bv - 1) / bv);
+    int64_t nf = cr.f_end - cr.f_beg, nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
+    chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(nf, std::max(nt, nw))));
+    auto cut = [](int beg, int64_t n, int64_t k, int64_t parts, int end) {
+        return k >= parts ? end : beg + (int)((n * k / parts) & ~31ll);
+    };
+    for (int64_t k = 0; k < chunks; k++) {
+        int fb = cut(cr.f_beg, nf, k, chunks, cr.f_end), fe = cut(cr.f_beg, nf, k + 1, chunks, cr.f_end);
+        int tb = cut(cr.t_beg, nt, k, chunks, cr.t_end), te = cut(cr.t_beg, nt, k + 1, chunks, cr.t_end);
+        int wb = cr.w_beg + (int)(nw * k / chunks), we = cr.w_beg + (int)(nw * (k + 1) / chunks);
+        if (g->wide) {
+            if (smem) NB_TRY((launch_learn_range<true, true>(g, a, fb, fe, tb, te, wb, we)));
+            else NB_TRY((launch_learn_range<true, false>(g, a, fb, fe, tb, te, wb, we)));
+        } else {
+            if (smem) NB_TRY((launch_learn_range<false, true>(g, a, fb, fe, tb, te, wb, we)));
+            else NB_TRY((launch_learn_range<false, false>(g, a, fb, fe, tb, te, wb, we)));
+        }
+    }
+    return NB_OK;
+}
+
+// mini-batch size: at most this many visits of any one weight between two applications
+static int64_t default_batch_visits(double step, int64_t batch_visits)
+{
+    return batch_visits > 0 ? batch_visits : (int64_t)std::max(1.0, std::floor(0.5 / std::max(std::fabs(step), 1e-12)));
+}
+
+int nb_learn_color(nb_graph *g, int color, double step, int regularization, double reg_param, double truncation,
+                   int learn_non_evidence, uint64_t seed, uint64_t epoch, int64_t batch_visits)
+{
+    if (color < 0 || color >= g->n_colors) return NB_OK;   // a colour this rank does not own
+    LearnArgs a;
+    std::vector<int64_t> vmax;
+    NB_TRY(learn_prepare(g, a, vmax, learn_non_evidence));
+    a.seed = seed; a.reg_param = reg_param; a.truncation = truncation; a.regularization = regularization;
+    a.step = step; a.epoch = epoch;
+    NB_TRY(learn_one_color(g, a, color, vmax[(size_t)color], default_batch_visits(step, batch_visits)));
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
 int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, int regularization, double reg_param,
                  double truncation, int learn_non_evidence, uint64_t seed, int64_t batch_visits)
 {
     if (n_epochs <= 0) return NB_OK;
-    const bool smem = g->W <= NB_LEARN_SMEM_W;
-    NB_TRY(ensure_learn_buffers(g, smem));
-    LearnArgs a = learn_args(g);
-    a.seed = seed; a.reg_param = reg_param; a.truncation = truncation;
-    a.regularization = regularization; a.learn_non_evidence = learn_non_evidence;
-
+    LearnArgs a;
     std::vector<int64_t> vmax;
-    NB_TRY(color_visit_bounds(g, a, vmax));
-
+    NB_TRY(learn_prepare(g, a, vmax, learn_non_evidence));
+    a.seed = seed; a.reg_param = reg_param; a.truncation = truncation; a.regularization = regularization;
     double step = *stepsize;
     for (int64_t ep = 0; ep < n_epochs; ep++) {
         a.step = step;
         a.epoch = g->epoch_counter++;
-        // mini-batch size: at most `bv` visits of any one weight between two applications
-        int64_t bv = batch_visits > 0 ? batch_visits
-                                      : (int64_t)std::max(1.0, std::floor(0.5 / std::max(std::fabs(step), 1e-12)));
-        for (int c = 0; c < g->n_colors; c++) {
-            const NbColorRange &cr = g->colors[(size_t)c];
-            int64_t chunks = std::max<int64_t>(1, (vmax[(size_t)c] + bv - 1) / bv);
-            int64_t nf = cr.f_end - cr.f_beg, nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
-            chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(nf, std::max(nt, nw))));
-            auto cut = [](int beg, int64_t n, int64_t k, int64_t parts, int end) {
-                return k >= parts ? end : beg + (int)((n * k / parts) & ~31ll);
-            };
-            for (int64_t k = 0; k < chunks; k++) {
-                int fb = cut(cr.f_beg, nf, k, chunks, cr.f_end), fe = cut(cr.f_beg, nf, k + 1, chunks, cr.f_end);
-                int tb = cut(cr.t_beg, nt, k, chunks, cr.t_end), te = cut(cr.t_beg, nt, k + 1, chunks, cr.t_end);
-                int wb = cr.w_beg + (int)(nw * k / chunks), we = cr.w_beg + (int)(nw * (k + 1) / chunks);
-                if (g->wide) {
-                    if (smem) NB_TRY((launch_learn_range<true, true>(g, a, fb, fe, tb, te, wb, we)));
-                    else NB_TRY((launch_learn_range<true, false>(g, a, fb, fe, tb, te, wb, we)));
-                } else {
-                    if (smem) NB_TRY((launch_learn_range<false, true>(g, a, fb, fe, tb, te, wb, we)));
-                    else NB_TRY((launch_learn_range<false, false>(g, a, fb, fe, tb, te, wb, we)));
-                }
-            }
-        }
+        const int64_t bv = default_batch_visits(step, batch_visits);
+        for (int c = 0; c < g->n_colors; c++) NB_TRY(learn_one_color(g, a, c, vmax[(size_t)c], bv));
         NB_CUDA(cudaGetLastError());
         step *= decay;   // factorgraph.py:206
     }

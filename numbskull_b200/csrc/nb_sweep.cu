@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp(SweepArg
 
 int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed, uint64_t epoch)
 {
-    if (color < 0 || color >= g->n_colors) NB_FAIL(NB_ERR_INVALID, "colour %d out of range [0, %d)", color, g->n_colors);
+    if (color < 0) NB_FAIL(NB_ERR_INVALID, "negative colour %d", color);
+    if (color >= g->n_colors) return NB_OK;   // partitioned graphs: a colour this rank does not own
     const NbColorRange &c = g->colors[(size_t)color];
     SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
     if (c.f_end > c.f_beg) {

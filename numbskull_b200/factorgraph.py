@@ -78,6 +78,7 @@ class FactorGraph(object):
         self.preset_color = None
         self.warp_row_words = int(os.environ.get("NUMBSKULL_B200_WARP_ROW_WORDS", 0))  # 0 = default
         self.sigma_shift = int(os.environ.get("NUMBSKULL_B200_SIGMA_SHIFT", 0))        # 0 = default
+        self.deferred_coloring = False  # partitioned graphs: colouring is driven by partition.py
         self._g = None
 
     # ------------------------------------------------------------------
@@ -100,7 +101,8 @@ class FactorGraph(object):
                 _lib.ptr(k["factor"]), len(k["factor"]), _lib.ptr(k["fmap"]), len(k["fmap"]),
                 _lib.ptr(k["vmap"]), len(k["vmap"]), _lib.ptr(k["factor_index"]), len(k["factor_index"]),
                 self.device, self.color_seed, _lib.ptr(k["global_vid"]),
-                int(self.warp_row_words), int(self.sigma_shift), _lib.ptr(k["preset_color"]))
+                int(self.warp_row_words), int(self.sigma_shift), _lib.ptr(k["preset_color"]),
+                int(bool(self.deferred_coloring)))
             g = C.c_void_p()
             _lib.check(L.nb_graph_create(C.byref(desc), C.byref(g)))
             self._g = g

@@ -1,0 +1,325 @@
+"""Variable-partitioned multi-GPU execution (one process per GPU).
+
+Follows the reference's master/minion scheme (salt/src/numbskull_master.py:343,
+numbskull_minion.py:185, messages.py:1308-1319): every rank OWNS a block of
+variables, holds every factor that touches one of them, and keeps the remote
+members of those factors as ghost variables with ``isEvidence == 4`` -- the
+flag both reference kernels skip (inference.py:21-23, learning.py:24-26).
+Where the reference ships values once per epoch, here the owner's fresh
+values go to the ghost copies after EVERY colour, so the partitioned sampler
+is the same chromatic Gibbs chain as the single-GPU one: colours come from a
+distributed Jones-Plassmann run whose priorities depend only on the global
+variable id, and the Philox streams are keyed by the global id too, so an
+N-GPU run reproduces the 1-GPU samples bit for bit.
+
+Learning adds the reference's per-epoch weight-delta sum
+(numbskull_master.py:223-224): w <- w_prev + sum_r (w_r - w_prev), one
+all-reduce per epoch.
+
+``torch.distributed`` is plumbing only (rendezvous, point-to-point transport:
+NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic).
+"""
+from __future__ import print_function
+
+import ctypes as C
+
+import numpy as np
+
+from .numbskulltypes import Factor, FactorToVar, Variable
+
+
+# --------------------------------------------------------------------------- partitioning
+def block_bounds(n, world):
+    """Contiguous owner blocks: rank r owns global ids [b[r], b[r+1])."""
+    return np.array([(r * n) // world for r in range(world + 1)], np.int64)
+
+
+def extract_local(weight, variable, factor, fmap, lo, hi):
+    """Owner-computes sub-graph of the block [lo, hi) of a global graph.
+
+    Keeps (in global order) every factor with at least one owned member;
+    local variables are the owned block followed by the ghosts in increasing
+    global id; ghosts get ``isEvidence = 4``.  Returns a dict with the local
+    record arrays, ``global_vid`` and ``n_owned``."""
+    arity = factor["arity"].astype(np.int64)
+    fid_of_entry = np.repeat(np.arange(len(factor), dtype=np.int64), arity)
+    # entries of a factor are contiguous at ftv_offset; build the entry index explicitly
+    entry = np.repeat(factor["ftv_offset"].astype(np.int64), arity) + \
+        (np.arange(len(fid_of_entry), dtype=np.int64) - np.repeat(np.cumsum(arity) - arity, arity))
+    vids = fmap["vid"][entry].astype(np.int64)
+    owned_entry = (vids >= lo) & (vids < hi)
+    keep_factor = np.zeros(len(factor), bool)
+    keep_factor[fid_of_entry[owned_entry]] = True
+    keep_entry = keep_factor[fid_of_entry]
+
+    loc_factor = factor[keep_factor].copy()
+    loc_arity = loc_factor["arity"].astype(np.int64)
+    off = np.zeros(len(loc_factor), np.int64)
+    if len(loc_factor) > 1:
+        np.cumsum(loc_arity[:-1], out=off[1:])
+    loc_factor["ftv_offset"] = off
+    loc_entries = entry[keep_entry]
+    loc_vids = vids[keep_entry]
+
+    ghosts = np.unique(loc_vids[(loc_vids < lo) | (loc_vids >= hi)])
+    n_owned = hi - lo
+    global_vid = np.concatenate((np.arange(lo, hi, dtype=np.int64), ghosts))
+    loc_variable = variable[global_vid].copy()
+    loc_variable["isEvidence"][n_owned:] = 4
+    loc_variable["vtf_offset"] = 0
+
+    loc_fmap = np.zeros(len(loc_entries), FactorToVar)
+    is_owned = (loc_vids >= lo) & (loc_vids < hi)
+    lid = np.where(is_owned, loc_vids - lo, n_owned + np.searchsorted(ghosts, loc_vids))
+    loc_fmap["vid"] = lid
+    loc_fmap["dense_equal_to"] = fmap["dense_equal_to"][loc_entries]
+    return dict(weight=weight.copy(), variable=loc_variable, factor=loc_factor, fmap=loc_fmap,
+                domain_mask=np.zeros(len(loc_variable), np.bool_), global_vid=global_vid,
+                n_owned=int(n_owned))
+
+
+def ising_strip(rows, cols, rank, world, coupling=0.1):
+    """Rank ``rank``'s share of a (rows*world) x cols Ising grid (BASELINE config 2
+    shape, weak scaling): it owns ``rows`` grid rows and sees the row above and
+    below as ghosts.  Built locally -- the global graph is never materialised."""
+    from . import synth
+    top = 1 if rank > 0 else 0
+    bot = 1 if rank < world - 1 else 0
+    w, v, f, fm, dm, e = synth.ising_grid(rows + top + bot, cols, coupling)
+    first_global_row = rank * rows - top
+    gv = first_global_row * cols + np.arange(len(v), dtype=np.int64)
+    lo, hi = top * cols, (top + rows) * cols          # owned block in sub-grid ids
+    local = extract_local(w, v, f, fm, lo, hi)
+    # extract_local numbers owned first, then ghosts; translate its ids to the true global ids
+    local["global_vid"] = gv[local["global_vid"]]
+    return local, (rows * world) * cols
+
+
+# --------------------------------------------------------------------------- halo plan
+class HaloPlan(object):
+    """Who needs whose values.  ``send_ids[p]`` are local ids of owned variables
+    that rank p holds as ghosts, ``recv_ids[p]`` the local ids of this rank's
+    ghosts owned by p, in matching order."""
+
+    def __init__(self, global_vid, n_owned, bounds, rank, world, group=None):
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        ghosts = np.asarray(global_vid[n_owned:], np.int64)
+        owner = np.searchsorted(bounds, ghosts, side="right") - 1
+        requests = [ghosts[owner == p] for p in range(world)]
+        self.recv_ids = [np.nonzero(owner == p)[0].astype(np.int64) + n_owned for p in range(world)]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, [r.tolist() for r in requests], group=group)
+        else:
+            gathered = [[r.tolist() for r in requests]]
+        lo = int(bounds[rank])
+        self.send_ids = []
+        for p in range(world):
+            asked = np.asarray(gathered[p][rank], np.int64)
+            assert ((asked >= lo) & (asked < bounds[rank + 1])).all()
+            self.send_ids.append(asked - lo)
+        assert len(self.send_ids[rank]) == 0 and len(self.recv_ids[rank]) == 0
+
+    def restrict(self, keep_local):
+        """Per-peer (send, recv) id lists of the variables flagged in ``keep_local``."""
+        send = [ids[keep_local[ids]] for ids in self.send_ids]
+        recv = [ids[keep_local[ids]] for ids in self.recv_ids]
+        return send, recv
+
+
+class Exchange(object):
+    """One fixed communication pattern: gather -> point-to-point -> scatter."""
+
+    def __init__(self, send, recv, rank, world, dtype, device, group=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.group = rank, world, group
+        self.send_counts = [len(x) for x in send]
+        self.recv_counts = [len(x) for x in recv]
+        self.n_send, self.n_recv = sum(self.send_counts), sum(self.recv_counts)
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)  # noqa: E731
+        self.send_ids = torch.from_numpy(cat(send).astype(np.int32)).to(device)
+        self.recv_ids = torch.from_numpy(cat(recv).astype(np.int32)).to(device)
+        self.send_buf = torch.zeros(max(self.n_send, 1), dtype=dtype, device=device)
+        self.recv_buf = torch.zeros(max(self.n_recv, 1), dtype=dtype, device=device)
+        # gloo moves host memory only: device buffers are staged through the CPU (1-GPU tests);
+        # NCCL sends the device buffers directly over NVLink
+        import torch.distributed as dist
+        self.stage = (world > 1 and self.send_buf.is_cuda and dist.get_backend(group) == "gloo")
+
+    def run(self, gather, scatter):
+        """gather(ids, out) fills out[i] = x[ids[i]]; scatter(ids, buf) sets x[ids[i]] = buf[i]."""
+        import torch.distributed as dist
+        if self.n_send:
+            gather(self.send_ids, self.send_buf[:self.n_send])
+        sbuf = self.send_buf.cpu() if self.stage else self.send_buf
+        rbuf = self.recv_buf.cpu() if self.stage else self.recv_buf
+        ops, so, ro = [], 0, 0
+        for p in range(self.world):
+            ns, nr = self.send_counts[p], self.recv_counts[p]
+            if ns:
+                ops.append(dist.P2POp(dist.isend, sbuf[so:so + ns], p, group=self.group))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, rbuf[ro:ro + nr], p, group=self.group))
+            so += ns
+            ro += nr
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if self.stage:
+            self.recv_buf.copy_(rbuf)
+        if self.n_recv:
+            scatter(self.recv_ids, self.recv_buf[:self.n_recv])
+
+
+# --------------------------------------------------------------------------- runner
+class PartitionedGibbs(object):
+    """One rank of a partitioned factor graph on its GPU."""
+
+    def __init__(self, local, n_global, rank, world, device, seed, color_seed=0x5EED, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .dataloading import assign_vtf_offsets, compute_var_map
+        from .factorgraph import FactorGraph
+        from .numbskulltypes import VarToFactor
+        self.torch, self.dist, self.lib = torch, dist, _lib
+        self.rank, self.world, self.group = rank, world, group
+        self.n_owned = local["n_owned"]
+        self.global_vid = local["global_vid"]
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+
+        variable = local["variable"]
+        n_vtf = assign_vtf_offsets(variable)
+        vmap = np.zeros(n_vtf, VarToFactor)
+        findex = np.zeros(len(local["fmap"]), np.int64)
+        compute_var_map(variable, local["factor"], local["fmap"], vmap, findex, local["domain_mask"])
+        fg = FactorGraph(local["weight"], variable, local["factor"], local["fmap"], vmap, findex, 1, 1,
+                         rank, 1, device=device, seed=seed)
+        fg.global_vid = self.global_vid
+        fg.color_seed = color_seed
+        fg.deferred_coloring = True
+        self.fg = fg
+        L = _lib.lib()
+        g = fg._device_graph()
+        # everything (library kernels and NCCL transport) is ordered on torch's current stream
+        _lib.check(L.nb_set_stream(g, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+        bounds = block_bounds(n_global, world)
+        assert bounds[rank + 1] - bounds[rank] == self.n_owned and self.global_vid[0] == bounds[rank]
+        self.plan = HaloPlan(self.global_vid, self.n_owned, bounds, rank, world, group)
+
+        # ---- distributed Jones-Plassmann ----
+        full = Exchange(self.plan.send_ids, self.plan.recv_ids, rank, world, torch.int32, self.dev, group)
+        rounds = 0
+        while True:
+            rem = C.c_int64(0)
+            _lib.check(L.nb_color_round(g, C.byref(rem)))
+            full.run(lambda ids, out: _lib.check(L.nb_gather_colors_dev(g, ids.data_ptr(), ids.numel(), out.data_ptr())),
+                     lambda ids, buf: _lib.check(L.nb_scatter_colors_dev(g, ids.data_ptr(), ids.numel(), buf.data_ptr())))
+            t = torch.tensor([rem.value], device=self.dev, dtype=torch.int64)
+            if world > 1:
+                dist.all_reduce(t, group=group)
+            rounds += 1
+            if int(t.item()) == 0:
+                break
+        self.jp_rounds = rounds
+        torch.cuda.synchronize()
+        _lib.check(L.nb_graph_finalize(g))
+        colors = fg.colors()
+        t = torch.tensor([int(colors.max()) + 1 if len(colors) else 0], device=self.dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        self.n_colors = int(t.item())
+        self.colors = colors
+
+        # ---- per-colour halo exchanges (uint8 values) ----
+        self.halo = []
+        for c in range(self.n_colors):
+            send, recv = self.plan.restrict(colors == c)
+            self.halo.append(Exchange(send, recv, rank, world, torch.uint8, self.dev, group))
+        self.halo_bytes_per_sweep = sum(h.n_send for h in self.halo)
+
+    # -- device helpers
+    def _exchange(self, c, chain):
+        L, g, lib = self.lib.lib(), self.fg._g, self.lib
+        self.halo[c].run(
+            lambda ids, out: lib.check(L.nb_gather_values_dev(g, chain, ids.data_ptr(), ids.numel(), out.data_ptr())),
+            lambda ids, buf: lib.check(L.nb_scatter_values_dev(g, chain, ids.data_ptr(), ids.numel(), buf.data_ptr())))
+
+    def sweeps(self, n, burnin, sample_evidence):
+        """n chromatic Gibbs sweeps; after each colour the owners' new values reach the ghosts."""
+        L, g, lib = self.lib.lib(), self.fg._g, self.lib
+        for _ in range(n):
+            ep = C.c_int64(0)
+            lib.check(L.nb_begin_epoch(g, C.byref(ep)))
+            for c in range(self.n_colors):
+                lib.check(L.nb_gibbs_color_phase(g, c, int(bool(burnin)), int(bool(sample_evidence)),
+                                                 self.fg.seed, ep.value))
+                if self.world > 1:
+                    self._exchange(c, 0)
+
+    def inference(self, burnin_epochs, epochs, sample_evidence=True):
+        """FactorGraph.inference for the owned block; returns the owned marginals."""
+        fg, L = self.fg, self.lib.lib()
+        fg._upload(0, 0)
+        self.sweeps(burnin_epochs, True, sample_evidence)
+        self.lib.check(L.nb_reset_counts(fg._g))
+        self.sweeps(epochs, False, sample_evidence)
+        self.torch.cuda.synchronize()
+        fg._download(0, 0, counts=True)
+        if epochs:
+            fg.marginals = fg.count / float(epochs)
+        return fg.marginals[:fg.cstart[self.n_owned]]
+
+    def inference_e2e(self, epochs):
+        return self.inference(0, epochs, True)
+
+    def learn(self, burnin_epochs, epochs, stepsize, decay, regularization, reg_param, truncation,
+              learn_non_evidence=False):
+        """FactorGraph.learn across the ranks: per colour both chains' boundary values are
+        exchanged; per epoch the weight deltas are summed (numbskull_master.py:223-224)."""
+        fg, L, lib, torch = self.fg, self.lib.lib(), self.lib, self.torch
+        g = fg._device_graph()
+        fg._upload(0, 0)
+        self.sweeps(burnin_epochs, True, True)
+        w_prev = torch.from_numpy(fg.weight_value[0].copy()).to(self.dev)
+        w_now = torch.empty_like(w_prev)
+        for _ in range(epochs):
+            ep = C.c_int64(0)
+            lib.check(L.nb_begin_epoch(g, C.byref(ep)))
+            for c in range(self.n_colors):
+                lib.check(L.nb_learn_color_phase(g, c, float(stepsize), int(regularization), float(reg_param),
+                                                 float(truncation), int(bool(learn_non_evidence)), fg.seed,
+                                                 ep.value, int(fg.batch_visits)))
+                if self.world > 1:
+                    self._exchange(c, 0)
+                    self._exchange(c, 1)
+            if self.world > 1:
+                torch.cuda.synchronize()
+                host = np.empty(len(fg.weight), np.float64)
+                lib.check(L.nb_get_weights(g, lib.ptr(host)))
+                w_now.copy_(torch.from_numpy(host))
+                delta = w_now - w_prev
+                self.dist.all_reduce(delta, group=self.group)
+                w_prev = w_prev + delta
+                host[:] = w_prev.cpu().numpy()
+                lib.check(L.nb_set_weights(g, lib.ptr(host)))
+            stepsize *= decay
+        torch.cuda.synchronize()
+        fg._download(0, 0, evid=True, weights=True)
+        return stepsize
+
+
+def partition_graph(weight, variable, factor, fmap, rank, world, device, seed, group=None, color_seed=0x5EED):
+    """Block-partition a global graph (every rank passes the same arrays)."""
+    bounds = block_bounds(len(variable), world)
+    local = extract_local(weight, variable, factor, fmap, int(bounds[rank]), int(bounds[rank + 1]))
+    return PartitionedGibbs(local, len(variable), rank, world, device, seed, color_seed, group)
+
+
+def ising_strip_runner(rows, cols, rank, world, device, seed):
+    local, n_global = ising_strip(rows, cols, rank, world)
+    return PartitionedGibbs(local, n_global, rank, world, device, seed)
