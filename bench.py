@@ -167,7 +167,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     L = _lib.lib()
@@ -209,6 +211,14 @@ def run_ours(args):
     barrier()
     l0 = C.c_int64(0)
     L.nb_launch_count(g, C.byref(l0))
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     with ClockSampler(local_rank) as clocks:
         barrier()
         _lib.check(L.nb_timer_start(g))
@@ -218,18 +228,14 @@ def run_ours(args):
         _lib.check(L.nb_timer_stop(g, C.byref(ms)))
         barrier()
         wall = time.perf_counter() - t0
-        # keep the GPU busy a little longer so that the sampler sees clocks under load
-        if ms.value < 1500:
-            sweeps(max(1, int(steps * 1500 / max(ms.value, 1e-3)) // 4))
+        dev_ms = max_over_ranks(ms.value)                      # max over ranks, device clock
+        l1 = C.c_int64(0)
+        L.nb_launch_count(g, C.byref(l1))
+        # keep the GPUs busy a little longer so that the sampler sees clocks under load
+        # (same count on every rank: it is derived from the rank-agreed dev_ms)
+        if dev_ms < 1500:
+            sweeps(max(1, int(steps * 1500 / max(dev_ms, 1e-3)) // 4))
             barrier()
-    l1 = C.c_int64(0)
-    L.nb_launch_count(g, C.byref(l1))
-    dev_ms = float(ms.value)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dev_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
 
     # ---- end to end through the public API with host arrays ----
     e2e_steps = max(1, min(steps, 5))
@@ -248,14 +254,12 @@ def run_ours(args):
         for _ in range(e2e_steps):
             runner.inference_e2e(1)
         barrier()
-        e2e_dt = (time.perf_counter() - t0) / e2e_steps
-        import torch.distributed as dist
-        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+        e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     V, Wn = len(fg.variable), len(fg.weight)
-    h2d = 2 * V * 8 + Wn * 8
-    d2h = V * 8 + len(fg.count) * 8
+    # bytes that cross PCIe per step: values travel as 1 byte, counts as 4 (narrowed / widened
+    # on the host next to pinned staging buffers), weights as float64
+    h2d = V * 1 + Wn * 8
+    d2h = V * 1 + len(fg.count) * 4
 
     if rank != 0:
         if world > 1:

@@ -147,6 +147,8 @@ int nb_reset_counts(nb_graph *g);
 /* accumulate != 0: counts[i] += device tally (the reference's count is cumulative,
  * factorgraph.py:172-173); else counts[i] = device tally. */
 int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate);
+/* Same, and in the same host pass marginals[i] = counts[i] / epochs (factorgraph.py:172-173). */
+int nb_get_counts_marginals(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double epochs);
 
 /* ------------------------------ hot path ------------------------------ */
 

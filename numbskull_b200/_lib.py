@@ -70,6 +70,7 @@ SIGNATURES = {
     "nb_get_weights": (C.c_int, [_P, _P]),
     "nb_reset_counts": (C.c_int, [_P]),
     "nb_get_counts": (C.c_int, [_P, _P, C.c_int]),
+    "nb_get_counts_marginals": (C.c_int, [_P, _P, C.c_int, _P, _DBL]),
     "nb_potentials": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P, _I64]),
     "nb_gibbs_sweeps": (C.c_int, [_P, _I64, C.c_int, C.c_int, _U64]),
     "nb_learn_sweeps": (C.c_int, [_P, _I64, C.POINTER(_DBL), _DBL, C.c_int, _DBL, _DBL, C.c_int, _U64, _I64]),

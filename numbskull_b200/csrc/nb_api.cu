@@ -1,6 +1,7 @@
 // C-ABI entry points: graph lifecycle, state exchange at call boundaries,
 // sweep drivers and measurement helpers (include/numbskull_b200.h).
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <thread>
 
@@ -82,34 +83,69 @@ extern "C" int nb_graph_color_edges(const nb_graph *g, int64_t *edges_per_color)
 
 // ---------------------------------------------------------------------------
 // state exchange
+//
+// The caller's arrays keep the reference's types (int64 values and counts,
+// float64 weights).  They are narrowed / widened on the host by a few threads
+// next to pinned staging buffers, so only 1 byte per variable and 4 bytes per
+// count entry cross PCIe.
 // ---------------------------------------------------------------------------
-__global__ void k_scatter_values_i64(int64_t V, const int64_t *in, const int32_t *old2new, const int32_t *v_card,
-                                     nb_val_t *val, int *bad)
+template <class F>
+static void host_parallel(int64_t n, F fn)
+{
+    int nt = n > (1 << 18) ? (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    int64_t chunk = ((n + nt - 1) / nt + 63) & ~63ll;
+    for (int t = 0; t < nt; t++) {
+        int64_t a = t * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([=] { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
+
+__global__ void k_scatter_values_u8(int64_t V, const uint8_t *in, const int32_t *old2new, const int32_t *v_card,
+                                    nb_val_t *val, int *bad)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= V) return;
-    int64_t x = in[v];
-    if (x < 0 || x >= v_card[v]) { *bad = 1; x = 0; }
+    int x = in[v];
+    if (x >= v_card[v]) { *bad = 1; x = 0; }
     val[old2new[v]] = (nb_val_t)x;
 }
 
-__global__ void k_gather_values_i64(int64_t V, const nb_val_t *val, const int32_t *old2new, int64_t *out)
+__global__ void k_gather_values_u8(int64_t V, const nb_val_t *val, const int32_t *old2new, uint8_t *out)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (v < V) out[v] = (int64_t)val[old2new[v]];
+    if (v < V) out[v] = val[old2new[v]];
 }
 
 extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
 {
     if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
     NB_CUDA(cudaSetDevice(g->device));
     const int64_t V = g->V;
-    NB_TRY(nb_ensure_xfer(g, (size_t)V * 8 + 16));
-    int *d_bad = (int *)((char *)g->d_xfer + (size_t)V * 8);
-    NB_CUDA(cudaMemcpyAsync(g->d_xfer, values, (size_t)V * 8, cudaMemcpyHostToDevice, g->stream));
+    if (V == 0) return NB_OK;
+    NB_TRY(nb_ensure_pinned(g, (size_t)V + 64));
+    NB_TRY(nb_ensure_xfer(g, (size_t)V + 64));
+    uint8_t *stage = (uint8_t *)g->h_pinned;
+    std::atomic<int> out_of_range(0);
+    host_parallel(V, [&](int64_t a, int64_t b) {
+        int bad = 0;
+        for (int64_t i = a; i < b; i++) {
+            int64_t x = values[i];
+            bad |= (x < 0) | (x > NB_MAX_CARD);
+            stage[i] = (uint8_t)x;
+        }
+        if (bad) out_of_range.store(1);
+    });
+    if (out_of_range.load()) NB_FAIL(NB_ERR_INVALID, "var_value holds entries outside [0, cardinality)");
+    int *d_bad = (int *)((char *)g->d_xfer + (((size_t)V + 15) & ~(size_t)15));
+    NB_CUDA(cudaMemcpyAsync(g->d_xfer, stage, (size_t)V, cudaMemcpyHostToDevice, g->stream));
     NB_CUDA(cudaMemsetAsync(d_bad, 0, 4, g->stream));
-    k_scatter_values_i64<<<grid_for(V), 256, 0, g->stream>>>(V, (const int64_t *)g->d_xfer, g->d_old2new, g->d_v_card,
-                                                             g->d_val[chain], d_bad);
+    k_scatter_values_u8<<<grid_for(V), 256, 0, g->stream>>>(V, (const uint8_t *)g->d_xfer, g->d_old2new, g->d_v_card,
+                                                            g->d_val[chain], d_bad);
     int bad = 0;
     NB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
@@ -120,12 +156,17 @@ extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
 extern "C" int nb_get_var_values(nb_graph *g, int chain, int64_t *values)
 {
     if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
     NB_CUDA(cudaSetDevice(g->device));
     const int64_t V = g->V;
-    NB_TRY(nb_ensure_xfer(g, (size_t)V * 8));
-    k_gather_values_i64<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_val[chain], g->d_old2new, (int64_t *)g->d_xfer);
-    NB_CUDA(cudaMemcpyAsync(values, g->d_xfer, (size_t)V * 8, cudaMemcpyDeviceToHost, g->stream));
+    if (V == 0) return NB_OK;
+    NB_TRY(nb_ensure_pinned(g, (size_t)V + 64));
+    NB_TRY(nb_ensure_xfer(g, (size_t)V + 64));
+    k_gather_values_u8<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_val[chain], g->d_old2new, (uint8_t *)g->d_xfer);
+    NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)V, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
+    const uint8_t *stage = (const uint8_t *)g->h_pinned;
+    host_parallel(V, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; i++) values[i] = (int64_t)stage[i]; });
     return NB_OK;
 }
 
@@ -147,50 +188,55 @@ extern "C" int nb_get_weights(nb_graph *g, double *weights)
 
 extern "C" int nb_reset_counts(nb_graph *g)
 {
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
     NB_CUDA(cudaSetDevice(g->device));
     NB_CUDA(cudaMemsetAsync(g->d_count, 0, (size_t)g->count_entries * 4, g->stream));
     return NB_OK;
 }
 
-// new-order int32 tallies -> reference cstart layout, int64
+// new-order tallies -> reference cstart layout (still int32; widened on the host)
 __global__ void k_counts_to_old(int64_t V, const int32_t *count, const uint32_t *cstart_new, const int64_t *cstart_old,
-                                const int32_t *old2new, const int32_t *v_card, int64_t *out)
+                                const int32_t *old2new, const int32_t *v_card, int32_t *out)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= V) return;
     int n = v_card[v] == 2 ? 1 : v_card[v];
     uint32_t s = cstart_new[old2new[v]];
     int64_t d = cstart_old[v];
-    for (int j = 0; j < n; j++) out[d + j] = (int64_t)count[s + j];
+    for (int j = 0; j < n; j++) out[d + j] = count[s + j];
+}
+
+static int fetch_counts(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double divisor)
+{
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
+    NB_CUDA(cudaSetDevice(g->device));
+    const int64_t n = g->count_entries;
+    if (n == 0) return NB_OK;
+    NB_TRY(nb_ensure_xfer(g, (size_t)n * 4));
+    NB_TRY(nb_ensure_pinned(g, (size_t)n * 4));
+    k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_cstart, g->d_cstart_old, g->d_old2new,
+                                                            g->d_v_card, (int32_t *)g->d_xfer);
+    NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)n * 4, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    const int32_t *src = (const int32_t *)g->h_pinned;
+    host_parallel(n, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            int64_t c = accumulate ? counts[i] + src[i] : (int64_t)src[i];
+            counts[i] = c;
+            if (marginals) marginals[i] = (double)c / divisor;
+        }
+    });
+    return NB_OK;
 }
 
 extern "C" int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate)
 {
-    NB_CUDA(cudaSetDevice(g->device));
-    const int64_t n = g->count_entries;
-    if (n == 0) return NB_OK;
-    NB_TRY(nb_ensure_xfer(g, (size_t)n * 8));
-    k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_cstart, g->d_cstart_old, g->d_old2new,
-                                                            g->d_v_card, (int64_t *)g->d_xfer);
-    if (!accumulate) {
-        NB_CUDA(cudaMemcpyAsync(counts, g->d_xfer, (size_t)n * 8, cudaMemcpyDeviceToHost, g->stream));
-        NB_CUDA(cudaStreamSynchronize(g->stream));
-        return NB_OK;
-    }
-    NB_TRY(nb_ensure_pinned(g, (size_t)n * 8));
-    NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)n * 8, cudaMemcpyDeviceToHost, g->stream));
-    NB_CUDA(cudaStreamSynchronize(g->stream));
-    const int64_t *src = (const int64_t *)g->h_pinned;
-    int nt = n > (1 << 20) ? (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    std::vector<std::thread> th;
-    int64_t chunk = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; t++) {
-        int64_t a = t * chunk, b = std::min(n, a + chunk);
-        if (a >= b) break;
-        th.emplace_back([=] { for (int64_t i = a; i < b; i++) counts[i] += src[i]; });
-    }
-    for (auto &t : th) t.join();
-    return NB_OK;
+    return fetch_counts(g, counts, accumulate, nullptr, 1.0);
+}
+
+extern "C" int nb_get_counts_marginals(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double epochs)
+{
+    return fetch_counts(g, counts, accumulate, marginals, epochs);
 }
 
 // ---------------------------------------------------------------------------

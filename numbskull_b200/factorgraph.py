@@ -143,27 +143,48 @@ class FactorGraph(object):
                                             _lib.ptr(offs), _lib.ptr(out), len(out)))
         return out
 
-    def _upload(self, var_copy, weight_copy):
-        L, g = _lib.lib(), self._device_graph()
-        _lib.check(L.nb_set_var_values(g, 0, _lib.ptr(_lib.contiguous(self.var_value[var_copy], np.int64))))
-        _lib.check(L.nb_set_var_values(g, 1, _lib.ptr(_lib.contiguous(self.var_value_evid[var_copy], np.int64))))
-        _lib.check(L.nb_set_weights(g, _lib.ptr(_lib.contiguous(self.weight_value[weight_copy], np.float64))))
+    def _row(self, arr, copy, dtype):
+        """The caller-visible row `arr[copy]` as a C-contiguous array the library can read AND
+        write in place (true for arrays built by __init__; anything else goes through a copy)."""
+        row = arr[copy]
+        if row.dtype == dtype and row.flags.c_contiguous and row.flags.writeable:
+            return row, None
+        tmp = np.ascontiguousarray(row, dtype=dtype)
+        return tmp, row
 
-    def _download(self, var_copy, weight_copy, evid=False, weights=False, counts=False):
-        L, g = _lib.lib(), self._g
-        buf = np.empty(self.variable.shape[0], np.int64)
-        _lib.check(L.nb_get_var_values(g, 0, _lib.ptr(buf)))
-        self.var_value[var_copy][:] = buf
+    def _upload(self, var_copy, weight_copy, evid=True):
+        L, g = _lib.lib(), self._device_graph()
+        _lib.check(L.nb_set_var_values(g, 0, _lib.ptr(self._row(self.var_value, var_copy, np.int64)[0])))
         if evid:
-            _lib.check(L.nb_get_var_values(g, 1, _lib.ptr(buf)))
-            self.var_value_evid[var_copy][:] = buf
+            _lib.check(L.nb_set_var_values(g, 1, _lib.ptr(self._row(self.var_value_evid, var_copy, np.int64)[0])))
+        _lib.check(L.nb_set_weights(g, _lib.ptr(self._row(self.weight_value, weight_copy, np.float64)[0])))
+
+    def _download(self, var_copy, weight_copy, evid=False, weights=False, counts=False, epochs=0):
+        L, g = _lib.lib(), self._g
+
+        def fetch(arr, copy, dtype, call):
+            buf, dst = self._row(arr, copy, dtype)
+            _lib.check(call(_lib.ptr(buf)))
+            if dst is not None:
+                dst[:] = buf
+
+        fetch(self.var_value, var_copy, np.int64, lambda p: L.nb_get_var_values(g, 0, p))
+        if evid:
+            fetch(self.var_value_evid, var_copy, np.int64, lambda p: L.nb_get_var_values(g, 1, p))
         if weights:
-            w = np.empty(self.weight.shape[0], np.float64)
-            _lib.check(L.nb_get_weights(g, _lib.ptr(w)))
-            self.weight_value[weight_copy][:] = w
+            fetch(self.weight_value, weight_copy, np.float64, lambda p: L.nb_get_weights(g, p))
         if counts:
             assert self.count.dtype == np.int64 and self.count.flags.c_contiguous
-            _lib.check(L.nb_get_counts(g, _lib.ptr(self.count), 1))
+            if epochs:
+                # count += tally and marginals = count / epochs (factorgraph.py:172-173) in one host pass
+                m = self.marginals
+                if not (isinstance(m, np.ndarray) and m.dtype == np.float64 and m.shape == self.count.shape
+                        and m.flags.c_contiguous and m.flags.writeable):
+                    m = np.empty(self.count.shape, np.float64)
+                _lib.check(L.nb_get_counts_marginals(g, _lib.ptr(self.count), 1, _lib.ptr(m), float(epochs)))
+                self.marginals = m
+            else:
+                _lib.check(L.nb_get_counts(g, _lib.ptr(self.count), 1))
 
     def clear(self):
         """factorgraph.py:75-78 (the thread pool's role is played by the device graph)."""
@@ -233,7 +254,7 @@ class FactorGraph(object):
         if diagnostics:
             print("FACTOR " + str(self.fid) + ": STARTED BURN-IN...")
         if not _resident:
-            self._upload(var_copy, weight_copy)
+            self._upload(var_copy, weight_copy, evid=False)
         self._sweeps(epochs, True, sample_evidence)
         if not _resident:
             self._download(var_copy, weight_copy)
@@ -244,7 +265,7 @@ class FactorGraph(object):
                   diagnostics=False, var_copy=0, weight_copy=0):
         """factorgraph.py:145-175."""
         L = _lib.lib()
-        self._upload(var_copy, weight_copy)
+        self._upload(var_copy, weight_copy, evid=False)     # the Gibbs sweep only touches chain 0
         if burnin_epochs > 0:
             self.burnIn(burnin_epochs, sample_evidence, diagnostics=diagnostics,
                         var_copy=var_copy, weight_copy=weight_copy, _resident=True)
@@ -263,11 +284,9 @@ class FactorGraph(object):
                 self._sweeps(epochs, False, sample_evidence)
             self.inference_epoch_time = timer.interval / epochs
             self.inference_total_time += timer.interval
-        self._download(var_copy, weight_copy, counts=True)
+        self._download(var_copy, weight_copy, counts=True, epochs=epochs)
         if diagnostics:
             print("FACTOR " + str(self.fid) + ": DONE WITH INFERENCE")
-        if epochs != 0:
-            self.marginals = self.count / float(epochs)
         if diagnostics:
             self.diagnostics(epochs)
 

@@ -264,14 +264,12 @@ class PartitionedGibbs(object):
     def inference(self, burnin_epochs, epochs, sample_evidence=True):
         """FactorGraph.inference for the owned block; returns the owned marginals."""
         fg, L = self.fg, self.lib.lib()
-        fg._upload(0, 0)
+        fg._upload(0, 0, evid=False)
         self.sweeps(burnin_epochs, True, sample_evidence)
         self.lib.check(L.nb_reset_counts(fg._g))
         self.sweeps(epochs, False, sample_evidence)
         self.torch.cuda.synchronize()
-        fg._download(0, 0, counts=True)
-        if epochs:
-            fg.marginals = fg.count / float(epochs)
+        fg._download(0, 0, counts=True, epochs=epochs)
         return fg.marginals[:fg.cstart[self.n_owned]]
 
     def inference_e2e(self, epochs):
