@@ -370,6 +370,7 @@ extern "C" int nb_gather_values_dev(nb_graph *g, int chain, const int32_t *dev_l
     if (n == 0) return NB_OK;
     NB_CUDA(cudaSetDevice(g->device));
     k_gather_u8<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_old2new, g->d_val[chain], dev_out);
+    g->launches++;
     NB_CUDA(cudaGetLastError());
     return NB_OK;
 }
@@ -380,6 +381,7 @@ extern "C" int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_
     if (n == 0) return NB_OK;
     NB_CUDA(cudaSetDevice(g->device));
     k_scatter_u8<<<grid_for(n), 256, 0, g->stream>>>(n, dev_local_ids, g->d_old2new, g->d_val[chain], dev_in);
+    g->launches++;
     NB_CUDA(cudaGetLastError());
     return NB_OK;
 }

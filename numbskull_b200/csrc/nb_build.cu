@@ -121,7 +121,7 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
             int code = G.f_code[f], a = G.f_arity[f];
             words += nb_incidence_words(G.wide, code, a, G.f_feat[f] != 1.0);
             if (ok) {   // truth-table class: arity <= 3, integer-valued function, small member domains
-                if (!nb_code_tt_ok(code) || a > 3) ok = false;
+                if (!nb_code_tt_ok(code) || a > 3 || G.f_feat[f] != 1.0) ok = false;
                 else if (!nb_code_tt_const_compare(code))
                     for (int j = 0; j < a; j++) ok &= G.v_card[G.m_vid[G.f_off[f] + j]] <= 3;
             }
@@ -392,20 +392,21 @@ __global__ void k_tt_slice_width(int64_t n_slices, const int32_t *new2old, const
     quads[s] = (int64_t)w * 32;
 }
 
-__global__ void k_tt_pad(uint4 *tt, int64_t n)
+__global__ void k_tt_pad(uint4 *tt, uint32_t *base, int64_t n)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) tt[i] = make_uint4(0u, 0u, NB_TT_NEUTRAL, 0u);
+    if (i < n) { tt[i] = make_uint4(0u, 0u, NB_TT_NEUTRAL | NB_TT_FIXED_BIT, 0u); base[i] = NB_TT_BASE_NEUTRAL; }
 }
 
 __global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, const int64_t *tt_ptr, uint4 *tt,
-                          const uint8_t *wfixed)
+                          uint32_t *tt_base, const uint8_t *wfixed)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= G.V || G.v_evid[v] == 4) return;
     const int64_t nid = old2new[v];
     if (nid >= n_frows) return;
     uint4 *row = tt + tt_ptr[nid >> 5] + (nid & 31);
+    uint32_t *brow = tt_base + tt_ptr[nid >> 5] + (nid & 31);
     const int64_t off = G.b_off[G.v_vtf[v]];
     const int len = G.b_len[G.v_vtf[v]];
     for (int e = 0; e < len; e++) {
@@ -425,19 +426,22 @@ __global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, c
             int m = nb_code_abstain_member(code);
             extra = m < a ? G.v_card[G.m_vid[mo + m]] - 1 : 0;
         }
-        uint32_t table = 0;
+        uint32_t table = 0, base = 0;
         for (int xa = 0; xa < 3; xa++)
             for (int xb = 0; xb < 3; xb++) {
                 NbFastStats st;
                 st.reset();
                 st.extra = extra;
                 for (int j = 0; j < a; j++) st.member(j, a, slot[j] < 0, slot[j] < 0 ? 0 : (slot[j] == 0 ? xa : xb));
-                int d = (int)(st.value(code, 1) - st.value(code, 0));
+                int f0 = (int)st.value(code, 0);
+                int d = (int)st.value(code, 1) - f0;
                 table |= (uint32_t)(d + 2) << (3 * (3 * xa + xb));
+                base |= (uint32_t)(f0 + 1) << (2 * (3 * xa + xb));
             }
         const uint32_t wid = (uint32_t)G.f_wid[f];
         if (wfixed[wid]) table |= NB_TT_FIXED_BIT;
         row[(size_t)e * 32] = make_uint4(other[0], other[1], table, wid);
+        brow[(size_t)e * 32] = base;
     }
 }
 
@@ -827,6 +831,31 @@ int nb_build_finalize(nb_graph *g)
         NB_CUDA(cudaStreamSynchronize(g->stream));
         NB_TRY(nb_alloc(g, &g->d_wwords, (size_t)g->n_wwords));
         NB_TRY(nb_alloc(g, &g->d_inc, (size_t)g->n_inc));
+        // tasks: at most NB_WARP_TASK incidences of one row each
+        std::vector<int64_t> inc_ptr((size_t)nw + 1), task_ptr((size_t)nw + 1, 0);
+        NB_CUDA(cudaMemcpyAsync(inc_ptr.data(), g->d_inc_ptr, ((size_t)nw + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        std::vector<int32_t> task_row, task_beg;
+        for (int64_t r = 0; r < nw; r++) {
+            int64_t n = inc_ptr[(size_t)r + 1] - inc_ptr[(size_t)r];
+            task_ptr[(size_t)r] = (int64_t)task_row.size();
+            for (int64_t b = 0; b < std::max<int64_t>(n, 1); b += NB_WARP_TASK) {
+                task_row.push_back((int32_t)r);
+                task_beg.push_back((int32_t)b);
+            }
+        }
+        task_ptr[(size_t)nw] = (int64_t)task_row.size();
+        g->n_wtasks = (int64_t)task_row.size();
+        g->wpart_stride = g->max_card > 4 ? ((g->max_card + 3) & ~3) : 4;
+        NB_TRY(upload(g, &g->d_wtask_row, task_row));
+        NB_TRY(upload(g, &g->d_wtask_beg, task_beg));
+        NB_TRY(upload(g, &g->d_wtask_ptr, task_ptr));
+        NB_TRY(nb_alloc(g, &g->d_wpart, (size_t)g->n_wtasks * (size_t)g->wpart_stride));
+        for (int c = 0; c < nc; c++) {
+            NbColorRange &cr = g->colors[(size_t)c];
+            cr.k_beg = (int32_t)task_ptr[(size_t)cr.w_beg];
+            cr.k_end = (int32_t)task_ptr[(size_t)cr.w_end];
+        }
     }
     k_fill_rows<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_trows, g->d_slice_ptr, g->d_twords,
                                                     g->d_wrow_ptr, g->d_wwords, g->d_inc_ptr, g->d_inc, g->d_wfixed);
@@ -842,9 +871,11 @@ int nb_build_finalize(nb_graph *g)
         NB_CUDA(cudaMemcpyAsync(&g->n_tt_quads, g->d_tt_ptr + nfs, 8, cudaMemcpyDeviceToHost, g->stream));
         NB_CUDA(cudaStreamSynchronize(g->stream));
         NB_TRY(nb_alloc(g, &g->d_tt, (size_t)g->n_tt_quads + 1, false));
+        NB_TRY(nb_alloc(g, &g->d_tt_base, (size_t)g->n_tt_quads + 1, false));
         if (g->n_tt_quads) {
-            k_tt_pad<<<grid_for(g->n_tt_quads), 256, 0, g->stream>>>(g->d_tt, g->n_tt_quads);
-            k_fill_tt<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_tt_ptr, g->d_tt, g->d_wfixed);
+            k_tt_pad<<<grid_for(g->n_tt_quads), 256, 0, g->stream>>>(g->d_tt, g->d_tt_base, g->n_tt_quads);
+            k_fill_tt<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_tt_ptr, g->d_tt, g->d_tt_base,
+                                                          g->d_wfixed);
         }
     }
     NB_CUDA(cudaGetLastError());

@@ -153,6 +153,7 @@ __host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, 
 #define NB_CLASS_FAST 0
 #define NB_CLASS_GEN 1
 #define NB_CLASS_WARP 2
+#define NB_WARP_TASK 1024   /* incidences per warp task */
 
 typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
 #define NB_MAX_CARD 255
@@ -164,6 +165,7 @@ struct NbColorRange {
     int32_t f_beg, f_end;  // FAST thread rows [f_beg, f_end) in new ids (f_beg % 32 == 0)
     int32_t t_beg, t_end;  // GEN thread rows [t_beg, t_end) in new ids (t_beg % 32 == 0)
     int32_t w_beg, w_end;  // warp-path rows, as indices into the warp-row arrays
+    int32_t k_beg, k_end;  // their tasks (slices of at most NB_WARP_TASK incidences of one row)
     int64_t edges;         // bucket entries owned by this colour
     int64_t learn_visits_max;  // max over weights of gradient visits in this colour (dataType-0 upper bound)
 };
@@ -242,6 +244,7 @@ struct nb_graph {
     int64_t n_frows = 0;             // FAST rows occupy new ids [0, n_frows)
     int64_t *d_tt_ptr = nullptr;     // [n_frows/32 + 1] quad offsets into d_tt
     uint4 *d_tt = nullptr;           // truth-table stream of the FAST rows (SELL-32, one quad per incidence)
+    uint32_t *d_tt_base = nullptr;   // f(self = 0) tables, one word per quad (learning only)
     int64_t n_tt_quads = 0;
     int64_t *d_wrow_ptr = nullptr;   // [n_wrows + 1] word offsets into d_wwords
     uint32_t *d_wwords = nullptr;    // contiguous warp-path rows
@@ -249,6 +252,13 @@ struct nb_graph {
     int64_t *d_inc_ptr = nullptr;    // [n_wrows + 1] offsets into d_inc
     uint2 *d_inc = nullptr;          // per incidence of a warp row: (word offset in row, bucket value)
     int64_t n_inc = 0;
+    // long rows are cut into tasks so that one hub variable is spread over many warps
+    int32_t *d_wtask_row = nullptr;  // [n_wtasks] warp-row index
+    int32_t *d_wtask_beg = nullptr;  // [n_wtasks] first incidence (relative to the row)
+    int64_t *d_wtask_ptr = nullptr;  // [n_wrows + 1] tasks of each row
+    double *d_wpart = nullptr;       // [n_wtasks][wpart_stride] partial energies
+    int64_t n_wtasks = 0;
+    int wpart_stride = 4;
 
     // ---- state ----
     nb_val_t *d_val[2] = {nullptr, nullptr};  // [Vn] chain 0 = free, 1 = evidence
@@ -260,6 +270,7 @@ struct nb_graph {
     float *d_grad = nullptr;         // [W]
     uint32_t *d_nvis = nullptr;      // [W] visits
     uint32_t *d_ntrunc = nullptr;    // [W] truncating visits (L1)
+    int32_t *d_gradi = nullptr;      // [W] integer gradient sums (truth-table rows)
     float *d_gpart = nullptr;        // block partials
     uint32_t *d_npart = nullptr;
     uint32_t *d_tpart = nullptr;

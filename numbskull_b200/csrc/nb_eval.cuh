@@ -541,12 +541,15 @@ struct NbFastStats {
 //     { other member A (new id), other member B (new id), table, weight id }
 // where table holds, for the 3 x 3 combinations of (min(xA, 2), min(xB, 2)),
 // the 3-bit code of f(self = 1) - f(self = 0) + 2 at bit 3 * (3 * a + b); bit 27
-// = weight is fixed.  Unused member slots point at the variable itself, padding
+// = weight is fixed / padding.  Unused member slots point at the variable itself, padding
 // quads carry the all-zero-difference table, so every lane of a warp runs the
 // same trip count with no parsing at all.
 // ---------------------------------------------------------------------------
 #define NB_TT_NEUTRAL 0x2492492u   /* 9 x code 2 (difference 0) */
-#define NB_TT_FIXED_BIT (1u << 27)
+#define NB_TT_FIXED_BIT (1u << 27) /* weight is fixed (also set on padding quads): no gradient */
+// A parallel word per quad (used by the learning sweep only) holds f(self = 0) + 1 in 2 bits per
+// combination, so that f(k) = f(0) + k * (f(1) - f(0)) is available for both chains.
+#define NB_TT_BASE_NEUTRAL 0x15555u /* 9 x code 1 (value 0) */
 
 __host__ __device__ inline bool nb_code_tt_const_compare(int c)
 {

@@ -40,9 +40,14 @@ struct LearnArgs {
     // reduction targets
     float *g_grad;        // [W] global table (large-W path) or unused
     uint32_t *g_cnt;      // [W]
-    float *p_grad;        // [blocks][W] per-block partials (shared-memory path)
+    float *p_grad;        // [blocks][W] per-block partials (shared-memory path; int32 for truth-table rows)
     uint32_t *p_cnt;
     uint32_t *done;       // completion counter
+    // truth-table rows
+    const int64_t *tt_ptr;
+    const uint4 *tt;
+    const uint32_t *tt_base;
+    int32_t *gi_grad;     // [W] global integer table (large-W path)
 };
 
 // ---------------------------------------------------------------------------
@@ -121,11 +126,13 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
 // block epilogue of the shared-memory path: flush the block's table, and let
 // the last block to finish sum the partials in block order and apply the update
 // ---------------------------------------------------------------------------
-__device__ inline void nb_flush_and_apply(const LearnArgs &a, float *s_grad, uint32_t *s_cnt)
+template <class T>
+__device__ inline void nb_flush_and_apply(const LearnArgs &a, T *s_grad, uint32_t *s_cnt)
 {
     __shared__ bool s_last;
     __syncthreads();
-    float *pg = a.p_grad + (size_t)blockIdx.x * a.W;
+    T *part = reinterpret_cast<T *>(a.p_grad);
+    T *pg = part + (size_t)blockIdx.x * a.W;
     uint32_t *pc = a.p_cnt + (size_t)blockIdx.x * a.W;
     for (int w = threadIdx.x; w < a.W; w += blockDim.x) { pg[w] = s_grad[w]; pc[w] = s_cnt[w]; }
     __threadfence();
@@ -138,8 +145,8 @@ __device__ inline void nb_flush_and_apply(const LearnArgs &a, float *s_grad, uin
         if (a.wfixed[w]) continue;
         double G = 0.0;
         uint32_t n = 0;
-        for (unsigned b = 0; b < gridDim.x; b++) {
-            G += (double)__ldcg(a.p_grad + (size_t)b * a.W + w);
+        for (unsigned b = 0; b < gridDim.x; b++) {      // fixed block order: deterministic
+            G += (double)__ldcg(part + (size_t)b * a.W + w);
             n += __ldcg(a.p_cnt + (size_t)b * a.W + w);
         }
         if (G != 0.0 || n != 0)
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, 
         } else if (a.regularization != 2) cnt_inc = 0;
         nb_row_gradient<WIDE, SMEM>(r, len, self, meta, ev, prop, a, cnt_inc, sink, 0, 1, nullptr, 0);
     }
-    if (SMEM) nb_flush_and_apply(a, s_grad, s_cnt);
+    if (SMEM) nb_flush_and_apply<float>(a, s_grad, s_cnt);
 }
 
 // ---------------------------------------------------------------------------
@@ -298,7 +305,135 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, in
         } else if (a.regularization != 2) cnt_inc = 0;
         nb_row_gradient<WIDE, SMEM>(r, 0, self, meta, ev, prop, a, cnt_inc, sink, lane, 32, inc, n_inc);
     }
-    if (SMEM) nb_flush_and_apply(a, s_grad, s_cnt);
+    if (SMEM) nb_flush_and_apply<float>(a, s_grad, s_cnt);
+}
+
+// ---------------------------------------------------------------------------
+// truth-table rows (Boolean variable, arity <= 3, unit featureValue): one warp per
+// SELL slice with a uniform trip count.  f(k) = f(0) + k (f(1) - f(0)) comes from
+// the two tables, so the gradient is an INTEGER; the per-weight sums are exact and
+// independent of the order of accumulation (warp REDUX -> shared int table ->
+// per-block partials summed in block order, or an integer global table).
+// ---------------------------------------------------------------------------
+struct GradSinkI {
+    int32_t *grad;
+    uint32_t *cnt;
+    __device__ __forceinline__ void add(uint32_t wid, int g, uint32_t c)
+    {
+        if (g) atomicAdd(grad + wid, g);
+        if (c) atomicAdd(cnt + wid, c);
+    }
+};
+
+__device__ __forceinline__ int nb_tt_index(int xa, int xb) { return min(xa, 2) * 3 + min(xb, 2); }
+
+template <bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int beg, int end, uint32_t kfree,
+                                                               uint32_t kevid, uint32_t ktrunc)
+{
+    extern __shared__ unsigned char s_raw[];
+    int32_t *s_grad = (int32_t *)s_raw;
+    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(int32_t) * (size_t)(SMEM ? a.W : 0));
+    if (SMEM) {
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
+        __syncthreads();
+    }
+    GradSinkI sink{SMEM ? s_grad : a.gi_grad, SMEM ? s_cnt : a.g_cnt};
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = blockIdx.x * (int64_t)NB_LWARPS + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
+    const nb_val_t *__restrict__ vF = a.val_free;
+    const nb_val_t *__restrict__ vE = a.val_evid;
+    const double *__restrict__ weight = a.weight;
+
+    for (int64_t s = (beg >> 5) + warp_global; s < (((int64_t)end + 31) >> 5); s += n_warps) {
+        const int64_t nid = (s << 5) + lane;
+        const uint32_t meta = a.vmeta[nid];
+        const uint32_t rid = a.rng_id[nid];
+        const int evid = NB_META_EVID(meta);
+        const bool valid = nid < end && NB_META_VALID(meta) && evid != 4;       // learning.py:24-26
+        const int64_t q0 = a.tt_ptr[s];
+        const int n = (int)((a.tt_ptr[s + 1] - q0) >> 5);
+        const uint4 *qp = a.tt + q0 + lane;
+        const uint32_t *bp = a.tt_base + q0 + lane;
+
+        // ---- pass 1: e1 - e0 under both chains ----
+        double dF = 0.0, dE = 0.0;
+        for (int j = 0; j < n; j += 2) {
+            uint4 q[2];
+#pragma unroll
+            for (int t = 0; t < 2; t++)
+                q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32)
+                                   : make_uint4((uint32_t)nid, (uint32_t)nid, NB_TT_NEUTRAL | NB_TT_FIXED_BIT, 0u);
+            int xf[2][2], xe[2][2];
+            double w[2];
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                xf[t][0] = vF[q[t].x]; xf[t][1] = vF[q[t].y];
+                xe[t][0] = vE[q[t].x]; xe[t][1] = vE[q[t].y];
+                w[t] = __ldg(weight + q[t].w);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                dF = fma(w[t], (double)((int)((q[t].z >> (3 * nb_tt_index(xf[t][0], xf[t][1]))) & 7u) - 2), dF);
+                dE = fma(w[t], (double)((int)((q[t].z >> (3 * nb_tt_index(xe[t][0], xe[t][1]))) & 7u) - 2), dE);
+            }
+        }
+        // ---- both samples (learning.py:53-69) ----
+        int ev;
+        if (evid != 1) {
+            const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, kevid);
+            ev = u <= (double)(1.0f / (1.0f + __expf((float)dE))) ? 0 : 1;
+        } else {
+            ev = (int)a.vinit[nid];
+        }
+        const double uf = nb_philox2x32_u53(rid, (uint32_t)a.epoch, kfree);
+        const int prop = uf <= (double)(1.0f / (1.0f + __expf((float)dF))) ? 0 : 1;
+        if (valid) { a.val_evid[nid] = (nb_val_t)ev; a.val_free[nid] = (nb_val_t)prop; }
+        const bool active = valid && (a.learn_non_evidence || evid == 1);        // :70-71
+        uint32_t cinc = 1;
+        if (a.regularization == 1)                                                // :90
+            cinc = nb_philox2x32_u53(rid, (uint32_t)a.epoch, ktrunc) < 1.0 / a.truncation ? 1u : 0u;
+        else if (a.regularization != 2) cinc = 0;
+
+        // ---- pass 2: integer gradient of every learnable incidence (:97-125) ----
+        if (__ballot_sync(FULL, active) == 0u) continue;
+        for (int j = 0; j < n; j++) {
+            const uint4 q = __ldg(qp + (size_t)j * 32);
+            const uint32_t b = __ldg(bp + (size_t)j * 32);
+            const int iF = nb_tt_index(vF[q.x], vF[q.y]), iE = nb_tt_index(vE[q.x], vE[q.y]);
+            // this variable's own slots read its just-written values; the tables ignore them
+            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * ((int)((q.z >> (3 * iF)) & 7u) - 2);
+            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * ((int)((q.z >> (3 * iE)) & 7u) - 2);
+            const bool contrib = active && !(q.z & NB_TT_FIXED_BIT);
+            const unsigned who = __ballot_sync(FULL, contrib);
+            if (who == 0u) continue;
+            const int leader = __ffs(who) - 1;
+            const uint32_t w0 = __shfl_sync(FULL, q.w, leader);
+            if (__all_sync(FULL, !contrib || q.w == w0)) {
+                const int G = __reduce_add_sync(FULL, contrib ? fF - fE : 0);
+                const unsigned Cn = __reduce_add_sync(FULL, contrib ? cinc : 0u);
+                if (lane == leader) sink.add(w0, G, Cn);
+            } else if (contrib) {
+                sink.add(q.w, fF - fE, cinc);
+            }
+        }
+    }
+    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt);
+}
+
+__global__ void k_apply_global_int(LearnArgs a)
+{
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.W) return;
+    int G = a.gi_grad[w];
+    uint32_t n = a.g_cnt[w];
+    if (G == 0 && n == 0u) return;
+    a.gi_grad[w] = 0;
+    a.g_cnt[w] = 0u;
+    if (a.wfixed[w]) return;
+    a.weight[w] = nb_apply_update(a.weight[w], (double)G, n, a.regularization, a.step, a.reg_param, a.truncation);
 }
 
 // large-W path: apply the global table and clear it
@@ -357,6 +492,7 @@ static LearnArgs learn_args(nb_graph *g)
     a.rng_id = g->d_rng_id; a.vinit = g->d_vinit; a.val_free = g->d_val[0]; a.val_evid = g->d_val[1];
     a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
     a.g_grad = g->d_grad; a.g_cnt = g->d_nvis; a.p_grad = g->d_gpart; a.p_cnt = g->d_npart; a.done = g->d_done;
+    a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.gi_grad = g->d_gradi;
     return a;
 }
 
@@ -365,6 +501,7 @@ static int ensure_learn_buffers(nb_graph *g, bool smem)
     if (!g->d_done) NB_TRY(nb_alloc(g, &g->d_done, 4));
     if (!g->d_grad) {
         NB_TRY(nb_alloc(g, &g->d_grad, (size_t)g->W));
+        NB_TRY(nb_alloc(g, &g->d_gradi, (size_t)g->W));
         NB_TRY(nb_alloc(g, &g->d_nvis, (size_t)g->W));
     }
     if (smem && !g->d_gpart) {
@@ -403,19 +540,29 @@ template <bool WIDE, bool SMEM>
 static int launch_learn_range(nb_graph *g, const LearnArgs &a, int fb, int fe, int tb, int te, int wb, int we)
 {
     size_t smem = SMEM ? (size_t)g->W * 8 : 0;
-    if (te > tb || fe > fb) {
-        int64_t need = ((int64_t)(te - tb) + (fe - fb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
-        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
-        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, fb, fe, tb, te);
+    const unsigned apply_grid = (unsigned)((g->W + 255) / 256);
+    if (fe > fb) {
+        int64_t need = ((((int64_t)fe + 31) >> 5) - (fb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
+        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
+        k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, fb, fe, nb_fold_key(a.seed, a.epoch, NB_TAG_FREE),
+                                                                      nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
+                                                                      nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC));
         g->launches++;
-        if (!SMEM) { k_apply_global<<<(unsigned)((g->W + 255) / 256), 256, 0, g->stream>>>(a); g->launches++; }
+        if (!SMEM) { k_apply_global_int<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
+    }
+    if (te > tb) {
+        int64_t need = ((int64_t)(te - tb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
+        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
+        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, 0, 0, tb, te);
+        g->launches++;
+        if (!SMEM) { k_apply_global<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
     }
     if (we > wb) {
         int64_t need = ((int64_t)(we - wb) + NB_LWARPS - 1) / NB_LWARPS;
         unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
         k_learn_warp<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, wb, we);
         g->launches++;
-        if (!SMEM) { k_apply_global<<<(unsigned)((g->W + 255) / 256), 256, 0, g->stream>>>(a); g->launches++; }
+        if (!SMEM) { k_apply_global<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
     }
     return NB_OK;
 }

@@ -114,12 +114,12 @@ __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__
 // ---------------------------------------------------------------------------
 #define NB_WARPS_PER_BLOCK 8
 
-// Energies of every value of the warp row `wr`, lanes striding over incidences.
-// dataType 0, card <= 4: returned in e[] on all lanes.  Otherwise the per-value
+// Energies of every value over incidences [i0, i1) of the warp row `wr`, lanes striding over
+// them.  dataType 0, card <= 4: returned in e[] on all lanes.  Otherwise the per-value
 // energies land in the warp's shared array se[0..card).
 template <bool WIDE>
 __device__ inline void nb_warp_row_energies(const uint32_t *__restrict__ wwords, const int64_t *__restrict__ wrow_ptr,
-                                            const int64_t *__restrict__ inc_ptr, const uint2 *__restrict__ inc,
+                                            const uint2 *__restrict__ inc, int64_t i0, int64_t i1,
                                             int64_t wr, uint32_t self, uint32_t meta,
                                             const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
                                             double e[4], double *se)
@@ -128,7 +128,6 @@ __device__ inline void nb_warp_row_energies(const uint32_t *__restrict__ wwords,
     const int card = NB_META_CARD(meta);
     const bool small = NB_META_DTYPE(meta) == 0 && card <= 4;
     NbRow r = nb_warp_row(wwords, wrow_ptr, wr);
-    const int64_t i0 = inc_ptr[wr], i1 = inc_ptr[wr + 1];
     if (!small) {
         for (int k = lane; k < card; k += 32) se[k] = 0.0;
         __syncwarp();
@@ -167,24 +166,70 @@ __device__ inline int nb_draw_shared(const double *se, int card, NbUniforms &rng
     return res.pick;
 }
 
+struct WarpTasks {
+    const int32_t *task_row;
+    const int32_t *task_beg;
+    const int64_t *task_ptr;
+    double *part;
+    int stride;
+};
+
+// Phase 1: one warp per task (a slice of one long row) -> partial energies.
 template <bool WIDE>
-__global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp(SweepArgs a, int wbeg, int wend)
+__global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_partial(SweepArgs a, WarpTasks t, int kbeg, int kend)
 {
     __shared__ double s_e[NB_WARPS_PER_BLOCK][NB_MAX_CARD + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t wr = (int64_t)wbeg + blockIdx.x * (int64_t)NB_WARPS_PER_BLOCK + warp;
+    const int64_t task = (int64_t)kbeg + blockIdx.x * (int64_t)NB_WARPS_PER_BLOCK + warp;
+    if (task >= kend) return;
+    const int64_t wr = t.task_row[task];
+    const int64_t nid = a.n_trows + wr;
+    const uint32_t meta = a.vmeta[nid];
+    const int evid = NB_META_EVID(meta), card = NB_META_CARD(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;
+    if (!(evid == 0 || a.sample_evidence)) return;
+    const int64_t i0 = a.inc_ptr[wr] + t.task_beg[task];
+    const int64_t i1 = min(i0 + (int64_t)NB_WARP_TASK, a.inc_ptr[wr + 1]);
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    nb_warp_row_energies<WIDE>(a.wwords, a.wrow_ptr, a.inc, i0, i1, wr, (uint32_t)nid, meta, a.val, a.weight, e, s_e[warp]);
+    double *out = t.part + (size_t)task * t.stride;
+    if (NB_META_DTYPE(meta) == 0 && card <= 4) {
+        if (lane < 4) out[lane] = lane == 0 ? e[0] : (lane == 1 ? e[1] : (lane == 2 ? e[2] : e[3]));
+    } else {
+        for (int k = lane; k < card; k += 32) out[k] = s_e[warp][k];
+    }
+}
+
+// Phase 2: one warp per row sums its tasks' partials in task order, samples, stores, tallies.
+template <bool WIDE>
+__global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_finish(SweepArgs a, WarpTasks t, int wbeg, int wend)
+{
+    __shared__ double s_e[NB_WARPS_PER_BLOCK][NB_MAX_CARD + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wr = (int64_t)wbeg + blockIdx.x * (int64_t)NB_WARPS_PER_BLOCK + warp;
     if (wr >= wend) return;
     const int64_t nid = a.n_trows + wr;
     const uint32_t meta = a.vmeta[nid];
     const int evid = NB_META_EVID(meta), card = NB_META_CARD(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;
     if (!(evid == 0 || a.sample_evidence)) return;
-    double e[4] = {0.0, 0.0, 0.0, 0.0};
-    nb_warp_row_energies<WIDE>(a.wwords, a.wrow_ptr, a.inc_ptr, a.inc, wr, (uint32_t)nid, meta, a.val, a.weight, e, s_e[warp]);
+    const int64_t t0 = t.task_ptr[wr], t1 = t.task_ptr[wr + 1];
+    for (int k = lane; k < card; k += 32) {
+        double s = 0.0;
+        for (int64_t q = t0; q < t1; q++) s += t.part[(size_t)q * t.stride + k];
+        s_e[warp][k] = s;
+    }
+    __syncwarp();
     NbUniforms rng(a.rng_id[nid], a.epoch, NB_TAG_FREE, a.seed);
     int k;
-    if (NB_META_DTYPE(meta) == 0 && card <= 4) k = nb_draw_small(e, card, rng.next());
-    else k = nb_draw_shared(s_e[warp], card, rng);
+    if (NB_META_DTYPE(meta) == 0 && card <= 4) {
+        double e[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < card) e[j] = s_e[warp][j];
+        k = nb_draw_small(e, card, rng.next());
+    } else {
+        k = nb_draw_shared(s_e[warp], card, rng);
+    }
     if (lane == 0) {
         a.val[nid] = (nb_val_t)k;
         nb_tally(a, nid, card, k);
@@ -210,10 +255,17 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
         g->launches++;
     }
     if (c.w_end > c.w_beg) {
-        unsigned grid = (unsigned)((c.w_end - c.w_beg + NB_WARPS_PER_BLOCK - 1) / NB_WARPS_PER_BLOCK);
-        if (g->wide) k_gibbs_warp<true><<<grid, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, c.w_beg, c.w_end);
-        else k_gibbs_warp<false><<<grid, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, c.w_beg, c.w_end);
-        g->launches++;
+        WarpTasks t{g->d_wtask_row, g->d_wtask_beg, g->d_wtask_ptr, g->d_wpart, g->wpart_stride};
+        unsigned grid1 = (unsigned)((c.k_end - c.k_beg + NB_WARPS_PER_BLOCK - 1) / NB_WARPS_PER_BLOCK);
+        unsigned grid2 = (unsigned)((c.w_end - c.w_beg + NB_WARPS_PER_BLOCK - 1) / NB_WARPS_PER_BLOCK);
+        if (g->wide) {
+            k_gibbs_warp_partial<true><<<grid1, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.k_beg, c.k_end);
+            k_gibbs_warp_finish<true><<<grid2, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.w_beg, c.w_end);
+        } else {
+            k_gibbs_warp_partial<false><<<grid1, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.k_beg, c.k_end);
+            k_gibbs_warp_finish<false><<<grid2, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.w_beg, c.w_end);
+        }
+        g->launches += 2;
     }
     NB_CUDA(cudaGetLastError());
     return NB_OK;

@@ -220,6 +220,37 @@ def test_marginals_match_oracle(oracle, name):
     assert np.array_equal(fg.var_value[0][ev], fg.variable["initialValue"][ev])
 
 
+def test_hub_row_is_split_into_warp_tasks(oracle):
+    """A variable with 3000 incidences (> NB_WARP_TASK) is spread over several warps."""
+    from numbskull_b200.numbskulltypes import Weight, Variable, Factor, FactorToVar
+    n = 3000
+    w = np.zeros(2, Weight)
+    w["initialValue"] = [0.004, -0.3]
+    v = np.zeros(n + 1, Variable)
+    v["cardinality"] = 2
+    f = np.zeros(n + 1, Factor)
+    f["factorFunction"] = 3            # EQUAL(hub, leaf_i)
+    f["factorFunction"][n] = 4         # ISTRUE(hub)
+    f["weightId"][n] = 1
+    f["featureValue"] = 1
+    f["arity"] = 2
+    f["arity"][n] = 1
+    f["ftv_offset"] = 2 * np.arange(n + 1)
+    fm = np.zeros(2 * n + 1, FactorToVar)
+    fm["vid"][0:2 * n:2] = 0
+    fm["vid"][1:2 * n:2] = 1 + np.arange(n)
+    fm["vid"][2 * n] = 0
+    fg = _fg_from_synth((w, v, f, fm, np.zeros(n + 1, np.bool_), 2 * n + 1), seed=8)
+    info = fg.device_info()
+    assert info["n_warp_rows"] == 1
+    og = _oracle_of(oracle, fg, seed=5)
+    assert np.allclose(fg.potentials(np.array([0])), [og.potential(0, 0), og.potential(0, 1)], rtol=1e-12)
+    fg.inference(50, 20000, sample_evidence=True)
+    og.inference(50, 20000, sample_evidence=True)
+    assert abs(fg.marginals[0] - og.marginals[0]) < 0.02
+    assert np.abs(fg.marginals[1:].mean() - og.marginals[1:].mean()) < 0.005
+
+
 def test_count_is_cumulative_and_seeded_runs_repeat():
     z = golden("run_bool_l2")
     a = _fg_from_golden(z, seed=99)

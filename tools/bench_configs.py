@@ -1,0 +1,166 @@
+#!/usr/bin/env python
+"""Throughput of the BASELINE.json configs other than the headline one
+(bench.py covers config 2).  Prints one JSON line per config:
+
+    python tools/bench_configs.py c3 [--scale 0.1]    # LF model, learning + marginals
+    python tools/bench_configs.py c4 [--scale 0.1]    # KBC-style Boolean graph, inference
+    python tools/bench_configs.py c5 [--scale 0.1]    # categorical card 16, learning + inference
+
+`--scale` multiplies the number of variables of the named config (1.0 = the
+BASELINE size).  Algorithmic bytes follow SURVEY.md section 8(d)."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numbskull_b200 as nb  # noqa: E402
+from numbskull_b200 import _lib, synth  # noqa: E402
+
+PEAK = 6535.7
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def device_time(fg, fn):
+    L, g = _lib.lib(), fg._g
+    _lib.check(L.nb_synchronize(g))
+    _lib.check(L.nb_timer_start(g))
+    fn()
+    ms = C.c_float(0)
+    _lib.check(L.nb_timer_stop(g, C.byref(ms)))
+    return ms.value * 1e-3
+
+
+def algorithmic_bytes(fg, sampled_mask, learn=False):
+    """B_inf = 16 N_v + sum_{edge evals} (20 + 5 arity) (+1 per member of categorical factors)."""
+    var, fac, vmap, fi = fg.variable, fg.factor, fg.vmap, fg.factor_index
+    nb_ = np.where(var["dataType"] == 0, 1, var["cardinality"]).astype(np.int64)
+    owner = np.repeat(np.arange(len(var)), nb_)                       # variable of every bucket
+    keep = sampled_mask[owner]
+    lens = vmap["factor_index_length"].astype(np.int64)
+    offs = vmap["factor_index_offset"].astype(np.int64)
+    total_edges = int(lens[keep].sum())
+    # arity of every bucket entry of the sampled variables
+    idx = np.repeat(offs[keep], lens[keep]) + (np.arange(total_edges) - np.repeat(np.cumsum(lens[keep]) - lens[keep], lens[keep]))
+    ar = fac["arity"][fi[idx]].astype(np.int64)
+    cat = np.isin(fac["factorFunction"][fi[idx]], (12, 14, 15, 16, 17))
+    b = 16.0 * int(sampled_mask.sum()) + float((20 + 5 * ar + cat * ar).sum())
+    return b, total_edges
+
+
+def report(name, fg, info, extra):
+    line = {"config": name, "variables": int(len(fg.variable)), "factors": int(len(fg.factor)),
+            "edges": int(info["n_edges"]), "colors": int(info["n_colors"]), "wide_headers": int(info["wide_headers"]),
+            "thread_rows": int(info["n_thread_rows"]), "warp_rows": int(info["n_warp_rows"]),
+            "device_GB": round(info["device_bytes"] / 1e9, 2), "jp_rounds": int(info["jp_rounds"]), "peak_GBs": PEAK}
+    line.update(extra)
+    print(json.dumps(line))
+    sys.stdout.flush()
+
+
+def load(g):
+    t0 = time.perf_counter()
+    ns = nb.NumbSkull(quiet=True)
+    ns.loadFactorGraph(*g)
+    fg = ns.factorGraphs[0]
+    fg.seed = 12345
+    t1 = time.perf_counter()
+    fg._device_graph()
+    t2 = time.perf_counter()
+    bad = C.c_int64(-1)
+    _lib.check(_lib.lib().nb_graph_check_coloring(fg._g, C.byref(bad)))
+    return fg, {"host_index_s": round(t1 - t0, 2), "device_build_s": round(t2 - t1, 2), "color_conflicts": int(bad.value)}
+
+
+def inference_rate(fg, sweeps, sample_evidence=True):
+    L, g = _lib.lib(), fg._g
+    fg._upload(0, 0)
+    _lib.check(L.nb_reset_counts(g))
+    _lib.check(L.nb_gibbs_sweeps(g, 3, 1, int(sample_evidence), fg.seed))
+    return device_time(fg, lambda: _lib.check(L.nb_gibbs_sweeps(g, sweeps, 0, int(sample_evidence), fg.seed))) / sweeps
+
+
+def learn_rate(fg, epochs, stepsize, reg, reg_param, lne):
+    L, g = _lib.lib(), fg._g
+    fg._upload(0, 0)
+
+    def run(n):
+        s = C.c_double(stepsize)
+        _lib.check(L.nb_learn_sweeps(g, n, C.byref(s), 1.0, reg, reg_param, 1.0, int(lne), fg.seed, 0))
+    run(1)
+    l0, l1 = C.c_int64(0), C.c_int64(0)
+    L.nb_launch_count(g, C.byref(l0))
+    dt = device_time(fg, lambda: run(epochs)) / epochs
+    L.nb_launch_count(g, C.byref(l1))
+    return dt, (l1.value - l0.value) / epochs
+
+
+def c3(scale):
+    copies, n_lf = max(1000, int(10_000_000 * scale)), 100
+    rng = np.random.default_rng(1003)
+    g = synth.lf_model(copies, n_lf, rng)
+    acc_true = None
+    fg, times = load(g)
+    info = fg.device_info()
+    every = fg.variable["isEvidence"] != 4
+    b_free, edges = algorithmic_bytes(fg, every)
+    b_evid, _ = algorithmic_bytes(fg, fg.variable["isEvidence"] != 1)
+    dt, launches = learn_rate(fg, 3, 1e-4, 1, 0.01, True)
+    fg._download(0, 0, evid=True, weights=True)
+    b_learn = b_free + (b_evid - 16.0 * int((fg.variable["isEvidence"] != 1).sum()) * 0.5) + 12.0 * edges
+    dti = inference_rate(fg, 10, sample_evidence=False)
+    q = fg.variable["isEvidence"] == 0
+    b_inf, e_inf = algorithmic_bytes(fg, q)
+    report("c3_lf_%dx%d" % (copies, n_lf), fg, info, dict(
+        times, learn_ms_per_epoch=1e3 * dt, learn_edge_evals_per_s=edges / dt, learn_launches_per_epoch=launches,
+        learn_roofline_frac=b_learn / dt / 1e9 / PEAK,
+        inference_ms_per_sweep=1e3 * dti, inference_edge_evals_per_s=e_inf / dti,
+        inference_roofline_frac=b_inf / dti / 1e9 / PEAK,
+        weights_head=[round(float(x), 4) for x in fg.weight_value[0][:6]]))
+
+
+def c4(scale):
+    nvar = max(10000, int(200_000_000 * scale))
+    g = synth.kbc(nvar, np.random.default_rng(1004))
+    fg, times = load(g)
+    info = fg.device_info()
+    every = fg.variable["isEvidence"] != 4
+    b, edges = algorithmic_bytes(fg, every)
+    dt = inference_rate(fg, 10)
+    extra = dict(times, inference_ms_per_sweep=1e3 * dt, inference_edge_evals_per_s=edges / dt,
+                 var_samples_per_s=int(every.sum()) / dt, inference_roofline_frac=b / dt / 1e9 / PEAK,
+                 algorithmic_GB_per_sweep=b / 1e9)
+    dtl, launches = learn_rate(fg, 1, 0.01, 2, 0.01, False)
+    extra.update(learn_ms_per_epoch=1e3 * dtl, learn_edge_evals_per_s=edges / dtl, learn_launches_per_epoch=launches)
+    report("c4_kbc_%d" % nvar, fg, info, extra)
+
+
+def c5(scale):
+    nvar = max(10000, int(50_000_000 * scale))
+    g = synth.categorical(nvar, 16, 3, np.random.default_rng(1005))
+    fg, times = load(g)
+    info = fg.device_info()
+    every = fg.variable["isEvidence"] != 4
+    b, edges = algorithmic_bytes(fg, every)
+    dt = inference_rate(fg, 10)
+    dtl, launches = learn_rate(fg, 2, 0.01, 2, 0.01, False)
+    report("c5_cat16_%d" % nvar, fg, info, dict(
+        times, inference_ms_per_sweep=1e3 * dt, inference_edge_evals_per_s=edges / dt,
+        var_samples_per_s=int(every.sum()) / dt, inference_roofline_frac=b / dt / 1e9 / PEAK,
+        learn_ms_per_epoch=1e3 * dtl, learn_edge_evals_per_s=edges / dtl, learn_launches_per_epoch=launches))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", choices=["c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=0.1)
+    a = ap.parse_args()
+    {"c3": c3, "c4": c4, "c5": c5}[a.config](a.scale)
