@@ -211,6 +211,18 @@ int nb_gather_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, i
 int nb_scatter_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, const int32_t *dev_in);
 /* Orders the variables and lays out the streams once every variable has its colour. */
 int nb_graph_finalize(nb_graph *g);
+/* Peer-to-peer halo exchange (ranks = processes on one NVLink node).  Each rank exports CUDA-IPC
+ * handles of its two value arrays and of a flag array (3 x 64 bytes), opens its neighbours',
+ * and installs a plan: per colour, (owned local variable, peer rank, slot in the peer's value
+ * array).  nb_p2p_exchange then pushes the colour's boundary values with NVLink peer stores and
+ * runs a flag barrier with the neighbours in the same kernel -- no NCCL, no pack / unpack. */
+int nb_p2p_export(nb_graph *g, int world, int rank, uint8_t *handles_3x64);
+int nb_p2p_open(nb_graph *g, const uint8_t *handles_world_x3x64, const int32_t *neighbours, int n_neighbours);
+int nb_p2p_local_slots(nb_graph *g, const int32_t *local_ids, int64_t n, int32_t *slots);
+int nb_p2p_set_plan(nb_graph *g, int n_colors, const int64_t *color_ptr, const int32_t *src_local,
+                    const int32_t *peer, const int32_t *dst_slot);
+int nb_p2p_exchange(nb_graph *g, int color, int chain_mask);
+int nb_p2p_check(nb_graph *g);
 /* run the sweeps on a caller-owned CUDA stream (cudaStream_t as void*) */
 int nb_set_stream(nb_graph *g, void *cuda_stream);
 int nb_begin_epoch(nb_graph *g, int64_t *epoch); /* returns and advances the sweep counter */

@@ -87,6 +87,12 @@ SIGNATURES = {
     "nb_gather_colors_dev": (C.c_int, [_P, _P, _I64, _P]),
     "nb_scatter_colors_dev": (C.c_int, [_P, _P, _I64, _P]),
     "nb_graph_finalize": (C.c_int, [_P]),
+    "nb_p2p_export": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "nb_p2p_open": (C.c_int, [_P, _P, _P, C.c_int]),
+    "nb_p2p_local_slots": (C.c_int, [_P, _P, _I64, _P]),
+    "nb_p2p_set_plan": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
+    "nb_p2p_exchange": (C.c_int, [_P, C.c_int, C.c_int]),
+    "nb_p2p_check": (C.c_int, [_P]),
     "nb_set_stream": (C.c_int, [_P, _P]),
     "nb_begin_epoch": (C.c_int, [_P, C.POINTER(_I64)]),
 }

@@ -45,6 +45,7 @@ extern "C" void nb_graph_destroy(nb_graph *g)
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
+    nb_p2p_destroy(g);
     for (void *p : g->allocs) cudaFree(p);
     if (g->d_xfer) cudaFree(g->d_xfer);
     if (g->d_flush) cudaFree(g->d_flush);

@@ -285,6 +285,7 @@ struct nb_graph {
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
 
+    void *p2p = nullptr;               // NbP2P (nb_p2p.cu)
     std::vector<int64_t> learn_vmax;   // per colour: max gradient visits of one weight
     int learn_vmax_flag = -1;
     std::vector<NbColorRange> colors;
@@ -300,6 +301,8 @@ inline int nb_alloc(nb_graph *g, T **p, size_t n, bool zero = true)
 }
 int nb_ensure_xfer(nb_graph *g, size_t bytes);
 int nb_ensure_pinned(nb_graph *g, size_t bytes);
+
+void nb_p2p_destroy(nb_graph *g);
 
 // build steps (nb_build.cu)
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);

@@ -241,10 +241,59 @@ class PartitionedGibbs(object):
             send, recv = self.plan.restrict(colors == c)
             self.halo.append(Exchange(send, recv, rank, world, torch.uint8, self.dev, group))
         self.halo_bytes_per_sweep = sum(h.n_send for h in self.halo)
+        self.p2p = False
+        import os
+        if (world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("NUMBSKULL_B200_P2P", "1") != "0"):
+            self._setup_p2p(colors)
+
+    def _setup_p2p(self, colors):
+        """Peer-to-peer halo: owners store boundary values straight into the neighbours' ghost
+        slots over NVLink (CUDA IPC mappings) and synchronise with a flag barrier in the kernel."""
+        L, lib, dist, g = self.lib.lib(), self.lib, self.dist, self.fg._g
+        world, rank = self.world, self.rank
+        handles = np.zeros(3 * 64, np.uint8)
+        lib.check(L.nb_p2p_export(g, world, rank, lib.ptr(handles)))
+        # slots (new ids) of my ghosts, per owner, in the order the owner sends them
+        my_slots = []
+        for p in range(world):
+            ids = np.ascontiguousarray(self.plan.recv_ids[p], dtype=np.int32)
+            out = np.zeros(len(ids), np.int32)
+            if len(ids):
+                lib.check(L.nb_p2p_local_slots(g, lib.ptr(ids), len(ids), lib.ptr(out)))
+            my_slots.append(out.tolist())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (handles.tobytes(), my_slots), group=self.group)
+        neigh = [p for p in range(world) if p != rank and (len(self.plan.send_ids[p]) or len(self.plan.recv_ids[p]))]
+        allh = np.zeros((world, 3 * 64), np.uint8)
+        for p in range(world):
+            allh[p] = np.frombuffer(gathered[p][0], np.uint8)
+        nb_arr = np.asarray(neigh, np.int32)
+        lib.check(L.nb_p2p_open(g, lib.ptr(allh), lib.ptr(nb_arr) if len(neigh) else None, len(neigh)))
+        src, peer, dst, ptr = [], [], [], [0]
+        for c in range(self.n_colors):
+            for p in range(world):
+                ids = self.plan.send_ids[p]
+                if not len(ids):
+                    continue
+                sel = colors[ids] == c
+                remote = np.asarray(gathered[p][1][rank], np.int32)     # p's slots for what I send it
+                src.append(ids[sel].astype(np.int32))
+                dst.append(remote[sel])
+                peer.append(np.full(int(sel.sum()), p, np.int32))
+            ptr.append(ptr[-1] + (sum(len(x) for x in src) - ptr[-1]))
+        cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.int32), dtype=np.int32)  # noqa: E731
+        src, peer, dst = cat(src), cat(peer), cat(dst)
+        ptr = np.asarray(ptr, np.int64)
+        lib.check(L.nb_p2p_set_plan(g, self.n_colors, lib.ptr(ptr), lib.ptr(src), lib.ptr(peer), lib.ptr(dst)))
+        dist.barrier(group=self.group)
+        self.p2p = True
 
     # -- device helpers
     def _exchange(self, c, chain):
         L, g, lib = self.lib.lib(), self.fg._g, self.lib
+        if self.p2p:
+            lib.check(L.nb_p2p_exchange(g, c, 1 << chain))
+            return
         self.halo[c].run(
             lambda ids, out: lib.check(L.nb_gather_values_dev(g, chain, ids.data_ptr(), ids.numel(), out.data_ptr())),
             lambda ids, buf: lib.check(L.nb_scatter_values_dev(g, chain, ids.data_ptr(), ids.numel(), buf.data_ptr())))
@@ -269,6 +318,8 @@ class PartitionedGibbs(object):
         self.lib.check(L.nb_reset_counts(fg._g))
         self.sweeps(epochs, False, sample_evidence)
         self.torch.cuda.synchronize()
+        if self.p2p:
+            self.lib.check(L.nb_p2p_check(fg._g))
         fg._download(0, 0, counts=True, epochs=epochs)
         return fg.marginals[:fg.cstart[self.n_owned]]
 
@@ -293,8 +344,11 @@ class PartitionedGibbs(object):
                                                  float(truncation), int(bool(learn_non_evidence)), fg.seed,
                                                  ep.value, int(fg.batch_visits)))
                 if self.world > 1:
-                    self._exchange(c, 0)
-                    self._exchange(c, 1)
+                    if self.p2p:
+                        lib.check(L.nb_p2p_exchange(g, c, 3))
+                    else:
+                        self._exchange(c, 0)
+                        self._exchange(c, 1)
             if self.world > 1:
                 torch.cuda.synchronize()
                 host = np.empty(len(fg.weight), np.float64)
