@@ -288,7 +288,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_sweep": bytes_sweep,
-                     "kernel": "k_gibbs_tt (one launch per colour; duration = CUDA-event time of the "
+                     "kernel": "k_gibbs_tt2 (one launch per colour; duration = CUDA-event time of the "
                                "timed region / sweeps)"},
         "gpu_launches": int(launches if runner is None else launches),
         "clocks": clocks.summary(),

@@ -192,19 +192,23 @@ extern "C" int nb_reset_counts(nb_graph *g)
     if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
     NB_CUDA(cudaSetDevice(g->device));
     NB_CUDA(cudaMemsetAsync(g->d_count, 0, (size_t)g->count_entries * 4, g->stream));
+    NB_CUDA(cudaMemsetAsync(g->d_count_b, 0, (size_t)g->Vn * 4, g->stream));
     return NB_OK;
 }
 
 // new-order tallies -> reference cstart layout (still int32; widened on the host)
-__global__ void k_counts_to_old(int64_t V, const int32_t *count, const uint32_t *cstart_new, const int64_t *cstart_old,
-                                const int32_t *old2new, const int32_t *v_card, int32_t *out)
+// (Boolean rows sampled by the truth-table kernels tally into count_b[new id].)
+__global__ void k_counts_to_old(int64_t V, const int32_t *count, const int32_t *count_b, const uint32_t *cstart_new,
+                                const int64_t *cstart_old, const int32_t *old2new, const int32_t *v_card, int32_t *out)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= V) return;
     int n = v_card[v] == 2 ? 1 : v_card[v];
-    uint32_t s = cstart_new[old2new[v]];
+    int nid = old2new[v];
+    uint32_t s = cstart_new[nid];
     int64_t d = cstart_old[v];
     for (int j = 0; j < n; j++) out[d + j] = count[s + j];
+    if (v_card[v] == 2) out[d] += count_b[nid];
 }
 
 static int fetch_counts(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double divisor)
@@ -215,8 +219,8 @@ static int fetch_counts(nb_graph *g, int64_t *counts, int accumulate, double *ma
     if (n == 0) return NB_OK;
     NB_TRY(nb_ensure_xfer(g, (size_t)n * 4));
     NB_TRY(nb_ensure_pinned(g, (size_t)n * 4));
-    k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_cstart, g->d_cstart_old, g->d_old2new,
-                                                            g->d_v_card, (int32_t *)g->d_xfer);
+    k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
+                                                            g->d_old2new, g->d_v_card, (int32_t *)g->d_xfer);
     NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)n * 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
     const int32_t *src = (const int32_t *)g->h_pinned;

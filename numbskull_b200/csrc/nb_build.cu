@@ -112,6 +112,7 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
     uint64_t words = 0, inc = 0;
     int nb = nbuckets(G, v);
     bool ok = G.v_dtype[v] == 0 && G.v_card[v] == 2;
+    bool pair = true;
     for (int b = 0; b < nb; b++) {
         int64_t off = G.b_off[G.v_vtf[v] + b];
         int len = G.b_len[G.v_vtf[v] + b];
@@ -124,6 +125,9 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
                 if (!nb_code_tt_ok(code) || a > 3 || G.f_feat[f] != 1.0) ok = false;
                 else if (!nb_code_tt_const_compare(code))
                     for (int j = 0; j < a; j++) ok &= G.v_card[G.m_vid[G.f_off[f] + j]] <= 3;
+                int others = 0;
+                for (int j = 0; j < a && j < 3; j++) others += G.m_vid[G.f_off[f] + j] != v;
+                pair &= others <= 1 && (uint32_t)G.f_wid[f] <= NB_PAIR_MAX_WID;
             }
         }
         inc += len;
@@ -131,7 +135,7 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
     if (words > 0x7FFFFFFFull || inc > 0x7FFFFFFFull) { *overflow = 1; words = 0; inc = 0; }
     rowlen[v] = (uint32_t)words;
     ninc[v] = (uint32_t)inc;
-    fast[v] = ok ? 1 : 0;
+    fast[v] = ok ? (pair ? 2 : 1) : 0;
 }
 
 __host__ __device__ inline uint64_t nb_mix64(uint64_t x)
@@ -233,7 +237,8 @@ __global__ void k_sort_keys(int64_t V, const int32_t *color, const int8_t *v_evi
     const bool ghost = v_evid[v] == 4 || color[v] < 0;
     int c = ghost ? n_colors : color[v];
     uint32_t len = rowlen[v];
-    int cls = len > (uint32_t)warp_row_words ? NB_CLASS_WARP : (fast[v] ? NB_CLASS_FAST : NB_CLASS_GEN);
+    int cls = len > (uint32_t)warp_row_words ? NB_CLASS_WARP
+                                             : (fast[v] == 2 ? NB_CLASS_PAIR : (fast[v] == 1 ? NB_CLASS_FAST : NB_CLASS_GEN));
     if (ghost) cls = NB_CLASS_GEN;
     uint64_t window = ((uint64_t)v >> sigma_shift) & ((1ull << 28) - 1);
     uint64_t l = len < (1u << 20) ? len : (1u << 20) - 1;
@@ -260,7 +265,7 @@ __global__ void k_assign_ids(int64_t V, const uint64_t *keys, const int32_t *sor
     int v = sorted_ids[i];
     old2new[v] = (int32_t)nid;
     new2old[nid] = v;
-    vmeta[nid] = nb_pack_meta(G.v_card[v], G.v_evid[v], G.v_dtype[v], 1, cls == NB_CLASS_FAST, rowlen[v]);
+    vmeta[nid] = nb_pack_meta(G.v_card[v], G.v_evid[v], G.v_dtype[v], 1, cls <= NB_CLASS_FAST, rowlen[v]);
     rowlen_new[nid] = rowlen[v];
     nb_val_t init = (nb_val_t)v_init[v];
     vinit[nid] = init;
@@ -442,6 +447,66 @@ __global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, c
         if (wfixed[wid]) table |= NB_TT_FIXED_BIT;
         row[(size_t)e * 32] = make_uint4(other[0], other[1], table, wid);
         brow[(size_t)e * 32] = base;
+    }
+}
+
+// ---- pair stream of the PAIR rows -----------------------------------------------------------
+__global__ void k_tt2_slice_width(int64_t n_slices, const int32_t *new2old, const uint32_t *ninc, int64_t *quads)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    uint32_t w = 0;
+    for (int l = 0; l < 32; l++) {
+        int v = new2old[s * 32 + l];
+        if (v >= 0) w = max(w, ninc[v]);
+    }
+    quads[s] = (int64_t)((w + 1) / 2) * 32;
+}
+
+__global__ void k_tt2_pad(uint4 *tt2, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const uint32_t w = nb_pack_pair(NB_PAIR_NEUTRAL, 1, 0u);
+    if (i < n) tt2[i] = make_uint4(0u, w, 0u, w);
+}
+
+__global__ void k_fill_tt2(RawGraph G, const int32_t *old2new, int64_t n_prows, const int64_t *tt2_ptr, uint4 *tt2,
+                           const uint8_t *wfixed)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || G.v_evid[v] == 4) return;
+    const int64_t nid = old2new[v];
+    if (nid >= n_prows) return;
+    uint4 *row = tt2 + tt2_ptr[nid >> 5] + (nid & 31);
+    const int64_t off = G.b_off[G.v_vtf[v]];
+    const int len = G.b_len[G.v_vtf[v]];
+    for (int e = 0; e < len; e++) {
+        const int f = G.fi[off + e];
+        const int code = G.f_code[f], a = G.f_arity[f];
+        const int64_t mo = G.f_off[f];
+        bool isself[3] = {true, true, true};
+        uint32_t other = (uint32_t)nid;
+        for (int j = 0; j < a; j++) {
+            int u = G.m_vid[mo + j];
+            if (u != v) { isself[j] = false; other = (uint32_t)old2new[u]; }
+        }
+        int extra = 0;
+        if (nb_code_has_extra(code)) {
+            int m = nb_code_abstain_member(code);
+            extra = m < a ? G.v_card[G.m_vid[mo + m]] - 1 : 0;
+        }
+        uint32_t table = 0;
+        for (int x = 0; x < 3; x++) {
+            NbFastStats st;
+            st.reset();
+            st.extra = extra;
+            for (int j = 0; j < a; j++) st.member(j, a, isself[j], isself[j] ? 0 : x);
+            int d = (int)st.value(code, 1) - (int)st.value(code, 0);
+            table |= (uint32_t)(d + 2) << (3 * x);
+        }
+        const uint32_t wid = (uint32_t)G.f_wid[f];
+        uint2 *slot = reinterpret_cast<uint2 *>(row + (size_t)(e >> 1) * 32) + (e & 1);
+        *slot = make_uint2(other, nb_pack_pair(table, wfixed[wid], wid));
     }
 }
 
@@ -700,7 +765,7 @@ int nb_build_finalize(nb_graph *g)
         NB_CUDA(cudaStreamSynchronize(g->stream));
         g->n_colors = maxc + 1;
     }
-    const int nc = g->n_colors, ng = 3 * (nc + 1);
+    const int nc = g->n_colors, ng = 4 * (nc + 1);
     if (nc >= 0x3FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 16382)", nc);
 
     // ---- ordering ----
@@ -726,11 +791,11 @@ int nb_build_finalize(nb_graph *g)
     NB_CUDA(cudaMemcpyAsync(cedges.data(), d_color_edges, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
 
-    // groups in sorted order: FAST colours 0..nc, GEN colours 0..nc (nc = ghosts), WARP colours 0..nc
+    // groups in sorted order: PAIR, FAST, GEN (colours 0..nc each, nc = ghosts), then WARP
     std::vector<int64_t> gstart((size_t)ng), gbase((size_t)ng);
     g->colors.assign((size_t)nc, NbColorRange());
     int64_t pos = 0, nid = 0;
-    for (int cls = 0; cls < 2; cls++) {
+    for (int cls = 0; cls < 3; cls++) {
         for (int c = 0; c <= nc; c++) {
             size_t gi = (size_t)(cls * (nc + 1) + c);
             gstart[gi] = pos;
@@ -738,18 +803,21 @@ int nb_build_finalize(nb_graph *g)
             gbase[gi] = nid;
             if (c < nc) {
                 NbColorRange &cr = g->colors[(size_t)c];
-                if (cls == NB_CLASS_FAST) { cr.f_beg = (int32_t)nid; cr.f_end = (int32_t)(nid + (int64_t)gcount[gi]); }
-                else { cr.t_beg = (int32_t)nid; cr.t_end = (int32_t)(nid + (int64_t)gcount[gi]); }
+                int32_t b = (int32_t)nid, e = (int32_t)(nid + (int64_t)gcount[gi]);
+                if (cls == NB_CLASS_PAIR) { cr.p_beg = b; cr.p_end = e; }
+                else if (cls == NB_CLASS_FAST) { cr.f_beg = b; cr.f_end = e; }
+                else { cr.t_beg = b; cr.t_end = e; }
             }
             pos += (int64_t)gcount[gi];
             nid += (int64_t)gcount[gi];
         }
+        if (cls == NB_CLASS_PAIR) { nid = (nid + 31) & ~31ll; g->n_prows = nid; }
         if (cls == NB_CLASS_FAST) { nid = (nid + 31) & ~31ll; g->n_frows = nid; }
     }
     g->n_trows = (nid + 31) & ~31ll;
     int64_t wr = 0;
     for (int c = 0; c <= nc; c++) {
-        size_t gi = (size_t)(2 * (nc + 1) + c);
+        size_t gi = (size_t)(3 * (nc + 1) + c);
         gstart[gi] = pos;
         gbase[gi] = g->n_trows + wr;
         if (c < nc) { g->colors[(size_t)c].w_beg = (int32_t)wr; g->colors[(size_t)c].w_end = (int32_t)(wr + (int64_t)gcount[gi]); g->colors[(size_t)c].edges = (int64_t)cedges[(size_t)c]; }
@@ -799,6 +867,7 @@ int nb_build_finalize(nb_graph *g)
             NB_FAIL(NB_ERR_UNSUPPORTED, "count array of %lld entries unsupported (new layout %u)", (long long)total, total_new);
         g->count_entries = total;
         NB_TRY(nb_alloc(g, &g->d_count, (size_t)total));
+        NB_TRY(nb_alloc(g, &g->d_count_b, (size_t)Vn));
     }
 
     // ---- SELL-32 slices (thread path) ----
@@ -876,6 +945,22 @@ int nb_build_finalize(nb_graph *g)
             k_tt_pad<<<grid_for(g->n_tt_quads), 256, 0, g->stream>>>(g->d_tt, g->d_tt_base, g->n_tt_quads);
             k_fill_tt<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_tt_ptr, g->d_tt, g->d_tt_base,
                                                           g->d_wfixed);
+        }
+    }
+    // ---- pair stream (PAIR rows = new ids [0, n_prows)) ----
+    {
+        const int64_t nps = g->n_prows / 32;
+        int64_t *d_q;
+        NB_TRY(nb_alloc(g, &d_q, (size_t)nps + 1));
+        NB_TRY(nb_alloc(g, &g->d_tt2_ptr, (size_t)nps + 1));
+        if (nps) k_tt2_slice_width<<<grid_for(nps), 256, 0, g->stream>>>(nps, g->d_new2old, d_ninc, d_q);
+        NB_TRY(exclusive_scan(g, d_q, g->d_tt2_ptr, nps + 1));
+        NB_CUDA(cudaMemcpyAsync(&g->n_tt2_quads, g->d_tt2_ptr + nps, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        NB_TRY(nb_alloc(g, &g->d_tt2, (size_t)g->n_tt2_quads + 1, false));
+        if (g->n_tt2_quads) {
+            k_tt2_pad<<<grid_for(g->n_tt2_quads), 256, 0, g->stream>>>(g->d_tt2, g->n_tt2_quads);
+            k_fill_tt2<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_tt2_ptr, g->d_tt2, g->d_wfixed);
         }
     }
     NB_CUDA(cudaGetLastError());

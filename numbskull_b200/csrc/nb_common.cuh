@@ -150,9 +150,11 @@ __host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, 
 // Row classes.  FAST: Boolean variable (dataType 0, cardinality 2) whose incidences all have
 // arity <= 3 and a tabulable function -- sampled from the truth-table stream by k_gibbs_tt;
 // GEN: any other row short enough for one thread; WARP: long rows, one per warp.
-#define NB_CLASS_FAST 0
-#define NB_CLASS_GEN 1
-#define NB_CLASS_WARP 2
+#define NB_CLASS_PAIR 0   /* FAST rows whose incidences all have at most one other member: 8-byte records */
+#define NB_CLASS_FAST 1
+#define NB_CLASS_GEN 2
+#define NB_CLASS_WARP 3
+#define NB_PAIR_MAX_WID ((1u << 22) - 1)
 #define NB_WARP_TASK 1024   /* incidences per warp task */
 
 typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
@@ -162,6 +164,7 @@ typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
 // device graph
 // ----------------------------------------------------------------------------
 struct NbColorRange {
+    int32_t p_beg, p_end;  // PAIR rows [p_beg, p_end) in new ids (p_beg % 32 == 0)
     int32_t f_beg, f_end;  // FAST thread rows [f_beg, f_end) in new ids (f_beg % 32 == 0)
     int32_t t_beg, t_end;  // GEN thread rows [t_beg, t_end) in new ids (t_beg % 32 == 0)
     int32_t w_beg, w_end;  // warp-path rows, as indices into the warp-row arrays
@@ -241,7 +244,12 @@ struct nb_graph {
     int64_t *d_slice_ptr = nullptr;  // [n_trows/32 + 1] QUAD (16-byte) offsets into d_twords
     uint32_t *d_twords = nullptr;    // SELL-32 thread-path stream: quad q of lane l at quad index ptr + q*32 + l
     int64_t n_twords = 0;
-    int64_t n_frows = 0;             // FAST rows occupy new ids [0, n_frows)
+    int64_t n_prows = 0;             // PAIR rows occupy new ids [0, n_prows)
+    int64_t *d_tt2_ptr = nullptr;    // [n_prows/32 + 1] quad offsets into d_tt2
+    uint4 *d_tt2 = nullptr;          // pair stream: two 8-byte incidences {other, table:9 fixed:1 wid:22} per quad
+    int64_t n_tt2_quads = 0;
+    int32_t *d_count_b = nullptr;    // [Vn] tallies of the truth-table kernels (Boolean rows), indexed by new id
+    int64_t n_frows = 0;             // PAIR + FAST rows occupy new ids [0, n_frows)
     int64_t *d_tt_ptr = nullptr;     // [n_frows/32 + 1] quad offsets into d_tt
     uint4 *d_tt = nullptr;           // truth-table stream of the FAST rows (SELL-32, one quad per incidence)
     uint32_t *d_tt_base = nullptr;   // f(self = 0) tables, one word per quad (learning only)

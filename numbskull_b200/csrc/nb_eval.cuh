@@ -560,3 +560,13 @@ __host__ __device__ inline bool nb_code_tt_ok(int c)
     return nb_code_tt_const_compare(c) || c == C_EQUAL || c == C_LINEAR || c == C_LOGICAL ||
            (c >= C_DP_CLASS_PRIOR && c <= C_DP_DEP_SIMILAR);
 }
+
+// Pair records (NB_CLASS_PAIR): incidences with at most ONE other member take 8 bytes,
+//     { other member (new id, or the variable itself), table:9 | fixed:1 | wid:22 }
+// table = 3-bit code of f(1) - f(0) + 2 for min(x_other, 2) in {0, 1, 2}; two records per quad.
+#define NB_PAIR_NEUTRAL 0x92u          /* 3 x code 2 */
+#define NB_PAIR_FIXED_BIT (1u << 9)
+__host__ __device__ inline uint32_t nb_pack_pair(uint32_t table9, int fixed, uint32_t wid)
+{
+    return table9 | ((uint32_t)fixed << 9) | (wid << 10);
+}

@@ -519,13 +519,13 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
     NB_TRY(nb_alloc(g, &d_max, 1));
     for (int c = 0; c < g->n_colors; c++) {
         const NbColorRange &cr = g->colors[(size_t)c];
-        int64_t n = (cr.f_end - cr.f_beg) + (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
+        int64_t n = (cr.f_end - cr.p_beg) + (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
         if (n == 0) continue;
         NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
         NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
         unsigned grid = (unsigned)((n + 255) / 256);
-        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, cr.f_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
-        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, cr.f_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, cr.p_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, cr.p_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
         k_max_u32<<<64, 256, 0, g->stream>>>(g->d_nvis, (int)g->W, d_max);
         uint32_t m = 0;
         NB_CUDA(cudaMemcpyAsync(&m, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
@@ -537,14 +537,17 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
 }
 
 template <bool WIDE, bool SMEM>
-static int launch_learn_range(nb_graph *g, const LearnArgs &a, int fb, int fe, int tb, int te, int wb, int we)
+static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int tb, int te, int wb, int we)
 {
     size_t smem = SMEM ? (size_t)g->W * 8 : 0;
     const unsigned apply_grid = (unsigned)((g->W + 255) / 256);
-    if (fe > fb) {
-        int64_t need = ((((int64_t)fe + 31) >> 5) - (fb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
+    const int tt_range[2][2] = {{pb, pe}, {fb, fe}};                // PAIR rows, then FAST rows: both have TT quads
+    for (int pass = 0; pass < 2; pass++) {
+        const int rb = tt_range[pass][0], re = tt_range[pass][1];
+        if (re <= rb) continue;
+        int64_t need = ((((int64_t)re + 31) >> 5) - (rb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
         unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
-        k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, fb, fe, nb_fold_key(a.seed, a.epoch, NB_TAG_FREE),
+        k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, rb, re, nb_fold_key(a.seed, a.epoch, NB_TAG_FREE),
                                                                       nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
                                                                       nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC));
         g->launches++;
@@ -587,21 +590,22 @@ static int learn_one_color(nb_graph *g, const LearnArgs &a, int c, int64_t vmax_
     const bool smem = g->W <= NB_LEARN_SMEM_W;
     const NbColorRange &cr = g->colors[(size_t)c];
     int64_t chunks = std::max<int64_t>(1, (vmax_c + bv - 1) / bv);
-    int64_t nf = cr.f_end - cr.f_beg, nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
-    chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(nf, std::max(nt, nw))));
+    int64_t np = cr.p_end - cr.p_beg, nf = cr.f_end - cr.f_beg, nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
+    chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(std::max(np, nf), std::max(nt, nw))));
     auto cut = [](int beg, int64_t n, int64_t k, int64_t parts, int end) {
         return k >= parts ? end : beg + (int)((n * k / parts) & ~31ll);
     };
     for (int64_t k = 0; k < chunks; k++) {
+        int pb = cut(cr.p_beg, np, k, chunks, cr.p_end), pe = cut(cr.p_beg, np, k + 1, chunks, cr.p_end);
         int fb = cut(cr.f_beg, nf, k, chunks, cr.f_end), fe = cut(cr.f_beg, nf, k + 1, chunks, cr.f_end);
         int tb = cut(cr.t_beg, nt, k, chunks, cr.t_end), te = cut(cr.t_beg, nt, k + 1, chunks, cr.t_end);
         int wb = cr.w_beg + (int)(nw * k / chunks), we = cr.w_beg + (int)(nw * (k + 1) / chunks);
         if (g->wide) {
-            if (smem) NB_TRY((launch_learn_range<true, true>(g, a, fb, fe, tb, te, wb, we)));
-            else NB_TRY((launch_learn_range<true, false>(g, a, fb, fe, tb, te, wb, we)));
+            if (smem) NB_TRY((launch_learn_range<true, true>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
+            else NB_TRY((launch_learn_range<true, false>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
         } else {
-            if (smem) NB_TRY((launch_learn_range<false, true>(g, a, fb, fe, tb, te, wb, we)));
-            else NB_TRY((launch_learn_range<false, false>(g, a, fb, fe, tb, te, wb, we)));
+            if (smem) NB_TRY((launch_learn_range<false, true>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
+            else NB_TRY((launch_learn_range<false, false>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
         }
     }
     return NB_OK;

@@ -19,6 +19,7 @@ struct SweepArgs {
     const uint32_t *rng_id;
     const uint32_t *cstart;
     int32_t *count;
+    int32_t *count_b;
     nb_val_t *val;
     const double *weight;
     int64_t n_trows;
@@ -31,7 +32,7 @@ static SweepArgs sweep_args(nb_graph *g, int chain, int burnin, int sample_evide
     SweepArgs a;
     a.vmeta = g->d_vmeta; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
     a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
-    a.rng_id = g->d_rng_id; a.cstart = g->d_cstart; a.count = g->d_count; a.val = g->d_val[chain];
+    a.rng_id = g->d_rng_id; a.cstart = g->d_cstart; a.count = g->d_count; a.count_b = g->d_count_b; a.val = g->d_val[chain];
     a.weight = g->d_weight; a.n_trows = g->n_trows; a.seed = seed; a.epoch = epoch;
     a.burnin = burnin; a.sample_evidence = sample_evidence;
     return a;
@@ -71,7 +72,6 @@ __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__
     // independent loads first: they overlap with the stream
     const uint32_t meta = a.vmeta[nid];
     const uint32_t rid = a.rng_id[nid];
-    const uint32_t cs = a.cstart[nid];
     const int64_t q0 = tt_ptr[nid >> 5], q1 = tt_ptr[(nid >> 5) + 1];
     const int n = (int)((q1 - q0) >> 5);                      // incidences of the longest row of this slice
     const uint4 *qp = tt + q0 + (nid & 31);
@@ -106,7 +106,53 @@ __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__
     const float p0 = 1.0f / (1.0f + __expf((float)d));
     const int k = u <= (double)p0 ? 0 : 1;
     a.val[nid] = (nb_val_t)k;
-    if (!a.burnin) a.count[cs] += k;                         // inference.py:30-31
+    if (!a.burnin) a.count_b[nid] += k;                      // inference.py:30-31
+}
+
+// PAIR rows: 8-byte records, two per quad.
+#define NB_TT2_UNROLL 2
+__global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *__restrict__ tt2_ptr,
+                                                   const uint4 *__restrict__ tt2, int beg, int end, uint32_t key)
+{
+    const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (nid >= end) return;
+    const uint32_t meta = a.vmeta[nid];
+    const uint32_t rid = a.rng_id[nid];
+    const int64_t q0 = tt2_ptr[nid >> 5], q1 = tt2_ptr[(nid >> 5) + 1];
+    const int n = (int)((q1 - q0) >> 5);                      // quads of the longest row of this slice
+    const uint4 *qp = tt2 + q0 + (nid & 31);
+    const nb_val_t *__restrict__ vals = a.val;
+    const double *__restrict__ weight = a.weight;
+    const uint32_t neutral = nb_pack_pair(NB_PAIR_NEUTRAL, 1, 0u);
+    double d = 0.0;                                           // e1 - e0
+    for (int j = 0; j < n; j += NB_TT2_UNROLL) {
+        uint4 q[NB_TT2_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT2_UNROLL; t++)
+            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4((uint32_t)nid, neutral, (uint32_t)nid, neutral);
+        int x0[NB_TT2_UNROLL], x1[NB_TT2_UNROLL];
+        double w0[NB_TT2_UNROLL], w1[NB_TT2_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT2_UNROLL; t++) {
+            x0[t] = (int)vals[q[t].x];
+            x1[t] = (int)vals[q[t].z];
+            w0[t] = __ldg(weight + (q[t].y >> 10));
+            w1[t] = __ldg(weight + (q[t].w >> 10));
+        }
+#pragma unroll
+        for (int t = 0; t < NB_TT2_UNROLL; t++) {
+            d = fma(w0[t], (double)((int)((q[t].y >> (3 * min(x0[t], 2))) & 7u) - 2), d);
+            d = fma(w1[t], (double)((int)((q[t].w >> (3 * min(x1[t], 2))) & 7u) - 2), d);
+        }
+    }
+    const int evid = NB_META_EVID(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
+    if (!(evid == 0 || a.sample_evidence)) return;          // :24
+    const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, key);
+    const float p0 = 1.0f / (1.0f + __expf((float)d));
+    const int k = u <= (double)p0 ? 0 : 1;
+    a.val[nid] = (nb_val_t)k;
+    if (!a.burnin) a.count_b[nid] += k;                      // inference.py:30-31
 }
 
 // ---------------------------------------------------------------------------
@@ -242,6 +288,12 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     if (color >= g->n_colors) return NB_OK;   // partitioned graphs: a colour this rank does not own
     const NbColorRange &c = g->colors[(size_t)color];
     SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
+    if (c.p_end > c.p_beg) {
+        unsigned grid = (unsigned)((c.p_end - c.p_beg + 255) / 256);
+        uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
+        k_gibbs_tt2<<<grid, 256, 0, g->stream>>>(a, g->d_tt2_ptr, g->d_tt2, c.p_beg, c.p_end, key);
+        g->launches++;
+    }
     if (c.f_end > c.f_beg) {
         unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
