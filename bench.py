@@ -64,7 +64,7 @@ def ncu_traffic():
     p = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_gibbs_thread_bytes_per_sweep")
+            return json.load(open(p)).get("k_gibbs_tt2_bytes_per_sweep")
         except Exception:
             pass
     return None
