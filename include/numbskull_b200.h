@@ -168,8 +168,9 @@ int nb_gibbs_sweeps(nb_graph *g, int64_t n_epochs, int burnin, int sample_eviden
 /* run_pool(learnthread) x n_epochs with stepsize *= decay after each
  * (factorgraph.py:188-206); *stepsize is updated to the final value.
  * Both chains are sampled in one sweep; gradients are reduced by weight id
- * and applied once per mini-batch of at most `batch_visits` visits per weight
- * (0 = default policy, see DESIGN.md "learning"). */
+ * and applied once per mini-batch (a block of consecutive variable ids holding
+ * at most `batch_visits` visits of any weight; 0 = default policy 0.25 / stepsize,
+ * see DESIGN.md "learning"). */
 int nb_learn_sweeps(nb_graph *g, int64_t n_epochs, double *stepsize, double decay,
                     int regularization, double reg_param, double truncation,
                     int learn_non_evidence, uint64_t seed, int64_t batch_visits);
@@ -198,17 +199,27 @@ int nb_gather_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, i
                          uint8_t *dev_out);
 int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_local_ids, int64_t n,
                           const uint8_t *dev_in);
-/* One colour of a learning sweep (both chains + gradient reduction + weight update for the
- * colour's mini-batches); the caller exchanges both chains' boundary values afterwards. */
-int nb_learn_color_phase(nb_graph *g, int color, double stepsize, int regularization, double reg_param,
-                         double truncation, int learn_non_evidence, uint64_t seed, int64_t epoch,
-                         int64_t batch_visits);
+/* Learning walks the graph in `n_blocks` blocks of consecutive variable ids (mini-batches) and,
+ * inside a block, colour by colour.  nb_learn_blocks gives the block count the library would use
+ * for this step size (partitioned graphs: take the MAX over ranks).  nb_learn_color_phase runs one
+ * (block, colour) cell: both chains, gradient reduction by weight id, weight update; the caller
+ * exchanges both chains' boundary values afterwards. */
+int nb_learn_blocks(nb_graph *g, double stepsize, int learn_non_evidence, int64_t batch_visits, int *n_blocks);
+int nb_learn_color_phase(nb_graph *g, int color, int block, int n_blocks, double stepsize, int regularization,
+                         double reg_param, double truncation, int learn_non_evidence, uint64_t seed, int64_t epoch);
 /* Distributed Jones-Plassmann (graphs created with deferred_coloring): one round over the
  * owned, still uncoloured variables; ghosts are consulted through the colours last scattered
  * in.  *remaining = owned variables still uncoloured after the round. */
 int nb_color_round(nb_graph *g, int64_t *remaining);
 int nb_gather_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, int32_t *dev_out);
 int nb_scatter_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, const int32_t *dev_in);
+/* Colour order = visiting order.  Single-GPU graphs are relabelled so that colours are visited in
+ * increasing order of the smallest variable id they contain (the chromatic analogue of the
+ * reference's ascending-id scan); partitioned graphs do the same globally: min_ids[c] = smallest
+ * GLOBAL id among this rank's owned variables of colour c (INT64_MAX if none), reduced with MIN
+ * over the ranks by the caller, who then installs the permutation map[old colour] = new colour. */
+int nb_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids);
+int nb_relabel_colors(nb_graph *g, const int32_t *map, int n);
 /* Orders the variables and lays out the streams once every variable has its colour. */
 int nb_graph_finalize(nb_graph *g);
 /* Peer-to-peer halo exchange (ranks = processes on one NVLink node).  Each rank exports CUDA-IPC

@@ -391,14 +391,21 @@ extern "C" int nb_scatter_values_dev(nb_graph *g, int chain, const int32_t *dev_
     return NB_OK;
 }
 
-extern "C" int nb_learn_color_phase(nb_graph *g, int color, double stepsize, int regularization, double reg_param,
-                                    double truncation, int learn_non_evidence, uint64_t seed, int64_t epoch,
-                                    int64_t batch_visits)
+extern "C" int nb_learn_color_phase(nb_graph *g, int color, int block, int n_blocks, double stepsize, int regularization,
+                                    double reg_param, double truncation, int learn_non_evidence, uint64_t seed,
+                                    int64_t epoch)
 {
     NB_CUDA(cudaSetDevice(g->device));
     NB_TRY(check_runnable(g));
-    return nb_learn_color(g, color, stepsize, regularization, reg_param, truncation, learn_non_evidence, seed,
-                          (uint64_t)epoch, batch_visits);
+    return nb_learn_color(g, color, block, n_blocks, stepsize, regularization, reg_param, truncation,
+                          learn_non_evidence, seed, (uint64_t)epoch);
+}
+
+extern "C" int nb_learn_blocks(nb_graph *g, double stepsize, int learn_non_evidence, int64_t batch_visits, int *n_blocks)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    return nb_learn_block_count(g, stepsize, learn_non_evidence, batch_visits, n_blocks);
 }
 
 extern "C" int nb_color_round(nb_graph *g, int64_t *remaining)
@@ -406,6 +413,18 @@ extern "C" int nb_color_round(nb_graph *g, int64_t *remaining)
     NB_CUDA(cudaSetDevice(g->device));
     if (g->finalized) { *remaining = 0; return NB_OK; }
     return nb_build_color_round(g, remaining);
+}
+
+extern "C" int nb_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    return nb_build_color_min_ids(g, n_colors, min_ids);
+}
+
+extern "C" int nb_relabel_colors(nb_graph *g, const int32_t *map, int n)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    return nb_build_relabel_colors(g, map, n);
 }
 
 extern "C" int nb_graph_finalize(nb_graph *g)

@@ -220,6 +220,22 @@ __global__ void k_check_coloring(RawGraph G, const int32_t *color, unsigned long
     if (bad) atomicAdd(conflicts, bad);
 }
 
+// smallest GLOBAL id of the owned variables of each colour
+__global__ void k_color_min_id(RawGraph G, const int32_t *color, int n_colors, unsigned long long *min_id)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || G.v_evid[v] == 4) return;
+    int c = color[v];
+    if (c < 0 || c >= n_colors) return;
+    atomicMin(&min_id[c], (unsigned long long)(G.gid ? G.gid[v] : v));
+}
+
+__global__ void k_relabel_colors(int64_t V, int32_t *color, const int32_t *map, int n)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v < V && color[v] >= 0 && color[v] < n) color[v] = map[color[v]];
+}
+
 __global__ void k_max_color(int64_t V, const int32_t *color, int *maxc)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -272,6 +288,22 @@ __global__ void k_assign_ids(int64_t V, const uint64_t *keys, const int32_t *sor
     val0[nid] = init;
     val1[nid] = init;
     rng_id[nid] = (uint32_t)(G.gid ? (uint64_t)G.gid[v] : (uint64_t)v);
+}
+
+// first new id of every (group, id-window) run of the sorted order (-1 where a window is empty)
+__global__ void k_window_starts(int64_t V, const uint64_t *keys, int n_colors, const int64_t *group_start,
+                                const int64_t *group_base, int64_t n_win, int32_t *win_start)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const uint64_t key = keys[i];
+    const int g = (int)(key >> 62) * (n_colors + 1) + (int)((key >> 48) & 0x3FFF);
+    const int64_t w = (int64_t)((key >> 20) & ((1ull << 28) - 1));
+    if (i > 0) {
+        const uint64_t prev = keys[i - 1];
+        if ((prev >> 48) == (key >> 48) && ((prev >> 20) & ((1ull << 28) - 1)) == (uint64_t)w) return;
+    }
+    win_start[(size_t)g * (size_t)(n_win + 1) + (size_t)w] = (int32_t)(group_base[g] + (i - group_start[g]));
 }
 
 __global__ void k_count_entries(int64_t Vn, const uint32_t *vmeta, uint32_t *entries)
@@ -554,93 +586,123 @@ static int extract_and_upload(nb_graph *g, const nb_graph_desc *d)
         if (bad.compare_exchange_strong(expected, 1)) snprintf(msg, sizeof(msg), "%s (index %lld)", what, (long long)idx);
     };
 
+    // Each section is validated, narrowed into SoA columns by host threads, uploaded and
+    // freed before the next one starts, so the host peak stays at one section.
     // ---- variables ----
-    std::vector<int8_t> v_evid(V), v_dtype(V);
-    std::vector<int32_t> v_card(V), v_init(V);
-    std::vector<int64_t> v_vtf(V);
-    parallel_for(V, [&](int64_t a, int64_t b) {
-        int mc = 1, cat = 0;
-        for (int64_t i = a; i < b; i++) {
-            const nb_variable_rec &r = d->variable[i];
-            if (r.dataType != 0 && r.dataType != 1) { fail("variable dataType must be 0 or 1", i); continue; }
-            if (r.cardinality < 1 || r.cardinality > NB_MAX_CARD) { fail("variable cardinality outside [1, 255]", i); continue; }
-            if (r.initialValue < 0 || r.initialValue >= r.cardinality) { fail("variable initialValue outside [0, cardinality)", i); continue; }
-            int64_t nb = r.dataType == 0 ? 1 : r.cardinality;
-            if (r.vtf_offset < 0 || r.vtf_offset + nb > NV) { fail("variable vtf_offset out of range", i); continue; }
-            v_evid[i] = r.isEvidence; v_dtype[i] = (int8_t)r.dataType;
-            v_card[i] = (int32_t)r.cardinality; v_init[i] = (int32_t)r.initialValue; v_vtf[i] = r.vtf_offset;
-            mc = std::max(mc, (int)r.cardinality);
-            cat |= r.dataType == 1;
-        }
-        int cur = maxcard.load();
-        while (mc > cur && !maxcard.compare_exchange_weak(cur, mc)) {}
-        if (cat) anycat.store(1);
-    });
+    {
+        std::vector<int8_t> v_evid(V), v_dtype(V);
+        std::vector<int32_t> v_card(V), v_init(V);
+        std::vector<int64_t> v_vtf(V);
+        parallel_for(V, [&](int64_t a, int64_t b) {
+            int mc = 1, cat = 0;
+            for (int64_t i = a; i < b; i++) {
+                const nb_variable_rec &r = d->variable[i];
+                if (r.dataType != 0 && r.dataType != 1) { fail("variable dataType must be 0 or 1", i); continue; }
+                if (r.cardinality < 1 || r.cardinality > NB_MAX_CARD) { fail("variable cardinality outside [1, 255]", i); continue; }
+                if (r.initialValue < 0 || r.initialValue >= r.cardinality) { fail("variable initialValue outside [0, cardinality)", i); continue; }
+                int64_t nb = r.dataType == 0 ? 1 : r.cardinality;
+                if (r.vtf_offset < 0 || r.vtf_offset + nb > NV) { fail("variable vtf_offset out of range", i); continue; }
+                v_evid[i] = r.isEvidence; v_dtype[i] = (int8_t)r.dataType;
+                v_card[i] = (int32_t)r.cardinality; v_init[i] = (int32_t)r.initialValue; v_vtf[i] = r.vtf_offset;
+                mc = std::max(mc, (int)r.cardinality);
+                cat |= r.dataType == 1;
+            }
+            int cur = maxcard.load();
+            while (mc > cur && !maxcard.compare_exchange_weak(cur, mc)) {}
+            if (cat) anycat.store(1);
+        });
+        if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+        NB_TRY(upload(g, &g->d_v_evid, v_evid));
+        NB_TRY(upload(g, &g->d_v_dtype, v_dtype));
+        NB_TRY(upload(g, &g->d_v_card, v_card));
+        NB_TRY(upload(g, &g->d_v_init, v_init));
+        NB_TRY(upload(g, &g->d_v_vtf, v_vtf));
+    }
     // ---- buckets ----
-    std::vector<int64_t> b_off(NV);
-    std::vector<int32_t> b_len(NV);
     std::atomic<int64_t> edges(0);
-    parallel_for(NV, [&](int64_t a, int64_t b) {
-        int64_t sum = 0;
-        for (int64_t i = a; i < b; i++) {
-            const nb_vtf_rec &r = d->vmap[i];
-            if (r.factor_index_length < 0 || r.factor_index_offset < 0 ||
-                r.factor_index_offset + r.factor_index_length > NFI || r.factor_index_length > 0x7FFFFFFF) {
-                fail("vmap bucket outside factor_index", i);
-                continue;
+    {
+        std::vector<int64_t> b_off(NV);
+        std::vector<int32_t> b_len(NV);
+        parallel_for(NV, [&](int64_t a, int64_t b) {
+            int64_t sum = 0;
+            for (int64_t i = a; i < b; i++) {
+                const nb_vtf_rec &r = d->vmap[i];
+                if (r.factor_index_length < 0 || r.factor_index_offset < 0 ||
+                    r.factor_index_offset + r.factor_index_length > NFI || r.factor_index_length > 0x7FFFFFFF) {
+                    fail("vmap bucket outside factor_index", i);
+                    continue;
+                }
+                b_off[i] = r.factor_index_offset;
+                b_len[i] = (int32_t)r.factor_index_length;
+                sum += r.factor_index_length;
             }
-            b_off[i] = r.factor_index_offset;
-            b_len[i] = (int32_t)r.factor_index_length;
-            sum += r.factor_index_length;
-        }
-        edges += sum;
-    });
-    std::vector<int32_t> fi(NFI);
-    parallel_for(NFI, [&](int64_t a, int64_t b) {
-        for (int64_t i = a; i < b; i++) {
-            int64_t f = d->factor_index[i];
-            // entries beyond a bucket's de-duplicated length are scratch; clamp instead of failing
-            fi[i] = (f >= 0 && f < F) ? (int32_t)f : 0;
-        }
-    });
+            edges += sum;
+        });
+        if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+        NB_TRY(upload(g, &g->d_b_off, b_off));
+        NB_TRY(upload(g, &g->d_b_len, b_len));
+    }
+    {
+        std::vector<int32_t> fi(NFI);
+        parallel_for(NFI, [&](int64_t a, int64_t b) {
+            for (int64_t i = a; i < b; i++) {
+                int64_t f = d->factor_index[i];
+                // entries beyond a bucket's de-duplicated length are scratch; clamp instead of failing
+                fi[i] = (f >= 0 && f < F) ? (int32_t)f : 0;
+            }
+        });
+        NB_TRY(upload(g, &g->d_fi, fi));
+    }
     // ---- factors ----
-    std::vector<uint8_t> f_code(F);
-    std::vector<int32_t> f_wid(F), f_arity(F);
-    std::vector<double> f_feat(F);
-    std::vector<int64_t> f_off(F);
-    parallel_for(F, [&](int64_t a, int64_t b) {
-        int ma = 0, cat = 0;
-        for (int64_t i = a; i < b; i++) {
-            const nb_factor_rec &r = d->factor[i];
-            int code = nb_code_of_func(r.factorFunction);
-            if (code == C_UNKNOWN) {
-                int64_t cur = unknown.load();
-                while ((cur < 0 || i < cur) && !unknown.compare_exchange_weak(cur, i)) {}
+    {
+        std::vector<uint8_t> f_code(F);
+        std::vector<int32_t> f_wid(F), f_arity(F);
+        std::vector<double> f_feat(F);
+        std::vector<int64_t> f_off(F);
+        parallel_for(F, [&](int64_t a, int64_t b) {
+            int ma = 0, cat = 0;
+            for (int64_t i = a; i < b; i++) {
+                const nb_factor_rec &r = d->factor[i];
+                int code = nb_code_of_func(r.factorFunction);
+                if (code == C_UNKNOWN) {
+                    int64_t cur = unknown.load();
+                    while ((cur < 0 || i < cur) && !unknown.compare_exchange_weak(cur, i)) {}
+                }
+                if (r.weightId < 0 || r.weightId >= W) { fail("factor weightId out of range", i); continue; }
+                if (r.arity < 0 || r.arity >= (1 << 24) || r.ftv_offset < 0 || r.ftv_offset + r.arity > NF) { fail("factor fmap range out of bounds", i); continue; }
+                f_code[i] = (uint8_t)code; f_wid[i] = (int32_t)r.weightId; f_arity[i] = (int32_t)r.arity;
+                f_feat[i] = r.featureValue; f_off[i] = r.ftv_offset;
+                ma = std::max(ma, (int)r.arity);
+                cat |= nb_code_has_eq(code);
             }
-            if (r.weightId < 0 || r.weightId >= W) { fail("factor weightId out of range", i); continue; }
-            if (r.arity < 0 || r.arity >= (1 << 24) || r.ftv_offset < 0 || r.ftv_offset + r.arity > NF) { fail("factor fmap range out of bounds", i); continue; }
-            f_code[i] = (uint8_t)code; f_wid[i] = (int32_t)r.weightId; f_arity[i] = (int32_t)r.arity;
-            f_feat[i] = r.featureValue; f_off[i] = r.ftv_offset;
-            ma = std::max(ma, (int)r.arity);
-            cat |= nb_code_has_eq(code);
-        }
-        int cur = maxarity.load();
-        while (ma > cur && !maxarity.compare_exchange_weak(cur, ma)) {}
-        if (cat) anycat.store(1);
-    });
+            int cur = maxarity.load();
+            while (ma > cur && !maxarity.compare_exchange_weak(cur, ma)) {}
+            if (cat) anycat.store(1);
+        });
+        if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+        NB_TRY(upload(g, &g->d_f_code, f_code));
+        NB_TRY(upload(g, &g->d_f_wid, f_wid));
+        NB_TRY(upload(g, &g->d_f_arity, f_arity));
+        NB_TRY(upload(g, &g->d_f_feat, f_feat));
+        NB_TRY(upload(g, &g->d_f_off, f_off));
+    }
     // ---- members ----
-    std::vector<int32_t> m_vid(NF), m_eq;
     const bool need_eq = anycat.load() != 0;
-    if (need_eq) m_eq.resize(NF);
-    parallel_for(NF, [&](int64_t a, int64_t b) {
-        for (int64_t i = a; i < b; i++) {
-            const nb_ftv_rec &r = d->fmap[i];
-            if (r.vid < 0 || r.vid >= V) { fail("fmap vid out of range", i); continue; }
-            m_vid[i] = (int32_t)r.vid;
-            if (need_eq) m_eq[i] = (int32_t)std::min<int64_t>(std::max<int64_t>(r.dense_equal_to, -1), 0x7FFFFFFF);
-        }
-    });
-    if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+    {
+        std::vector<int32_t> m_vid(NF), m_eq;
+        if (need_eq) m_eq.resize(NF);
+        parallel_for(NF, [&](int64_t a, int64_t b) {
+            for (int64_t i = a; i < b; i++) {
+                const nb_ftv_rec &r = d->fmap[i];
+                if (r.vid < 0 || r.vid >= V) { fail("fmap vid out of range", i); continue; }
+                m_vid[i] = (int32_t)r.vid;
+                if (need_eq) m_eq[i] = (int32_t)std::min<int64_t>(std::max<int64_t>(r.dense_equal_to, -1), 0x7FFFFFFF);
+            }
+        });
+        if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+        NB_TRY(upload(g, &g->d_m_vid, m_vid));
+        if (need_eq) NB_TRY(upload(g, &g->d_m_eq, m_eq));
+    }
 
     g->n_edges = edges.load();
     g->max_card = maxcard.load();
@@ -651,22 +713,6 @@ static int extract_and_upload(nb_graph *g, const nb_graph_desc *d)
         g->unknown_func_factor = unknown.load();
         g->unknown_func_id = d->factor[unknown.load()].factorFunction;
     }
-
-    NB_TRY(upload(g, &g->d_v_evid, v_evid));
-    NB_TRY(upload(g, &g->d_v_dtype, v_dtype));
-    NB_TRY(upload(g, &g->d_v_card, v_card));
-    NB_TRY(upload(g, &g->d_v_init, v_init));
-    NB_TRY(upload(g, &g->d_v_vtf, v_vtf));
-    NB_TRY(upload(g, &g->d_b_off, b_off));
-    NB_TRY(upload(g, &g->d_b_len, b_len));
-    NB_TRY(upload(g, &g->d_fi, fi));
-    NB_TRY(upload(g, &g->d_f_code, f_code));
-    NB_TRY(upload(g, &g->d_f_wid, f_wid));
-    NB_TRY(upload(g, &g->d_f_arity, f_arity));
-    NB_TRY(upload(g, &g->d_f_feat, f_feat));
-    NB_TRY(upload(g, &g->d_f_off, f_off));
-    NB_TRY(upload(g, &g->d_m_vid, m_vid));
-    if (need_eq) NB_TRY(upload(g, &g->d_m_eq, m_eq));
     if (d->global_vid) {
         std::vector<int64_t> gid(d->global_vid, d->global_vid + V);
         NB_TRY(upload(g, &g->d_gid, gid));
@@ -721,12 +767,64 @@ static int color_graph(nb_graph *g, const nb_graph_desc *d)
     return NB_OK;
 }
 
+// Colours are visited in increasing order of the smallest (global) variable id they contain:
+// the chromatic analogue of the reference's ascending-id scan (inference.py:16-20,
+// learning.py:20-23).  It matters for learning, whose first sweep otherwise computes a whole
+// colour's gradients against neighbours that still hold their initial values.
+int nb_build_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids)
+{
+    if (n_colors <= 0) return NB_OK;
+    unsigned long long *d_min;
+    NB_CUDA(cudaMalloc(&d_min, (size_t)n_colors * 8));
+    cudaMemsetAsync(d_min, 0xFF, (size_t)n_colors * 8, g->stream);
+    k_color_min_id<<<grid_for(g->V), 256, 0, g->stream>>>(raw_view(g), g->d_color, n_colors, d_min);
+    std::vector<unsigned long long> h((size_t)n_colors);
+    cudaMemcpyAsync(h.data(), d_min, (size_t)n_colors * 8, cudaMemcpyDeviceToHost, g->stream);
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_min);
+    NB_CUDA(e);
+    for (int c = 0; c < n_colors; c++) min_ids[c] = h[(size_t)c] > 0x7FFFFFFFFFFFFFFFull ? INT64_MAX : (int64_t)h[(size_t)c];
+    return NB_OK;
+}
+
+int nb_build_relabel_colors(nb_graph *g, const int32_t *map, int n)
+{
+    if (g->finalized) NB_FAIL(NB_ERR_INVALID, "colours cannot be relabelled after nb_graph_finalize");
+    if (n <= 0) return NB_OK;
+    int32_t *d_map;
+    NB_CUDA(cudaMalloc(&d_map, (size_t)n * 4));
+    cudaMemcpyAsync(d_map, map, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream);
+    k_relabel_colors<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_color, d_map, n);
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_map);
+    NB_CUDA(e);
+    return NB_OK;
+}
+
+static int order_colors_by_min_id(nb_graph *g, int n_colors)
+{
+    std::vector<int64_t> mins((size_t)n_colors);
+    NB_TRY(nb_build_color_min_ids(g, n_colors, mins.data()));
+    std::vector<int32_t> order((size_t)n_colors), map((size_t)n_colors);
+    for (int c = 0; c < n_colors; c++) order[(size_t)c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return mins[(size_t)a] < mins[(size_t)b]; });
+    for (int i = 0; i < n_colors; i++) map[(size_t)order[(size_t)i]] = i;
+    return nb_build_relabel_colors(g, map.data(), n_colors);
+}
+
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *d)
 {
     if (d->warp_row_words > 0) g->warp_row_words = d->warp_row_words;
-    if (d->sigma_shift > 0) g->sigma_shift = d->sigma_shift;
     g->deferred = d->deferred_coloring != 0;
     NB_TRY(extract_and_upload(g, d));
+    if (d->sigma_shift > 0) g->sigma_shift = d->sigma_shift;
+    else {
+        // id windows: 4096 ids on large graphs (gather locality of the SELL order), finer on small ones so
+        // that learning still has ~1000 windows to cut its mini-batches from
+        int lg = 0;
+        while ((1ll << (lg + 1)) <= std::max<int64_t>(g->V, 1)) lg++;
+        g->sigma_shift = std::min(12, std::max(5, lg - 10));
+    }
     const int64_t V = g->V;
     RawGraph G = raw_view(g);
 
@@ -765,6 +863,7 @@ int nb_build_finalize(nb_graph *g)
         NB_CUDA(cudaStreamSynchronize(g->stream));
         g->n_colors = maxc + 1;
     }
+    if (!g->deferred) NB_TRY(order_colors_by_min_id(g, g->n_colors));   // partitioned graphs: done by the caller, globally
     const int nc = g->n_colors, ng = 4 * (nc + 1);
     if (nc >= 0x3FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 16382)", nc);
 
@@ -845,6 +944,25 @@ int nb_build_finalize(nb_graph *g)
     k_assign_ids<<<grid_for(V), 256, 0, g->stream>>>(V, d_keys_sorted, d_ids_sorted, nc, d_gstart, d_gbase, G,
                                                      g->d_v_init, d_rowlen, d_fast, g->d_old2new, g->d_new2old, g->d_vmeta,
                                                      d_rowlen_new, g->d_vinit, g->d_rng_id, g->d_val[0], g->d_val[1]);
+
+    // ---- id windows of every (class, colour) group: learning walks the graph window by window ----
+    {
+        g->n_win = (V >> g->sigma_shift) + 1;
+        const size_t row = (size_t)g->n_win + 1, total = (size_t)ng * row;
+        int32_t *d_ws;
+        NB_TRY(nb_alloc(g, &d_ws, total, false));
+        NB_CUDA(cudaMemsetAsync(d_ws, 0xFF, total * 4, g->stream));
+        k_window_starts<<<grid_for(V), 256, 0, g->stream>>>(V, d_keys_sorted, nc, d_gstart, d_gbase, g->n_win, d_ws);
+        g->win_start.assign(total, -1);
+        NB_CUDA(cudaMemcpyAsync(g->win_start.data(), d_ws, total * 4, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        for (int gi = 0; gi < ng; gi++) {
+            int32_t *ws = g->win_start.data() + (size_t)gi * row;
+            // end of the group in its own id space (thread classes: new ids; warp class: new ids too)
+            ws[g->n_win] = (int32_t)(gbase[(size_t)gi] + (int64_t)gcount[(size_t)gi]);
+            for (int64_t w = g->n_win - 1; w >= 0; w--) if (ws[w] < 0) ws[w] = ws[w + 1];
+        }
+    }
 
     // ---- count layouts ----
     {

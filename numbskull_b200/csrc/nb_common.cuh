@@ -294,6 +294,8 @@ struct nb_graph {
     size_t flush_bytes = 0;
 
     void *p2p = nullptr;               // NbP2P (nb_p2p.cu)
+    int64_t n_win = 0;                 // id windows (original id >> sigma_shift)
+    std::vector<int32_t> win_start;    // [4 * (n_colors + 1)][n_win + 1] first new id of each window per group
     std::vector<int64_t> learn_vmax;   // per colour: max gradient visits of one weight
     int learn_vmax_flag = -1;
     std::vector<NbColorRange> colors;
@@ -316,8 +318,11 @@ void nb_p2p_destroy(nb_graph *g);
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);
 int nb_build_color_round(nb_graph *g, int64_t *remaining);
 int nb_build_finalize(nb_graph *g);
-int nb_learn_color(nb_graph *g, int color, double step, int regularization, double reg_param, double truncation,
-                   int learn_non_evidence, uint64_t seed, uint64_t epoch, int64_t batch_visits);
+int nb_build_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids);
+int nb_build_relabel_colors(nb_graph *g, const int32_t *map, int n);
+int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step, int regularization, double reg_param,
+                   double truncation, int learn_non_evidence, uint64_t seed, uint64_t epoch);
+int nb_learn_block_count(nb_graph *g, double step, int learn_non_evidence, int64_t batch_visits, int *n_blocks);
 
 // sweeps (nb_sweep.cu / nb_learn.cu)
 int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed,

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
         const uint32_t meta = a.vmeta[nid];
         const uint32_t rid = a.rng_id[nid];
         const int evid = NB_META_EVID(meta);
-        const bool valid = nid < end && NB_META_VALID(meta) && evid != 4;       // learning.py:24-26
+        const bool valid = nid >= beg && nid < end && NB_META_VALID(meta) && evid != 4;   // learning.py:24-26
         const int64_t q0 = a.tt_ptr[s];
         const int n = (int)((a.tt_ptr[s + 1] - q0) >> 5);
         const uint4 *qp = a.tt + q0 + lane;
@@ -418,6 +418,77 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
             } else if (contrib) {
                 sink.add(q.w, fF - fE, cinc);
             }
+        }
+    }
+    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt);
+}
+
+// Same algorithm, one WARP per row with the lanes striding over the row's quads: used when the
+// rows are long (data-programming models: a label variable with ~100 labelling functions), where
+// the mini-batches are too small to fill the GPU with one thread per row.
+template <bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, int beg, int end, uint32_t kfree,
+                                                                   uint32_t kevid, uint32_t ktrunc)
+{
+    extern __shared__ unsigned char s_raw[];
+    int32_t *s_grad = (int32_t *)s_raw;
+    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(int32_t) * (size_t)(SMEM ? a.W : 0));
+    if (SMEM) {
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
+        __syncthreads();
+    }
+    GradSinkI sink{SMEM ? s_grad : a.gi_grad, SMEM ? s_cnt : a.g_cnt};
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = blockIdx.x * (int64_t)NB_LWARPS + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
+    const nb_val_t *__restrict__ vF = a.val_free;
+    const nb_val_t *__restrict__ vE = a.val_evid;
+    const double *__restrict__ weight = a.weight;
+
+    for (int64_t nid = (int64_t)beg + warp_global; nid < end; nid += n_warps) {
+        const uint32_t meta = a.vmeta[nid];
+        const int evid = NB_META_EVID(meta);
+        if (!NB_META_VALID(meta) || evid == 4) continue;                         // learning.py:24-26
+        const uint32_t rid = a.rng_id[nid];
+        const int64_t s = nid >> 5;
+        const int64_t q0 = a.tt_ptr[s];
+        const int n = (int)((a.tt_ptr[s + 1] - q0) >> 5);
+        const uint4 *qp = a.tt + q0 + (nid & 31);
+        const uint32_t *bp = a.tt_base + q0 + (nid & 31);
+        double dF = 0.0, dE = 0.0;
+        for (int j = lane; j < n; j += 32) {
+            const uint4 q = __ldg(qp + (size_t)j * 32);
+            const double w = __ldg(weight + q.w);
+            dF = fma(w, (double)((int)((q.z >> (3 * nb_tt_index(vF[q.x], vF[q.y]))) & 7u) - 2), dF);
+            dE = fma(w, (double)((int)((q.z >> (3 * nb_tt_index(vE[q.x], vE[q.y]))) & 7u) - 2), dE);
+        }
+        dF = nb_warp_sum(dF);
+        dE = nb_warp_sum(dE);
+        int ev;
+        if (evid != 1) {
+            const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, kevid);
+            ev = u <= (double)(1.0f / (1.0f + __expf((float)dE))) ? 0 : 1;
+        } else {
+            ev = (int)a.vinit[nid];
+        }
+        const double uf = nb_philox2x32_u53(rid, (uint32_t)a.epoch, kfree);
+        const int prop = uf <= (double)(1.0f / (1.0f + __expf((float)dF))) ? 0 : 1;
+        __syncwarp();
+        if (lane == 0) { a.val_evid[nid] = (nb_val_t)ev; a.val_free[nid] = (nb_val_t)prop; }
+        if (!a.learn_non_evidence && evid != 1) continue;                        // :70-71
+        uint32_t cinc = 1;
+        if (a.regularization == 1)
+            cinc = nb_philox2x32_u53(rid, (uint32_t)a.epoch, ktrunc) < 1.0 / a.truncation ? 1u : 0u;
+        else if (a.regularization != 2) cinc = 0;
+        for (int j = lane; j < n; j += 32) {
+            const uint4 q = __ldg(qp + (size_t)j * 32);
+            if (q.z & NB_TT_FIXED_BIT) continue;
+            const uint32_t b = __ldg(bp + (size_t)j * 32);
+            // slots that point at the variable itself are ignored by the tables
+            const int iF = nb_tt_index(vF[q.x], vF[q.y]), iE = nb_tt_index(vE[q.x], vE[q.y]);
+            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * ((int)((q.z >> (3 * iF)) & 7u) - 2);
+            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * ((int)((q.z >> (3 * iE)) & 7u) - 2);
+            sink.add(q.w, fF - fE, cinc);
         }
     }
     if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt);
@@ -537,7 +608,8 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
 }
 
 template <bool WIDE, bool SMEM>
-static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int tb, int te, int wb, int we)
+static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int tb, int te, int wb, int we,
+                              bool long_rows)
 {
     size_t smem = SMEM ? (size_t)g->W * 8 : 0;
     const unsigned apply_grid = (unsigned)((g->W + 255) / 256);
@@ -545,11 +617,17 @@ static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, i
     for (int pass = 0; pass < 2; pass++) {
         const int rb = tt_range[pass][0], re = tt_range[pass][1];
         if (re <= rb) continue;
-        int64_t need = ((((int64_t)re + 31) >> 5) - (rb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
-        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
-        k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, rb, re, nb_fold_key(a.seed, a.epoch, NB_TAG_FREE),
-                                                                      nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
-                                                                      nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC));
+        const uint32_t kf = nb_fold_key(a.seed, a.epoch, NB_TAG_FREE), ke = nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
+                       kt = nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC);
+        if (long_rows) {     // one warp per row
+            int64_t need = ((int64_t)(re - rb) + NB_LWARPS - 1) / NB_LWARPS;
+            unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
+            k_learn_tt_row<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, rb, re, kf, ke, kt);
+        } else {             // one thread per row, one warp per SELL slice
+            int64_t need = ((((int64_t)re + 31) >> 5) - (rb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
+            unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
+            k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, rb, re, kf, ke, kt);
+        }
         g->launches++;
         if (!SMEM) { k_apply_global_int<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
     }
@@ -585,48 +663,80 @@ static int learn_prepare(nb_graph *g, LearnArgs &a, std::vector<int64_t> &vmax, 
     return NB_OK;
 }
 
-static int learn_one_color(nb_graph *g, const LearnArgs &a, int c, int64_t vmax_c, int64_t bv)
+// Rows of colour c whose original id falls into block `b` of `nb` (blocks = runs of id windows).
+// The learning epoch walks the blocks in increasing id order and, inside a block, the colours:
+// weights and chains advance together through the graph like in the reference's ascending-id
+// scan (learning.py:20-31), instead of one whole colour (all of a variable type) at a time.
+static int learn_block_of_color(nb_graph *g, const LearnArgs &a, int c, int b, int nb)
 {
     const bool smem = g->W <= NB_LEARN_SMEM_W;
     const NbColorRange &cr = g->colors[(size_t)c];
-    int64_t chunks = std::max<int64_t>(1, (vmax_c + bv - 1) / bv);
-    int64_t np = cr.p_end - cr.p_beg, nf = cr.f_end - cr.f_beg, nt = cr.t_end - cr.t_beg, nw = cr.w_end - cr.w_beg;
-    chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, std::max(std::max(np, nf), std::max(nt, nw))));
-    auto cut = [](int beg, int64_t n, int64_t k, int64_t parts, int end) {
-        return k >= parts ? end : beg + (int)((n * k / parts) & ~31ll);
+    const int64_t w_lo = g->n_win * (int64_t)b / nb, w_hi = g->n_win * (int64_t)(b + 1) / nb;
+    const size_t row = (size_t)g->n_win + 1;
+    auto range = [&](int cls, int &beg, int &end) {
+        const int32_t *ws = g->win_start.data() + (size_t)(cls * (g->n_colors + 1) + c) * row;
+        beg = ws[w_lo];
+        end = ws[w_hi];
     };
-    for (int64_t k = 0; k < chunks; k++) {
-        int pb = cut(cr.p_beg, np, k, chunks, cr.p_end), pe = cut(cr.p_beg, np, k + 1, chunks, cr.p_end);
-        int fb = cut(cr.f_beg, nf, k, chunks, cr.f_end), fe = cut(cr.f_beg, nf, k + 1, chunks, cr.f_end);
-        int tb = cut(cr.t_beg, nt, k, chunks, cr.t_end), te = cut(cr.t_beg, nt, k + 1, chunks, cr.t_end);
-        int wb = cr.w_beg + (int)(nw * k / chunks), we = cr.w_beg + (int)(nw * (k + 1) / chunks);
-        if (g->wide) {
-            if (smem) NB_TRY((launch_learn_range<true, true>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
-            else NB_TRY((launch_learn_range<true, false>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
-        } else {
-            if (smem) NB_TRY((launch_learn_range<false, true>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
-            else NB_TRY((launch_learn_range<false, false>(g, a, pb, pe, fb, fe, tb, te, wb, we)));
-        }
+    int pb, pe, fb, fe, tb, te, wb, we;
+    range(NB_CLASS_PAIR, pb, pe);
+    range(NB_CLASS_FAST, fb, fe);
+    range(NB_CLASS_GEN, tb, te);
+    range(NB_CLASS_WARP, wb, we);
+    wb -= (int)g->n_trows;          // warp rows are addressed by their index
+    we -= (int)g->n_trows;
+    if (pe <= pb && fe <= fb && te <= tb && we <= wb) return NB_OK;
+    const int64_t rows = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
+    // truth-table rows of this colour average >= 16 incidences: spread each row over a warp
+    const bool long_rows = (cr.f_end - cr.p_beg) > 0 && cr.edges >= 16 * rows;
+    if (g->wide) {
+        if (smem) return launch_learn_range<true, true>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
+        return launch_learn_range<true, false>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
     }
+    if (smem) return launch_learn_range<false, true>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
+    return launch_learn_range<false, false>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
+}
+
+// Mini-batch size: at most this many visits of any one weight between two applications.  The
+// reference applies every visit immediately (learning.py:110-125); a batch of n visits with a
+// stale weight moves it by about step * n * E[g], which must stay small against the scale on
+// which the gradient itself changes or strongly driven transients overshoot (and L1 then traps
+// the weights at 0).  step * n <= 0.25 keeps the batched trajectory on the per-visit one
+// (measured against the oracle on the labelling-function model, tools/lf_check.py).
+static int64_t default_batch_visits(double step, int64_t batch_visits)
+{
+    return batch_visits > 0 ? batch_visits : (int64_t)std::max(1.0, std::floor(0.25 / std::max(std::fabs(step), 1e-12)));
+}
+
+// number of id blocks per epoch: enough that no weight collects more than the batch bound in a block
+static int block_count(const nb_graph *g, const std::vector<int64_t> &vmax, int64_t bv)
+{
+    int64_t total = 0;
+    for (int64_t v : vmax) total += v;       // a weight can be visited from every colour inside a block
+    int64_t nb = std::max<int64_t>(1, (total + bv - 1) / bv);
+    return (int)std::min<int64_t>(nb, std::max<int64_t>(1, g->n_win));
+}
+
+int nb_learn_block_count(nb_graph *g, double step, int learn_non_evidence, int64_t batch_visits, int *n_blocks)
+{
+    LearnArgs a;
+    std::vector<int64_t> vmax;
+    NB_TRY(learn_prepare(g, a, vmax, learn_non_evidence));
+    *n_blocks = block_count(g, vmax, default_batch_visits(step, batch_visits));
     return NB_OK;
 }
 
-// mini-batch size: at most this many visits of any one weight between two applications
-static int64_t default_batch_visits(double step, int64_t batch_visits)
-{
-    return batch_visits > 0 ? batch_visits : (int64_t)std::max(1.0, std::floor(0.5 / std::max(std::fabs(step), 1e-12)));
-}
-
-int nb_learn_color(nb_graph *g, int color, double step, int regularization, double reg_param, double truncation,
-                   int learn_non_evidence, uint64_t seed, uint64_t epoch, int64_t batch_visits)
+int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step, int regularization, double reg_param,
+                   double truncation, int learn_non_evidence, uint64_t seed, uint64_t epoch)
 {
     if (color < 0 || color >= g->n_colors) return NB_OK;   // a colour this rank does not own
+    if (n_blocks < 1 || block < 0 || block >= n_blocks) NB_FAIL(NB_ERR_INVALID, "block %d of %d", block, n_blocks);
     LearnArgs a;
     std::vector<int64_t> vmax;
     NB_TRY(learn_prepare(g, a, vmax, learn_non_evidence));
     a.seed = seed; a.reg_param = reg_param; a.truncation = truncation; a.regularization = regularization;
     a.step = step; a.epoch = epoch;
-    NB_TRY(learn_one_color(g, a, color, vmax[(size_t)color], default_batch_visits(step, batch_visits)));
+    NB_TRY(learn_block_of_color(g, a, color, block, n_blocks));
     NB_CUDA(cudaGetLastError());
     return NB_OK;
 }
@@ -643,8 +753,9 @@ int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, 
     for (int64_t ep = 0; ep < n_epochs; ep++) {
         a.step = step;
         a.epoch = g->epoch_counter++;
-        const int64_t bv = default_batch_visits(step, batch_visits);
-        for (int c = 0; c < g->n_colors; c++) NB_TRY(learn_one_color(g, a, c, vmax[(size_t)c], bv));
+        const int nb = block_count(g, vmax, default_batch_visits(step, batch_visits));
+        for (int b = 0; b < nb; b++)
+            for (int c = 0; c < g->n_colors; c++) NB_TRY(learn_block_of_color(g, a, c, b, nb));
         NB_CUDA(cudaGetLastError());
         step *= decay;   // factorgraph.py:206
     }

@@ -227,12 +227,24 @@ class PartitionedGibbs(object):
                 break
         self.jp_rounds = rounds
         torch.cuda.synchronize()
-        _lib.check(L.nb_graph_finalize(g))
         colors = fg.colors()
         t = torch.tensor([int(colors.max()) + 1 if len(colors) else 0], device=self.dev, dtype=torch.int64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         self.n_colors = int(t.item())
+        # visit colours in increasing order of their smallest global variable id (same rule as the
+        # single-GPU build, decided globally so that every rank relabels identically)
+        mins = np.full(max(self.n_colors, 1), np.iinfo(np.int64).max, np.int64)
+        _lib.check(L.nb_color_min_ids(g, self.n_colors, _lib.ptr(mins)))
+        tm = torch.from_numpy(mins).to(self.dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MIN, group=group)
+        order = np.argsort(tm.cpu().numpy()[:self.n_colors], kind="stable")
+        cmap = np.empty(self.n_colors, np.int32)
+        cmap[order] = np.arange(self.n_colors, dtype=np.int32)
+        _lib.check(L.nb_relabel_colors(g, _lib.ptr(cmap), self.n_colors))
+        _lib.check(L.nb_graph_finalize(g))
+        colors = fg.colors()
         self.colors = colors
 
         # ---- per-colour halo exchanges (uint8 values) ----
@@ -339,16 +351,25 @@ class PartitionedGibbs(object):
         for _ in range(epochs):
             ep = C.c_int64(0)
             lib.check(L.nb_begin_epoch(g, C.byref(ep)))
-            for c in range(self.n_colors):
-                lib.check(L.nb_learn_color_phase(g, c, float(stepsize), int(regularization), float(reg_param),
-                                                 float(truncation), int(bool(learn_non_evidence)), fg.seed,
-                                                 ep.value, int(fg.batch_visits)))
-                if self.world > 1:
-                    if self.p2p:
-                        lib.check(L.nb_p2p_exchange(g, c, 3))
-                    else:
-                        self._exchange(c, 0)
-                        self._exchange(c, 1)
+            nb = C.c_int(1)
+            lib.check(L.nb_learn_blocks(g, float(stepsize), int(bool(learn_non_evidence)), int(fg.batch_visits),
+                                        C.byref(nb)))
+            n_blocks = nb.value
+            if self.world > 1:
+                t = torch.tensor([n_blocks], device=self.dev, dtype=torch.int64)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+                n_blocks = int(t.item())
+            for b in range(n_blocks):
+                for c in range(self.n_colors):
+                    lib.check(L.nb_learn_color_phase(g, c, b, n_blocks, float(stepsize), int(regularization),
+                                                     float(reg_param), float(truncation),
+                                                     int(bool(learn_non_evidence)), fg.seed, ep.value))
+                    if self.world > 1:
+                        if self.p2p:
+                            lib.check(L.nb_p2p_exchange(g, c, 3))
+                        else:
+                            self._exchange(c, 0)
+                            self._exchange(c, 1)
             if self.world > 1:
                 torch.cuda.synchronize()
                 host = np.empty(len(fg.weight), np.float64)

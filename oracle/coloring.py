@@ -50,6 +50,23 @@ def greedy_coloring(variable, factor, fmap, seed, global_vid=None):
         while c in used:
             c += 1
         color[v] = c
+    return relabel_by_min_id(color, gid)
+
+
+def relabel_by_min_id(color, gid):
+    """Colours are numbered in increasing order of the smallest global id they contain
+    (csrc/nb_build.cu order_colors_by_min_id)."""
+    color = np.asarray(color).copy()
+    n = int(color.max()) + 1 if len(color) else 0
+    if n == 0:
+        return color
+    mins = np.full(n, np.iinfo(np.int64).max, np.int64)
+    owned = color >= 0
+    np.minimum.at(mins, color[owned], np.asarray(gid)[owned])
+    order = np.argsort(mins, kind="stable")
+    cmap = np.empty(n, np.int32)
+    cmap[order] = np.arange(n, dtype=np.int32)
+    color[owned] = cmap[color[owned]]
     return color
 
 

@@ -331,6 +331,27 @@ def test_learned_weights_within_3_sigma_of_oracle(oracle, name, reg):
     assert np.array_equal(wg[0][fixed], z["weight"]["initialValue"][fixed])
 
 
+def test_lf_model_learning_long_rows(oracle):
+    """Data-programming shape (BASELINE config 3): label variables with 24 labelling functions
+    go through the warp-per-row truth-table learning kernel; accuracies are recovered and agree
+    with the oracle's SGD (same options as test_lf_learning.py:129-137, L1, learn_non_evidence)."""
+    from numbskull_b200 import synth
+    acc = np.linspace(0.6, 0.9, 24)
+    g = synth.lf_model(1500, 24, np.random.default_rng(41), accuracy=acc, abstain_prob=0.5)
+    args = (5, 60, 0.001, 0.98, 1, 0.01, 1)
+
+    def run(x):
+        x.learn(*args, learn_non_evidence=True)
+        return np.asarray(x.weight_value, np.float64).reshape(-1).copy()
+
+    wg = np.array([run(_fg_from_synth(g, seed=s)) for s in (1, 2, 3)])
+    fg = _fg_from_synth(g, seed=9)
+    wc = np.array([run(_oracle_of(oracle, fg, seed=s)) for s in (11, 12, 13)])
+    assert np.abs(wg.mean(0) - wc.mean(0)).max() < 0.08, (wg.mean(0), wc.mean(0))
+    # weight = log-odds/2 of the accuracy: monotone in the true accuracies
+    assert np.corrcoef(wg.mean(0)[1:], acc)[0, 1] > 0.9
+
+
 def test_learning_large_weight_table_path():
     """W > shared-memory table -> global accumulation path."""
     from numbskull_b200 import synth

@@ -133,7 +133,11 @@ def c4(scale):
     fg, times = load(g)
     info = fg.device_info()
     every = fg.variable["isEvidence"] != 4
-    b, edges = algorithmic_bytes(fg, every)
+    # every variable is sampled and no factor repeats a member: each factor is seen once from each
+    # member, so B_inf = 16 N_v + sum_f arity_f (20 + 5 arity_f) without materialising the edge list
+    ar = fg.factor["arity"].astype(np.int64)
+    b, edges = 16.0 * int(every.sum()) + float((ar * (20 + 5 * ar)).sum()), int(info["n_edges"])
+    del ar
     dt = inference_rate(fg, 10)
     extra = dict(times, inference_ms_per_sweep=1e3 * dt, inference_edge_evals_per_s=edges / dt,
                  var_samples_per_s=int(every.sum()) / dt, inference_roofline_frac=b / dt / 1e9 / PEAK,
@@ -141,6 +145,52 @@ def c4(scale):
     dtl, launches = learn_rate(fg, 1, 0.01, 2, 0.01, False)
     extra.update(learn_ms_per_epoch=1e3 * dtl, learn_edge_evals_per_s=edges / dtl, learn_launches_per_epoch=launches)
     report("c4_kbc_%d" % nvar, fg, info, extra)
+
+
+def c4_partitioned(scale):
+    """C4 across the ranks of a torchrun launch: every rank builds the same global graph
+    (same seed), keeps its block (owner-computes) and exchanges boundary values per colour."""
+    import torch
+    import torch.distributed as dist
+    from numbskull_b200 import partition
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
+    nvar = max(10000, int(200_000_000 * scale))
+    w, v, f, fm, dm, e = synth.kbc(nvar, np.random.default_rng(1004))
+    t0 = time.perf_counter()
+    run = partition.partition_graph(w, v, f, fm, rank, world, local, seed=12345)
+    del w, v, f, fm
+    build_s = time.perf_counter() - t0
+    fg = run.fg
+    info = fg.device_info()
+    L, g = _lib.lib(), fg._g
+    fg._upload(0, 0, evid=False)
+    run.sweeps(3, True, True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sweeps = 10
+    _lib.check(L.nb_timer_start(g))
+    run.sweeps(sweeps, False, True)
+    ms = C.c_float(0)
+    _lib.check(L.nb_timer_stop(g, C.byref(ms)))
+    t = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e_loc = torch.tensor([float(fg.color_edges().sum()), float(run.n_owned), float(len(fg.variable) - run.n_owned),
+                          float(run.halo_bytes_per_sweep)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e_loc)
+    if rank == 0:
+        dt = float(t.item()) * 1e-3 / sweeps
+        print(json.dumps({"config": "c4_kbc_%d_partitioned" % nvar, "n_gpus": world, "variables": nvar,
+                          "edges": int(e_loc[0].item()), "ghost_variables_total": int(e_loc[2].item()),
+                          "halo_values_per_sweep_total": int(e_loc[3].item()), "colors": run.n_colors,
+                          "jp_rounds": run.jp_rounds, "p2p_halo": bool(run.p2p), "build_s": round(build_s, 1),
+                          "device_GB_rank0": round(info["device_bytes"] / 1e9, 2),
+                          "inference_ms_per_sweep": 1e3 * dt, "inference_edge_evals_per_s": e_loc[0].item() / dt,
+                          "var_samples_per_s": e_loc[1].item() / dt}))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def c5(scale):
@@ -163,4 +213,7 @@ if __name__ == "__main__":
     ap.add_argument("config", choices=["c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=0.1)
     a = ap.parse_args()
-    {"c3": c3, "c4": c4, "c5": c5}[a.config](a.scale)
+    if a.config == "c4" and int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        c4_partitioned(a.scale)
+    else:
+        {"c3": c3, "c4": c4, "c5": c5}[a.config](a.scale)
