@@ -8,11 +8,6 @@
 // key = 64-bit seed: every (variable, sweep, purpose) has its own stream, so
 // results do not depend on the launch geometry, the colouring or the partition.
 // ---------------------------------------------------------------------------
-struct NbPhilox {
-    uint32_t c[4];
-    uint32_t k[2];
-};
-
 __host__ __device__ inline void nb_philox_round(uint32_t *c, const uint32_t *k)
 {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];

@@ -702,7 +702,7 @@ static int learn_block_of_color(nb_graph *g, const LearnArgs &a, int c, int b, i
 // stale weight moves it by about step * n * E[g], which must stay small against the scale on
 // which the gradient itself changes or strongly driven transients overshoot (and L1 then traps
 // the weights at 0).  step * n <= 0.25 keeps the batched trajectory on the per-visit one
-// (measured against the oracle on the labelling-function model, tools/lf_check.py).
+// (measured against the CPU reference port on the labelling-function model, tools/lf_check.py).
 static int64_t default_batch_visits(double step, int64_t batch_visits)
 {
     return batch_visits > 0 ? batch_visits : (int64_t)std::max(1.0, std::floor(0.25 / std::max(std::fabs(step), 1e-12)));

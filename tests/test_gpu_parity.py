@@ -386,6 +386,39 @@ def test_numbskull_api_and_cli(tmp_path, capsys):
     assert np.allclose(fg.getMarginals(), fg.count / 10.0)
 
 
+def test_reference_test_py_invocation(tmp_path):
+    """The reference's own smoke test (test.py:1-18): `-l 100 -i 100 -t 10 -s 0.01
+    --regularization 2 -r 0.1 --quiet` on the coin graph; nthreads is accepted and ignored."""
+    import numbskull_b200 as nb
+    z = golden("coin")
+    for n in ("meta", "weights", "variables", "factors"):
+        z["raw_" + n].tofile(str(tmp_path / ("graph." + n)))
+    ns = nb.numbskull.load([str(tmp_path), "-l", "100", "-i", "100", "-t", "10", "-s", "0.01",
+                            "--regularization", "2", "-r", "0.1", "--quiet", "-o", str(tmp_path)])
+    ns.learning()
+    ns.inference()
+    c = ns.factorGraphs[0].count
+    assert c.shape == (18,) and c.min() >= 0 and c.max() <= 100
+    # eight of nine evidence coins are heads: the learned weight is positive, queries lean to 1
+    assert ns.factorGraphs[0].weight_value[0][0] > 0.1
+    assert c[9:].mean() > 55
+
+
+def test_learning_block_schedule_api():
+    """nb_learn_blocks: the mini-batch count follows 0.25 / stepsize and the visit bound."""
+    import ctypes as C
+    from numbskull_b200 import _lib, synth
+    fg = _fg_from_synth(synth.ising_pairs(20000, rng=np.random.default_rng(3)), seed=1)
+    fg._upload(0, 0)
+    L, g = _lib.lib(), fg._g
+    n1, n2 = C.c_int(0), C.c_int(0)
+    _lib.check(L.nb_learn_blocks(g, 0.01, 0, 0, C.byref(n1)))
+    _lib.check(L.nb_learn_blocks(g, 0.001, 0, 0, C.byref(n2)))
+    assert n1.value > n2.value >= 1
+    _lib.check(L.nb_learn_blocks(g, 0.01, 0, 10 ** 9, C.byref(n2)))
+    assert n2.value == 1
+
+
 # --------------------------------------------------------------------------- BASELINE-size properties
 def test_ising_full_size_properties():
     """BASELINE config 2 (4096 x 4096 EQUAL grid): valid colouring, reproducible
