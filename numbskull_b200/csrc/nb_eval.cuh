@@ -50,20 +50,21 @@ struct NbUniforms {
     uint32_t id, epoch_lo, epoch_hi_tag;
     uint64_t seed;
     uint32_t block;
-    double spare;
-    bool has_spare;
+    uint32_t r[4];
+    int left;   // unread 32-bit words of the current Philox block
     __device__ NbUniforms(uint32_t id_, uint64_t epoch, uint32_t tag, uint64_t seed_)
         : id(id_), epoch_lo((uint32_t)epoch), epoch_hi_tag((uint32_t)((epoch >> 32) & 0xFFFFu) | (tag << 24)),
-          seed(seed_), block(0), spare(0.0), has_spare(false) {}
-    __device__ double next()
+          seed(seed_), block(0), left(0) {}
+    __device__ __forceinline__ uint32_t word()
     {
-        if (has_spare) { has_spare = false; return spare; }
-        uint32_t r[4];
-        nb_philox4x32(id, epoch_lo, epoch_hi_tag, block++, seed, r);
-        spare = nb_u53(r[2], r[3]);
-        has_spare = true;
-        return nb_u53(r[0], r[1]);
+        if (left == 0) { nb_philox4x32(id, epoch_lo, epoch_hi_tag, block++, seed, r); left = 4; }
+        left--;
+        return left == 3 ? r[0] : (left == 2 ? r[1] : (left == 1 ? r[2] : r[3]));
     }
+    // 53-bit uniform (two words): the single draw of small-cardinality variables
+    __device__ double next() { uint32_t hi = word(); return nb_u53(hi, word()); }
+    // 32-bit uniform (one word): the per-value decisions of the streaming categorical sampler
+    __device__ double next32() { return ((double)word() + 0.5) * (1.0 / 4294967296.0); }
 };
 
 // ---------------------------------------------------------------------------
@@ -290,13 +291,14 @@ struct NbReservoir {
     int pick;
     bool empty;
     __device__ NbReservoir() : m(0.0), s(0.0), pick(0), empty(true) {}
-    // add `mult` items of energy e; returns true when the pick moved to this group
+    // add `mult` items of energy e; returns true when the pick moved to this group.  The
+    // rescaling factors only shape sampling probabilities: fp32 exp (1e-7 relative) is ample.
     __device__ bool add(double e, double mult, double u)
     {
         if (empty) { m = e; s = mult; empty = false; return true; }
         double t;
-        if (e > m) { s = s * exp(m - e) + mult; m = e; t = mult; }
-        else { t = mult * exp(e - m); s += t; }
+        if (e > m) { s = s * (double)__expf((float)(m - e)) + mult; m = e; t = mult; }
+        else { t = mult * (double)__expf((float)(e - m)); s += t; }
         return u * s < t;
     }
 };
@@ -361,7 +363,7 @@ __device__ inline int nb_nth_empty_value(const NbRow &r, int len, int j)
 __device__ __forceinline__ int nb_draw_small(const double e[4], int card, double u)
 {
     if (card == 2) {
-        double p0 = 1.0 / (1.0 + exp(e[1] - e[0]));
+        double p0 = (double)(1.0f / (1.0f + __expf((float)(e[1] - e[0]))));
         return u <= p0 ? 0 : 1;
     }
     double m = e[0];
@@ -369,7 +371,7 @@ __device__ __forceinline__ int nb_draw_small(const double e[4], int card, double
     for (int k = 1; k < 4; k++) if (k < card) m = fmax(m, e[k]);
     double z[4], tot = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { z[k] = k < card ? exp(e[k] - m) : 0.0; tot += z[k]; z[k] = tot; }
+    for (int k = 0; k < 4; k++) { z[k] = k < card ? (double)__expf((float)(e[k] - m)) : 0.0; tot += z[k]; z[k] = tot; }
     double t = u * tot;
     int pick = card - 1;
 #pragma unroll
@@ -392,7 +394,7 @@ __device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint
         }
         NbReservoir res;
         for (int k = 0; k < card; k++)
-            if (res.add(nb_row_energy_k<WIDE>(r, len, self, k, vals, weight), 1.0, rng.next())) res.pick = k;
+            if (res.add(nb_row_energy_k<WIDE>(r, len, self, k, vals, weight), 1.0, rng.next32())) res.pick = k;
         return res.pick;
     }
     // categorical: buckets in ascending value order, each introduced by a MARK
@@ -402,7 +404,7 @@ __device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint
     while (pos < len) {
         NbHdr h = nb_read_hdr<WIDE>(r, pos);
         if (h.code == C_MARK) {
-            if (cur >= 0 && res.add(e, 1.0, rng.next())) res.pick = cur;
+            if (cur >= 0 && res.add(e, 1.0, rng.next32())) res.pick = cur;
             cur = (int)h.wid;
             e = 0.0;
             nonempty++;
@@ -411,10 +413,10 @@ __device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint
         }
         pos += nb_inc_words<WIDE>(h);
     }
-    if (cur >= 0 && res.add(e, 1.0, rng.next())) res.pick = cur;
+    if (cur >= 0 && res.add(e, 1.0, rng.next32())) res.pick = cur;
     int n_empty = card - nonempty;
-    if (n_empty > 0 && res.add(0.0, (double)n_empty, rng.next())) {
-        int j = min(n_empty - 1, (int)(rng.next() * (double)n_empty));
+    if (n_empty > 0 && res.add(0.0, (double)n_empty, rng.next32())) {
+        int j = min(n_empty - 1, (int)(rng.next32() * (double)n_empty));
         res.pick = nb_nth_empty_value<WIDE>(r, len, j);
     }
     return res.pick;

@@ -254,7 +254,7 @@ __device__ inline int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_i
     else {
         NbReservoir res;
         for (int j = 0; j < card; j++)
-            if (res.add(se[j], 1.0, rng.next())) res.pick = j;
+            if (res.add(se[j], 1.0, rng.next32())) res.pick = j;
         k = res.pick;
     }
     __syncwarp();

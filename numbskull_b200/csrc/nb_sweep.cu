@@ -208,7 +208,7 @@ __device__ inline int nb_draw_shared(const double *se, int card, NbUniforms &rng
 {
     NbReservoir res;
     for (int k = 0; k < card; k++)
-        if (res.add(se[k], 1.0, rng.next())) res.pick = k;
+        if (res.add(se[k], 1.0, rng.next32())) res.pick = k;
     return res.pick;
 }
 
