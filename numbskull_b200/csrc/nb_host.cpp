@@ -1,8 +1,10 @@
 // Host-side integer work of the drop-in boundary: error strings, the DeepDive
 // binary parsers and the (bit-exact) variable-to-factor index builder.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "nb_common.cuh"
@@ -53,18 +55,37 @@ extern "C" int nb_assign_vtf_offsets(nb_variable_rec *variable, int64_t n_variab
 }
 
 // ---------------------------------------------------------------------------
-// dataloading.py:16-81 compute_var_map.  Same four steps and the same outputs:
-// (1) bucket lengths from every fmap entry, (2) exclusive scan -> offsets,
-// (3) scatter factor ids in factor order skipping factors_to_skip, (4) per
-// bucket sort + unique with the length shrunk and the offsets left alone.
-// Because step 3 visits factors in increasing id, buckets are already sorted;
-// the sort is kept only for inputs whose fmap order violates that.
+// dataloading.py:16-81 compute_var_map.  Same outputs as the reference's four
+// steps: (1) bucket lengths from every fmap entry, (2) exclusive scan ->
+// offsets, (3) factor ids scattered into the buckets (skipping factors_to_skip),
+// (4) per bucket sort + unique with the length shrunk and the offsets left alone.
+// The reference scatters in factor order, so its buckets come out ascending and
+// step 4 only removes duplicates; here steps 1, 3 and 4 run on host threads
+// (atomic bucket cursors, then each bucket is sorted), which yields the same
+// ascending, de-duplicated buckets whatever the thread interleaving.
 // ---------------------------------------------------------------------------
 static inline int64_t bucket_of(const nb_variable_rec *variable, const nb_ftv_rec &m)
 {
     const nb_variable_rec &v = variable[m.vid];
     return v.vtf_offset + (v.dataType == 1 ? m.dense_equal_to : 0);
 }
+
+template <class F>
+static void host_threads(int64_t n, F fn)
+{
+    int nt = n > (1 << 16) ? (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    int64_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        int64_t a = t * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([=] { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
+
+static inline int64_t atomic_fetch_add_i64(int64_t *p, int64_t x) { return __atomic_fetch_add(p, x, __ATOMIC_RELAXED); }
 
 extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                                   const nb_factor_rec *factor, int64_t n_factor,
@@ -73,40 +94,62 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                                   const uint8_t *domain_mask, const int64_t *factors_to_skip,
                                   int64_t n_skip)
 {
+    std::atomic<int> bad(0);
+    char msg[200] = "";
+    auto fail = [&](const char *what, int64_t idx) {
+        int expected = 0;
+        if (bad.compare_exchange_strong(expected, 1)) snprintf(msg, sizeof(msg), "%s (index %lld)", what, (long long)idx);
+    };
+    // :20-30 implicit domains
     for (int64_t i = 0; i < n_variable; i++) {
         const nb_variable_rec &v = variable[i];
-        if (v.dataType == 0) continue;
-        if (v.vtf_offset < 0 || v.vtf_offset + v.cardinality > n_vmap)
+        if (v.dataType == 0) {
+            if (v.vtf_offset < 0 || v.vtf_offset >= n_vmap) NB_FAIL(NB_ERR_INVALID, "variable %lld: vmap offset out of bounds", (long long)i);
+            continue;
+        }
+        if (v.vtf_offset < 0 || v.cardinality < 0 || v.vtf_offset + v.cardinality > n_vmap)
             NB_FAIL(NB_ERR_INVALID, "variable %lld: vmap range out of bounds", (long long)i);
         if (domain_mask && domain_mask[i]) continue;
         for (int64_t k = 0; k < v.cardinality; k++) vmap[v.vtf_offset + k].value = k;
     }
-    for (int64_t j = 0; j < n_fmap; j++) {
-        const nb_ftv_rec &m = fmap[j];
-        if (m.vid < 0 || m.vid >= n_variable)
-            NB_FAIL(NB_ERR_INVALID, "fmap[%lld].vid = %lld out of range", (long long)j, (long long)m.vid);
-        const nb_variable_rec &v = variable[m.vid];
-        if (v.dataType == 1 && (m.dense_equal_to < 0 || m.dense_equal_to >= v.cardinality))
-            NB_FAIL(NB_ERR_INVALID, "fmap[%lld].dense_equal_to = %lld outside cardinality %lld",
-                    (long long)j, (long long)m.dense_equal_to, (long long)v.cardinality);
-        int64_t b = bucket_of(variable, m);
-        if (b < 0 || b >= n_vmap) NB_FAIL(NB_ERR_INVALID, "fmap[%lld]: bucket out of range", (long long)j);
-        vmap[b].factor_index_length += 1;
+    // skip list -> flag per factor
+    std::vector<uint8_t> skip;
+    if (n_skip > 0) {
+        skip.assign((size_t)n_factor, 0);
+        for (int64_t s = 0; s < n_skip; s++) {
+            int64_t i = factors_to_skip[s];
+            if (i < 0 || i >= n_factor || (s > 0 && factors_to_skip[s - 1] >= i))
+                NB_FAIL(NB_ERR_INVALID, "factors_to_skip must be sorted, unique and in range");
+            skip[(size_t)i] = 1;
+        }
     }
-    // The reference counts the entries of skipped factors too and then never
-    // writes their slots, which leaves stale ids in the buckets (and overruns
-    // factor_index).  Here skipped factors simply do not occupy bucket space;
-    // with an empty skip list the result is identical to the reference's.
-    for (int64_t s = 0; s < n_skip; s++) {
-        int64_t i = factors_to_skip[s];
-        if (i < 0 || i >= n_factor || (s > 0 && factors_to_skip[s - 1] >= i))
-            NB_FAIL(NB_ERR_INVALID, "factors_to_skip must be sorted, unique and in range");
-        const nb_factor_rec &f = factor[i];
-        if (f.ftv_offset < 0 || f.arity < 0 || f.ftv_offset + f.arity > n_fmap)
-            NB_FAIL(NB_ERR_INVALID, "factor %lld: fmap range out of bounds", (long long)i);
-        for (int64_t j = f.ftv_offset; j < f.ftv_offset + f.arity; j++)
-            vmap[bucket_of(variable, fmap[j])].factor_index_length -= 1;
-    }
+    // :33-38 bucket lengths.  The reference also counts the entries of skipped factors and then
+    // never writes their slots, which leaves stale ids in the buckets (and overruns factor_index);
+    // here skipped factors simply occupy no bucket space.  With an empty skip list the result is
+    // identical to the reference's.
+    for (int64_t f = 0; f < n_factor; f++)
+        if (factor[f].ftv_offset < 0 || factor[f].arity < 0 || factor[f].ftv_offset + factor[f].arity > n_fmap)
+            NB_FAIL(NB_ERR_INVALID, "factor %lld: fmap range out of bounds", (long long)f);
+    host_threads(n_fmap, [&](int64_t a, int64_t b) {
+        for (int64_t j = a; j < b; j++) {
+            const nb_ftv_rec &m = fmap[j];
+            if (m.vid < 0 || m.vid >= n_variable) { fail("fmap vid out of range", j); continue; }
+            const nb_variable_rec &v = variable[m.vid];
+            if (v.dataType == 1 && (m.dense_equal_to < 0 || m.dense_equal_to >= v.cardinality)) {
+                fail("fmap dense_equal_to outside the variable's cardinality", j);
+                continue;
+            }
+            atomic_fetch_add_i64(&vmap[bucket_of(variable, m)].factor_index_length, 1);
+        }
+    });
+    if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+    if (n_skip > 0)
+        for (int64_t s = 0; s < n_skip; s++) {
+            const nb_factor_rec &f = factor[factors_to_skip[s]];
+            for (int64_t j = f.ftv_offset; j < f.ftv_offset + f.arity; j++)
+                vmap[bucket_of(variable, fmap[j])].factor_index_length -= 1;
+        }
+    // :40-46 exclusive scan
     int64_t last_len = 0, last_off = 0;
     for (int64_t i = 0; i < n_vmap; i++) {
         vmap[i].factor_index_offset = last_off + last_len;
@@ -118,30 +161,32 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                 "factor_index holds %lld entries but the buckets need %lld (the reference overruns "
                 "here when factors_to_skip is non-empty)",
                 (long long)n_factor_index, (long long)(last_off + last_len));
-
+    // :48-65 scatter (bucket cursors advanced atomically; order inside a bucket is fixed by the sort below)
     std::vector<int64_t> cursor((size_t)n_vmap);
     for (int64_t i = 0; i < n_vmap; i++) cursor[(size_t)i] = vmap[i].factor_index_offset;
-    int64_t fts = 0;
-    for (int64_t i = 0; i < n_factor; i++) {
-        if (fts < n_skip && factors_to_skip[fts] == i) { fts++; continue; }
-        const nb_factor_rec &f = factor[i];
-        if (f.ftv_offset < 0 || f.arity < 0 || f.ftv_offset + f.arity > n_fmap)
-            NB_FAIL(NB_ERR_INVALID, "factor %lld: fmap range out of bounds", (long long)i);
-        for (int64_t j = f.ftv_offset; j < f.ftv_offset + f.arity; j++)
-            factor_index[cursor[(size_t)bucket_of(variable, fmap[j])]++] = i;
-    }
-    for (int64_t i = 0; i < n_vmap; i++) {
-        int64_t off = vmap[i].factor_index_offset, len = vmap[i].factor_index_length;
-        int64_t *b = factor_index + off;
-        if (!std::is_sorted(b, b + len)) std::sort(b, b + len);
-        int64_t n = 0, last = -1;
-        for (int64_t k = 0; k < len; k++) {
-            if (b[k] == last) continue;
-            last = b[k];
-            b[n++] = last;
+    host_threads(n_factor, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            if (!skip.empty() && skip[(size_t)i]) continue;
+            const nb_factor_rec &f = factor[i];
+            for (int64_t j = f.ftv_offset; j < f.ftv_offset + f.arity; j++)
+                factor_index[atomic_fetch_add_i64(&cursor[(size_t)bucket_of(variable, fmap[j])], 1)] = i;
         }
-        vmap[i].factor_index_length = n;
-    }
+    });
+    // :67-81 sort + unique each bucket; offsets are not compacted
+    host_threads(n_vmap, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            int64_t off = vmap[i].factor_index_offset, len = vmap[i].factor_index_length;
+            int64_t *p = factor_index + off;
+            if (!std::is_sorted(p, p + len)) std::sort(p, p + len);
+            int64_t n = 0, last = -1;
+            for (int64_t k = 0; k < len; k++) {
+                if (p[k] == last) continue;
+                last = p[k];
+                p[n++] = last;
+            }
+            vmap[i].factor_index_length = n;
+        }
+    });
     return NB_OK;
 }
 

@@ -87,6 +87,30 @@ def test_compute_var_map_matches_oracle_on_random_graphs(oracle):
             assert np.array_equal(fi1[s:s + k], fi2[s:s + k])
 
 
+def test_compute_var_map_threaded_path_matches_oracle(oracle):
+    """> 65536 fmap entries: the multi-threaded scatter + per-bucket sort must give the same
+    (ascending, de-duplicated) buckets as the sequential reference algorithm."""
+    from numbskull_b200 import synth
+    from numbskull_b200.dataloading import assign_vtf_offsets, compute_var_map
+    from numbskull_b200.numbskulltypes import VarToFactor
+    w, v, f, fm, dm, e = synth.random_graph(20000, 90000, np.random.default_rng(77), funcs=(0, 1, 2, 3, 12, 14),
+                                            card=5, categorical_frac=0.4, allow_repeats=True, max_arity=4)
+    assert len(fm) > (1 << 16)
+    v1, v2 = v.copy(), v.copy()
+    n = assign_vtf_offsets(v1)
+    assign_vtf_offsets(v2)
+    vm1, vm2 = np.zeros(n, VarToFactor), np.zeros(n, VarToFactor)
+    fi1, fi2 = np.zeros(len(fm), np.int64), np.zeros(len(fm), np.int64)
+    compute_var_map(v1, f, fm, vm1, fi1, dm)
+    oracle.compute_var_map(v2, f, fm, vm2, fi2, dm)
+    assert np.array_equal(vm1, vm2)
+    keep = np.repeat(np.arange(len(vm1)), vm1["factor_index_length"])
+    pos = np.repeat(vm1["factor_index_offset"], vm1["factor_index_length"]) + \
+        (np.arange(len(keep)) - np.repeat(np.cumsum(vm1["factor_index_length"]) - vm1["factor_index_length"],
+                                          vm1["factor_index_length"]))
+    assert np.array_equal(fi1[pos], fi2[pos])
+
+
 def test_factors_to_skip_is_bounds_checked():
     """The reference overruns factor_index here; we size it safely and skip correctly."""
     import numbskull_b200 as nb
