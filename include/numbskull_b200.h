@@ -232,7 +232,13 @@ int nb_p2p_open(nb_graph *g, const uint8_t *handles_world_x3x64, const int32_t *
 int nb_p2p_local_slots(nb_graph *g, const int32_t *local_ids, int64_t n, int32_t *slots);
 int nb_p2p_set_plan(nb_graph *g, int n_colors, const int64_t *color_ptr, const int32_t *src_local,
                     const int32_t *peer, const int32_t *dst_slot);
+#define NB_P2P_NOWAIT 16 /* or-ed into chain_mask: signal only; the next sweep kernels wait in their prologue */
 int nb_p2p_exchange(nb_graph *g, int color, int chain_mask);
+int nb_p2p_wait(nb_graph *g);   /* block the stream until every neighbour reached the latest phase */
+/* nb_gibbs_sweeps for a partitioned graph: per colour the sweep kernels and the halo push, launched
+ * back to back from C (n_colors = the GLOBAL colour count). */
+int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, int sample_evidence, uint64_t seed,
+                        int n_colors, int nowait);
 int nb_p2p_check(nb_graph *g);
 /* run the sweeps on a caller-owned CUDA stream (cudaStream_t as void*) */
 int nb_set_stream(nb_graph *g, void *cuda_stream);

@@ -95,6 +95,8 @@ SIGNATURES = {
     "nb_p2p_local_slots": (C.c_int, [_P, _P, _I64, _P]),
     "nb_p2p_set_plan": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "nb_p2p_exchange": (C.c_int, [_P, C.c_int, C.c_int]),
+    "nb_p2p_wait": (C.c_int, [_P]),
+    "nb_gibbs_sweeps_p2p": (C.c_int, [_P, _I64, C.c_int, C.c_int, _U64, C.c_int, C.c_int]),
     "nb_p2p_check": (C.c_int, [_P]),
     "nb_set_stream": (C.c_int, [_P, _P]),
     "nb_begin_epoch": (C.c_int, [_P, C.POINTER(_I64)]),

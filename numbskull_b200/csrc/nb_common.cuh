@@ -313,6 +313,8 @@ int nb_ensure_xfer(nb_graph *g, size_t bytes);
 int nb_ensure_pinned(nb_graph *g, size_t bytes);
 
 void nb_p2p_destroy(nb_graph *g);
+void nb_p2p_wait_args(nb_graph *g, const volatile uint32_t **flags, const int32_t **neigh, int *n_neigh, uint32_t *phase,
+                      int **error);
 
 // build steps (nb_build.cu)
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);

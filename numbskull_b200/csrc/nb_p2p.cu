@@ -137,7 +137,7 @@ struct HaloArgs {
     uint32_t *const *peer_flags;
     volatile uint32_t *flags;
     const int32_t *neigh;
-    int n_neigh, rank, chain_mask;
+    int n_neigh, rank, chain_mask, wait;
     uint32_t phase;
     uint32_t *done;
     int *error;
@@ -163,21 +163,38 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloArgs a)
         const int r = a.neigh[k];
         ((volatile uint32_t *)a.peer_flags[r])[a.rank] = a.phase;       // my arrival, in r's memory
     }
-    __threadfence_system();
-    for (int k = threadIdx.x; k < a.n_neigh; k += blockDim.x) {
-        const int r = a.neigh[k];
-        const long long t0 = clock64();
-        while ((int32_t)(a.flags[r] - a.phase) < 0) {
-            if (clock64() - t0 > 20000000000ll) { *a.error = 1; break; }   // ~10 s: a peer died
+    if (a.wait) {
+        for (int k = threadIdx.x; k < a.n_neigh; k += blockDim.x) {
+            const int r = a.neigh[k];
+            const long long t0 = clock64();
+            while ((int32_t)(a.flags[r] - a.phase) < 0) {
+                if (clock64() - t0 > 20000000000ll) { *a.error = 1; break; }   // ~10 s: a peer died
+            }
         }
+        __threadfence_system();
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) *a.done = 0;
 }
 
+// wait until every neighbour has signalled `phase` (used after a run of non-blocking exchanges)
+__global__ void k_halo_wait(const volatile uint32_t *flags, const int32_t *neigh, int n_neigh, uint32_t phase, int *error)
+{
+    for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) {
+        const int r = neigh[k];
+        const long long t0 = clock64();
+        while ((int32_t)(flags[r] - phase) < 0) {
+            if (clock64() - t0 > 20000000000ll) { *error = 1; break; }
+        }
+    }
+    __threadfence_system();
+}
+
 // Push the boundary values of `color` (chain_mask: 1 = free chain, 2 = evidence chain, 3 = both)
-// to the peers and wait for theirs.  Every rank must call this the same number of times.
+// to the peers and wait for theirs.  With NB_P2P_NOWAIT (16) in chain_mask the kernel only
+// signals; the sweep kernels of the next colour then wait for the neighbours' signal in their
+// prologue, which takes the NVLink round trip off the critical path.  Every rank must call this
+// the same number of times.
 extern "C" int nb_p2p_exchange(nb_graph *g, int color, int chain_mask)
 {
     NB_CUDA(cudaSetDevice(g->device));
@@ -191,12 +208,56 @@ extern "C" int nb_p2p_exchange(nb_graph *g, int color, int chain_mask)
     a.val0 = g->d_val[0]; a.val1 = g->d_val[1];
     a.peer_val0 = p->d_peer_val[0]; a.peer_val1 = p->d_peer_val[1];
     a.peer_flags = p->d_peer_flags; a.flags = p->d_flags; a.neigh = p->d_neigh; a.n_neigh = p->n_neigh;
-    a.rank = p->rank; a.chain_mask = chain_mask; a.phase = ++p->phase; a.done = p->d_done; a.error = p->d_error;
+    a.rank = p->rank; a.chain_mask = chain_mask & 3; a.wait = (chain_mask & 16) ? 0 : 1;
+    a.phase = ++p->phase; a.done = p->d_done; a.error = p->d_error;
     int64_t n = a.end - a.beg;
     unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(1, (n + 255) / 256), 148);
     k_halo_push<<<grid, 256, 0, g->stream>>>(a);
     g->launches++;
     NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+extern "C" int nb_p2p_wait(nb_graph *g)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NbP2P *p = p2p_of(g);
+    if (!p || p->n_neigh == 0) return NB_OK;
+    k_halo_wait<<<1, 64, 0, g->stream>>>(p->d_flags, p->d_neigh, p->n_neigh, p->phase, p->d_error);
+    g->launches++;
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+// what a sweep kernel must wait for before it may read ghost values (nb_sweep.cu)
+void nb_p2p_wait_args(nb_graph *g, const volatile uint32_t **flags, const int32_t **neigh, int *n_neigh, uint32_t *phase,
+                      int **error)
+{
+    NbP2P *p = p2p_of(g);
+    if (!p || p->color_ptr.empty()) { *n_neigh = 0; *flags = nullptr; *neigh = nullptr; *phase = 0; *error = nullptr; return; }
+    *flags = p->d_flags; *neigh = p->d_neigh; *n_neigh = p->n_neigh; *phase = p->phase; *error = p->d_error;
+}
+
+// n_epochs chromatic sweeps of a partitioned graph, launched back to back from C: per colour the
+// colour's kernels and the halo push; n_colors is the GLOBAL colour count (ranks that own nothing
+// of a colour still take part in its exchange).
+extern "C" int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, int sample_evidence, uint64_t seed,
+                                   int n_colors, int nowait)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NbP2P *p = p2p_of(g);
+    if (!p || p->color_ptr.empty()) NB_FAIL(NB_ERR_INVALID, "p2p plan not set");
+    if (g->has_unknown_func)
+        NB_FAIL(NB_ERR_NOT_IMPLEMENTED, "Error: Factor Function %d ( used in factor %lld ) is not implemented.",
+                g->unknown_func_id, (long long)g->unknown_func_factor);
+    for (int64_t ep = 0; ep < n_epochs; ep++) {
+        const uint64_t epoch = g->epoch_counter++;
+        for (int c = 0; c < n_colors; c++) {
+            NB_TRY(nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch));
+            NB_TRY(nb_p2p_exchange(g, c, 1 | (nowait ? 16 : 0)));
+        }
+    }
+    if (nowait && n_epochs > 0) NB_TRY(nb_p2p_wait(g));
     return NB_OK;
 }
 

@@ -25,7 +25,31 @@ struct SweepArgs {
     int64_t n_trows;
     uint64_t seed, epoch;
     int burnin, sample_evidence;
+    // partitioned graphs with non-blocking halo pushes: neighbours' flags to wait for
+    const volatile uint32_t *w_flags;
+    const int32_t *w_neigh;
+    int w_n;
+    uint32_t w_phase;
+    int *w_error;
 };
+
+// Prologue of every sweep kernel: ghost values may only be read once each neighbour rank has
+// signalled the latest halo phase (its peer stores are fenced before the signal).
+__device__ __forceinline__ void nb_wait_halo(const SweepArgs &a)
+{
+    if (a.w_n == 0) return;
+    if ((int)threadIdx.x < a.w_n) {
+        const int r = a.w_neigh[threadIdx.x];
+        const long long t0 = clock64();
+        while ((int32_t)(a.w_flags[r] - a.w_phase) < 0) {
+            if (clock64() - t0 > 20000000000ll) { *a.w_error = 1; break; }
+        }
+    }
+    // the peer fenced its stores before the flag store, both land in this GPU's L2; this kernel has
+    // not touched the ghost slots yet (L1 is clean at launch), so ordering the loads after the
+    // flag read is all that is needed
+    __syncthreads();
+}
 
 static SweepArgs sweep_args(nb_graph *g, int chain, int burnin, int sample_evidence, uint64_t seed, uint64_t epoch)
 {
@@ -35,6 +59,7 @@ static SweepArgs sweep_args(nb_graph *g, int chain, int burnin, int sample_evide
     a.rng_id = g->d_rng_id; a.cstart = g->d_cstart; a.count = g->d_count; a.count_b = g->d_count_b; a.val = g->d_val[chain];
     a.weight = g->d_weight; a.n_trows = g->n_trows; a.seed = seed; a.epoch = epoch;
     a.burnin = burnin; a.sample_evidence = sample_evidence;
+    nb_p2p_wait_args(g, &a.w_flags, &a.w_neigh, &a.w_n, &a.w_phase, &a.w_error);
     return a;
 }
 
@@ -49,6 +74,7 @@ __device__ __forceinline__ void nb_tally(const SweepArgs &a, int64_t nid, int ca
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int end)
 {
+    nb_wait_halo(a);
     int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (nid >= end) return;
     const uint32_t meta = a.vmeta[nid];
@@ -67,6 +93,7 @@ __global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int 
 __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__restrict__ tt_ptr,
                                                   const uint4 *__restrict__ tt, int beg, int end, uint32_t key)
 {
+    nb_wait_halo(a);
     const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (nid >= end) return;
     // independent loads first: they overlap with the stream
@@ -114,6 +141,7 @@ __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__
 __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *__restrict__ tt2_ptr,
                                                    const uint4 *__restrict__ tt2, int beg, int end, uint32_t key)
 {
+    nb_wait_halo(a);
     const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (nid >= end) return;
     const uint32_t meta = a.vmeta[nid];
@@ -225,6 +253,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_partial(SweepArgs a, WarpTasks t, int kbeg, int kend)
 {
     __shared__ double s_e[NB_WARPS_PER_BLOCK][NB_MAX_CARD + 1];
+    nb_wait_halo(a);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t task = (int64_t)kbeg + blockIdx.x * (int64_t)NB_WARPS_PER_BLOCK + warp;
     if (task >= kend) return;

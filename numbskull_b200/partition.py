@@ -255,6 +255,7 @@ class PartitionedGibbs(object):
         self.halo_bytes_per_sweep = sum(h.n_send for h in self.halo)
         self.p2p = False
         import os
+        self.p2p_nowait = 16 if os.environ.get("NUMBSKULL_B200_P2P_NOWAIT", "1") != "0" else 0
         if (world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("NUMBSKULL_B200_P2P", "1") != "0"):
             self._setup_p2p(colors)
 
@@ -313,6 +314,11 @@ class PartitionedGibbs(object):
     def sweeps(self, n, burnin, sample_evidence):
         """n chromatic Gibbs sweeps; after each colour the owners' new values reach the ghosts."""
         L, g, lib = self.lib.lib(), self.fg._g, self.lib
+        if self.world > 1 and self.p2p:
+            # the whole launch sequence (colour kernels + halo pushes) is issued from C
+            lib.check(L.nb_gibbs_sweeps_p2p(g, int(n), int(bool(burnin)), int(bool(sample_evidence)), self.fg.seed,
+                                            self.n_colors, 1 if self.p2p_nowait else 0))
+            return
         for _ in range(n):
             ep = C.c_int64(0)
             lib.check(L.nb_begin_epoch(g, C.byref(ep)))
@@ -320,7 +326,13 @@ class PartitionedGibbs(object):
                 lib.check(L.nb_gibbs_color_phase(g, c, int(bool(burnin)), int(bool(sample_evidence)),
                                                  self.fg.seed, ep.value))
                 if self.world > 1:
-                    self._exchange(c, 0)
+                    if self.p2p:
+                        # push + signal only; the next colour's kernels wait for the neighbours' signal
+                        lib.check(L.nb_p2p_exchange(g, c, 1 | self.p2p_nowait))
+                    else:
+                        self._exchange(c, 0)
+        if self.world > 1 and self.p2p and n > 0:
+            lib.check(L.nb_p2p_wait(g))
 
     def inference(self, burnin_epochs, epochs, sample_evidence=True):
         """FactorGraph.inference for the owned block; returns the owned marginals."""
