@@ -386,6 +386,44 @@ def test_numbskull_api_and_cli(tmp_path, capsys):
     assert np.allclose(fg.getMarginals(), fg.count / 10.0)
 
 
+def test_loadfg_style_every_factor_function(oracle):
+    """The reference's loadfg.py:39-81: for EVERY entry of FACTORS a one-factor graph over 2 (3 for
+    DEP_FIXING / DEP_REINFORCING) Boolean variables, 100 learning + inference epochs.  The reference
+    only checks that nothing crashes; here the marginals must also agree with the oracle's sampler
+    and the learned weight (fixed in loadfg.py, learnable here as a second pass) must stay finite."""
+    import numbskull_b200 as nb
+    from numbskull_b200.numbskulltypes import Weight, Variable, Factor, FactorToVar
+    for name, func in sorted(nb.inference.FACTORS.items(), key=lambda kv: kv[1]):
+        nvar = 3 if name in ("DP_GEN_DEP_FIXING", "DP_GEN_DEP_REINFORCING") else 2
+        for fixed in (True, False):
+            w = np.zeros(1, Weight)
+            w["isFixed"], w["initialValue"] = fixed, 1.0
+            v = np.zeros(nvar, Variable)
+            v["cardinality"] = 2
+            v["isEvidence"][0] = 0 if fixed else 1
+            v["initialValue"][0] = 0 if fixed else 1
+            f = np.zeros(1, Factor)
+            f["factorFunction"], f["featureValue"], f["arity"] = func, 1.0, nvar
+            fm = np.zeros(nvar, FactorToVar)
+            fm["vid"] = np.arange(nvar)
+            ns = nb.NumbSkull(n_inference_epoch=100, n_learning_epoch=100, quiet=True)
+            ns.loadFactorGraph(w, v, f, fm, np.zeros(nvar, np.bool_), nvar)
+            fg = ns.factorGraphs[0]
+            fg.seed = 17
+            ns.learning(out=False)
+            ns.inference(out=False)
+            assert fg.count.shape == (nvar,) and fg.count.max() <= 100, name
+            assert np.isfinite(fg.weight_value).all(), name
+            if fixed:
+                assert fg.weight_value[0][0] == 1.0
+                og = _oracle_of(oracle, fg, seed=3)
+                og.var_value[:] = 0
+                fg.var_value[0][:] = 0
+                fg.inference(20, 40000, sample_evidence=True)
+                og.inference(20, 40000, sample_evidence=True)
+                assert np.abs(fg.marginals - og.marginals).max() < 0.02, (name, fg.marginals, og.marginals)
+
+
 def test_reference_test_py_invocation(tmp_path):
     """The reference's own smoke test (test.py:1-18): `-l 100 -i 100 -t 10 -s 0.01
     --regularization 2 -r 0.1 --quiet` on the coin graph; nthreads is accepted and ignored."""
