@@ -113,6 +113,7 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
     int nb = nbuckets(G, v);
     bool ok = G.v_dtype[v] == 0 && G.v_card[v] == 2;
     bool pair = true;
+    bool catok = G.v_dtype[v] == 1 && G.v_card[v] <= NB_CAT_MAX_CARD;
     for (int b = 0; b < nb; b++) {
         int64_t off = G.b_off[G.v_vtf[v] + b];
         int len = G.b_len[G.v_vtf[v] + b];
@@ -121,6 +122,7 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
             int f = G.fi[off + e];
             int code = G.f_code[f], a = G.f_arity[f];
             words += nb_incidence_words(G.wide, code, a, G.f_feat[f] != 1.0);
+            if (catok) catok = (code == C_AND_CAT || code == C_EQUAL_CAT_CONST) && a <= 3 && G.f_feat[f] == 1.0;
             if (ok) {   // truth-table class: arity <= 3, integer-valued function, small member domains
                 if (!nb_code_tt_ok(code) || a > 3 || G.f_feat[f] != 1.0) ok = false;
                 else if (!nb_code_tt_const_compare(code))
@@ -135,7 +137,7 @@ __global__ void k_row_size(RawGraph G, uint32_t *rowlen, uint32_t *ninc, uint8_t
     if (words > 0x7FFFFFFFull || inc > 0x7FFFFFFFull) { *overflow = 1; words = 0; inc = 0; }
     rowlen[v] = (uint32_t)words;
     ninc[v] = (uint32_t)inc;
-    fast[v] = ok ? (pair ? 2 : 1) : 0;
+    fast[v] = ok ? (pair ? 2 : 1) : (catok ? 3 : 0);
 }
 
 __host__ __device__ inline uint64_t nb_mix64(uint64_t x)
@@ -242,7 +244,7 @@ __global__ void k_max_color(int64_t V, const int32_t *color, int *maxc)
     if (v < V && color[v] >= 0) atomicMax(maxc, color[v]);
 }
 
-// sort key: class(2) | colour(14) | window(28) | row length(20); ghosts use colour = n_colors
+// sort key: class(3) | colour(14) | window(27) | row length(20); ghosts use colour = n_colors
 __global__ void k_sort_keys(int64_t V, const int32_t *color, const int8_t *v_evid, const uint32_t *rowlen, const uint8_t *fast, int n_colors,
                             int warp_row_words, int sigma_shift, uint64_t *keys, int32_t *ids,
                             unsigned long long *group_count, unsigned long long *color_edges,
@@ -253,12 +255,13 @@ __global__ void k_sort_keys(int64_t V, const int32_t *color, const int8_t *v_evi
     const bool ghost = v_evid[v] == 4 || color[v] < 0;
     int c = ghost ? n_colors : color[v];
     uint32_t len = rowlen[v];
-    int cls = len > (uint32_t)warp_row_words ? NB_CLASS_WARP
-                                             : (fast[v] == 2 ? NB_CLASS_PAIR : (fast[v] == 1 ? NB_CLASS_FAST : NB_CLASS_GEN));
+    int cls = len > (uint32_t)warp_row_words
+                  ? NB_CLASS_WARP
+                  : (fast[v] == 2 ? NB_CLASS_PAIR : (fast[v] == 1 ? NB_CLASS_FAST : (fast[v] == 3 ? NB_CLASS_CAT : NB_CLASS_GEN)));
     if (ghost) cls = NB_CLASS_GEN;
-    uint64_t window = ((uint64_t)v >> sigma_shift) & ((1ull << 28) - 1);
+    uint64_t window = ((uint64_t)v >> sigma_shift) & ((1ull << 27) - 1);
     uint64_t l = len < (1u << 20) ? len : (1u << 20) - 1;
-    keys[v] = ((uint64_t)cls << 62) | ((uint64_t)c << 48) | (window << 20) | l;
+    keys[v] = ((uint64_t)cls << 61) | ((uint64_t)c << 47) | (window << 20) | l;
     ids[v] = (int32_t)v;
     atomicAdd(&group_count[cls * (n_colors + 1) + c], 1ull);
     if (!ghost) atomicAdd(&color_edges[c], (unsigned long long)ninc[v]);
@@ -274,8 +277,8 @@ __global__ void k_assign_ids(int64_t V, const uint64_t *keys, const int32_t *sor
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= V) return;
     uint64_t key = keys[i];
-    int cls = (int)(key >> 62);
-    int c = (int)((key >> 48) & 0x3FFF);
+    int cls = NB_KEY_CLASS(key);
+    int c = NB_KEY_COLOR(key);
     int g = cls * (n_colors + 1) + c;
     int64_t nid = group_base[g] + (i - group_start[g]);
     int v = sorted_ids[i];
@@ -297,11 +300,11 @@ __global__ void k_window_starts(int64_t V, const uint64_t *keys, int n_colors, c
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= V) return;
     const uint64_t key = keys[i];
-    const int g = (int)(key >> 62) * (n_colors + 1) + (int)((key >> 48) & 0x3FFF);
-    const int64_t w = (int64_t)((key >> 20) & ((1ull << 28) - 1));
+    const int g = NB_KEY_CLASS(key) * (n_colors + 1) + NB_KEY_COLOR(key);
+    const int64_t w = NB_KEY_WINDOW(key);
     if (i > 0) {
         const uint64_t prev = keys[i - 1];
-        if ((prev >> 48) == (key >> 48) && ((prev >> 20) & ((1ull << 28) - 1)) == (uint64_t)w) return;
+        if (NB_KEY_GROUP_BITS(prev) == NB_KEY_GROUP_BITS(key) && NB_KEY_WINDOW(prev) == w) return;
     }
     win_start[(size_t)g * (size_t)(n_win + 1) + (size_t)w] = (int32_t)(group_base[g] + (i - group_start[g]));
 }
@@ -539,6 +542,59 @@ __global__ void k_fill_tt2(RawGraph G, const int32_t *old2new, int64_t n_prows, 
         const uint32_t wid = (uint32_t)G.f_wid[f];
         uint2 *slot = reinterpret_cast<uint2 *>(row + (size_t)(e >> 1) * 32) + (e & 1);
         *slot = make_uint2(other, nb_pack_pair(table, wfixed[wid], wid));
+    }
+}
+
+// ---- categorical records of the CAT rows ------------------------------------------------------
+__global__ void k_cat_slice_width(int64_t n_slices, int64_t first_id, const int32_t *new2old, const uint32_t *ninc, int64_t *quads)
+{
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    uint32_t w = 0;
+    for (int l = 0; l < 32; l++) {
+        int v = new2old[first_id + s * 32 + l];
+        if (v >= 0) w = max(w, ninc[v]);
+    }
+    quads[s] = (int64_t)w * 32;
+}
+
+__global__ void k_cat_pad(uint4 *cat, int64_t n)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) cat[i] = make_uint4(0u, 0u, nb_pack_cat(0, 0, 0, 3, 1), 0u);
+}
+
+__global__ void k_fill_cat(RawGraph G, const int32_t *old2new, int64_t first_id, int64_t end_id, const int64_t *cat_ptr,
+                           uint4 *cat, const uint8_t *wfixed)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || G.v_evid[v] == 4) return;
+    const int64_t nid = old2new[v];
+    if (nid < first_id || nid >= end_id) return;
+    uint4 *row = cat + cat_ptr[(nid - first_id) >> 5] + (nid & 31);
+    int e_out = 0;
+    const int card = G.v_card[v];
+    for (int k = 0; k < card; k++) {
+        const int64_t off = G.b_off[G.v_vtf[v] + k];
+        const int len = G.b_len[G.v_vtf[v] + k];
+        for (int e = 0; e < len; e++) {
+            const int f = G.fi[off + e];
+            const int a = G.f_arity[f];
+            const int64_t mo = G.f_off[f];
+            uint32_t other[2] = {(uint32_t)nid, (uint32_t)nid};
+            int eq[2] = {0, 0}, n_other = 0;
+            bool never = false;
+            for (int j = 0; j < a; j++) {
+                int u = G.m_vid[mo + j];
+                if (u == v) { never |= G.m_eq[mo + j] != k; continue; }   // v forced to k must equal every one of its own slots
+                if (n_other < 2) { other[n_other] = (uint32_t)old2new[u]; eq[n_other] = G.m_eq[mo + j] & 0xFF; }
+                n_other++;
+            }
+            const uint32_t wid = (uint32_t)G.f_wid[f];
+            row[(size_t)e_out * 32] = make_uint4(other[0], other[1],
+                                                 nb_pack_cat(k, eq[0], eq[1], never ? 3 : n_other, wfixed[wid]), wid);
+            e_out++;
+        }
     }
 }
 
@@ -864,7 +920,7 @@ int nb_build_finalize(nb_graph *g)
         g->n_colors = maxc + 1;
     }
     if (!g->deferred) NB_TRY(order_colors_by_min_id(g, g->n_colors));   // partitioned graphs: done by the caller, globally
-    const int nc = g->n_colors, ng = 4 * (nc + 1);
+    const int nc = g->n_colors, ng = NB_N_CLASSES * (nc + 1);
     if (nc >= 0x3FFF) NB_FAIL(NB_ERR_UNSUPPORTED, "colouring needs %d colours (limit 16382)", nc);
 
     // ---- ordering ----
@@ -890,11 +946,11 @@ int nb_build_finalize(nb_graph *g)
     NB_CUDA(cudaMemcpyAsync(cedges.data(), d_color_edges, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
 
-    // groups in sorted order: PAIR, FAST, GEN (colours 0..nc each, nc = ghosts), then WARP
+    // groups in sorted order: PAIR, FAST, CAT, GEN (colours 0..nc each, nc = ghosts), then WARP
     std::vector<int64_t> gstart((size_t)ng), gbase((size_t)ng);
     g->colors.assign((size_t)nc, NbColorRange());
     int64_t pos = 0, nid = 0;
-    for (int cls = 0; cls < 3; cls++) {
+    for (int cls = 0; cls < NB_CLASS_WARP; cls++) {
         for (int c = 0; c <= nc; c++) {
             size_t gi = (size_t)(cls * (nc + 1) + c);
             gstart[gi] = pos;
@@ -905,6 +961,7 @@ int nb_build_finalize(nb_graph *g)
                 int32_t b = (int32_t)nid, e = (int32_t)(nid + (int64_t)gcount[gi]);
                 if (cls == NB_CLASS_PAIR) { cr.p_beg = b; cr.p_end = e; }
                 else if (cls == NB_CLASS_FAST) { cr.f_beg = b; cr.f_end = e; }
+                else if (cls == NB_CLASS_CAT) { cr.c_beg = b; cr.c_end = e; }
                 else { cr.t_beg = b; cr.t_end = e; }
             }
             pos += (int64_t)gcount[gi];
@@ -912,11 +969,12 @@ int nb_build_finalize(nb_graph *g)
         }
         if (cls == NB_CLASS_PAIR) { nid = (nid + 31) & ~31ll; g->n_prows = nid; }
         if (cls == NB_CLASS_FAST) { nid = (nid + 31) & ~31ll; g->n_frows = nid; }
+        if (cls == NB_CLASS_CAT) { nid = (nid + 31) & ~31ll; g->n_crows = nid; }
     }
     g->n_trows = (nid + 31) & ~31ll;
     int64_t wr = 0;
     for (int c = 0; c <= nc; c++) {
-        size_t gi = (size_t)(3 * (nc + 1) + c);
+        size_t gi = (size_t)(NB_CLASS_WARP * (nc + 1) + c);
         gstart[gi] = pos;
         gbase[gi] = g->n_trows + wr;
         if (c < nc) { g->colors[(size_t)c].w_beg = (int32_t)wr; g->colors[(size_t)c].w_end = (int32_t)(wr + (int64_t)gcount[gi]); g->colors[(size_t)c].edges = (int64_t)cedges[(size_t)c]; }
@@ -1079,6 +1137,23 @@ int nb_build_finalize(nb_graph *g)
         if (g->n_tt2_quads) {
             k_tt2_pad<<<grid_for(g->n_tt2_quads), 256, 0, g->stream>>>(g->d_tt2, g->n_tt2_quads);
             k_fill_tt2<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_tt2_ptr, g->d_tt2, g->d_wfixed);
+        }
+    }
+    // ---- categorical records (CAT rows = new ids [n_frows, n_crows)) ----
+    {
+        const int64_t ncs = (g->n_crows - g->n_frows) / 32;
+        int64_t *d_q;
+        NB_TRY(nb_alloc(g, &d_q, (size_t)ncs + 1));
+        NB_TRY(nb_alloc(g, &g->d_cat_ptr, (size_t)ncs + 1));
+        if (ncs) k_cat_slice_width<<<grid_for(ncs), 256, 0, g->stream>>>(ncs, g->n_frows, g->d_new2old, d_ninc, d_q);
+        NB_TRY(exclusive_scan(g, d_q, g->d_cat_ptr, ncs + 1));
+        NB_CUDA(cudaMemcpyAsync(&g->n_cat_quads, g->d_cat_ptr + ncs, 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        NB_TRY(nb_alloc(g, &g->d_cat, (size_t)g->n_cat_quads + 1, false));
+        if (g->n_cat_quads) {
+            k_cat_pad<<<grid_for(g->n_cat_quads), 256, 0, g->stream>>>(g->d_cat, g->n_cat_quads);
+            k_fill_cat<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->n_crows, g->d_cat_ptr, g->d_cat,
+                                                           g->d_wfixed);
         }
     }
     NB_CUDA(cudaGetLastError());

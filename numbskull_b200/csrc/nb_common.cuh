@@ -152,8 +152,16 @@ __host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, 
 // GEN: any other row short enough for one thread; WARP: long rows, one per warp.
 #define NB_CLASS_PAIR 0   /* FAST rows whose incidences all have at most one other member: 8-byte records */
 #define NB_CLASS_FAST 1
-#define NB_CLASS_GEN 2
-#define NB_CLASS_WARP 3
+#define NB_CLASS_CAT 2    /* categorical variable (card <= 32), AND_CAT / EQUAL_CAT_CONST factors of arity <= 3 */
+#define NB_CLASS_GEN 3
+#define NB_CLASS_WARP 4
+#define NB_N_CLASSES 5
+#define NB_CAT_MAX_CARD 32
+// sort key: class:3 | colour:14 | id window:27 | row words:20
+#define NB_KEY_CLASS(k) ((int)((k) >> 61))
+#define NB_KEY_COLOR(k) ((int)(((k) >> 47) & 0x3FFF))
+#define NB_KEY_WINDOW(k) ((int64_t)(((k) >> 20) & ((1ull << 27) - 1)))
+#define NB_KEY_GROUP_BITS(k) ((k) >> 47)
 #define NB_PAIR_MAX_WID ((1u << 22) - 1)
 #define NB_WARP_TASK 1024   /* incidences per warp task */
 
@@ -166,6 +174,7 @@ typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
 struct NbColorRange {
     int32_t p_beg, p_end;  // PAIR rows [p_beg, p_end) in new ids (p_beg % 32 == 0)
     int32_t f_beg, f_end;  // FAST thread rows [f_beg, f_end) in new ids (f_beg % 32 == 0)
+    int32_t c_beg, c_end;  // CAT rows
     int32_t t_beg, t_end;  // GEN thread rows [t_beg, t_end) in new ids (t_beg % 32 == 0)
     int32_t w_beg, w_end;  // warp-path rows, as indices into the warp-row arrays
     int32_t k_beg, k_end;  // their tasks (slices of at most NB_WARP_TASK incidences of one row)
@@ -250,6 +259,10 @@ struct nb_graph {
     int64_t n_tt2_quads = 0;
     int32_t *d_count_b = nullptr;    // [Vn] tallies of the truth-table kernels (Boolean rows), indexed by new id
     int64_t n_frows = 0;             // PAIR + FAST rows occupy new ids [0, n_frows)
+    int64_t n_crows = 0;             // CAT rows occupy new ids [n_frows, n_crows)
+    int64_t *d_cat_ptr = nullptr;    // [(n_crows - n_frows)/32 + 1] quad offsets into d_cat
+    uint4 *d_cat = nullptr;          // categorical records {other A, other B, k:8 eqA:8 eqB:8 nOthers:2 fixed:1, wid}
+    int64_t n_cat_quads = 0;
     int64_t *d_tt_ptr = nullptr;     // [n_frows/32 + 1] quad offsets into d_tt
     uint4 *d_tt = nullptr;           // truth-table stream of the FAST rows (SELL-32, one quad per incidence)
     uint32_t *d_tt_base = nullptr;   // f(self = 0) tables, one word per quad (learning only)
@@ -295,7 +308,7 @@ struct nb_graph {
 
     void *p2p = nullptr;               // NbP2P (nb_p2p.cu)
     int64_t n_win = 0;                 // id windows (original id >> sigma_shift)
-    std::vector<int32_t> win_start;    // [4 * (n_colors + 1)][n_win + 1] first new id of each window per group
+    std::vector<int32_t> win_start;    // [NB_N_CLASSES * (n_colors + 1)][n_win + 1] first new id of each window per group
     std::vector<int64_t> learn_vmax;   // per colour: max gradient visits of one weight
     int learn_vmax_flag = -1;
     std::vector<NbColorRange> colors;

@@ -567,3 +567,14 @@ __host__ __device__ inline uint32_t nb_pack_pair(uint32_t table9, int fixed, uin
 {
     return table9 | ((uint32_t)fixed << 9) | (wid << 10);
 }
+
+// Categorical records (NB_CLASS_CAT): one quad per incidence of an AND_CAT / EQUAL_CAT_CONST factor
+// (inference.py:251-258) seen from a categorical variable in its bucket k:
+//     { other A, other B, k:8 | eqA:8 | eqB:8 | n_others:2 | fixed:1, weight id }
+// The factor is 1 iff every other member equals its dense_equal_to (the variable itself matches by
+// construction of the bucket); n_others == 3 marks "never satisfied" (padding, or the variable
+// occurring twice with different values).
+__host__ __device__ inline uint32_t nb_pack_cat(int k, int eq_a, int eq_b, int n_others, int fixed)
+{
+    return (uint32_t)k | ((uint32_t)eq_a << 8) | ((uint32_t)eq_b << 16) | ((uint32_t)n_others << 24) | ((uint32_t)fixed << 26);
+}

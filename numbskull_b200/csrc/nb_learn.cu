@@ -522,13 +522,26 @@ __global__ void k_apply_global(LearnArgs a)
 }
 
 // visits per weight of one colour (upper bound: every incidence of a learnable row)
+struct RowRanges {
+    int beg[4], end[4];    // thread-row id ranges (PAIR, FAST, CAT, GEN)
+    int wbeg, wend;        // warp rows
+};
+
 template <bool WIDE>
-__global__ void k_visit_histogram(LearnArgs a, int beg0, int end0, int beg, int end, int wbeg, int wend, uint32_t *hist)
+__global__ void k_visit_histogram(LearnArgs a, RowRanges rr, uint32_t *hist)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t nf = end0 - beg0, nt = end - beg, nw = wend - wbeg;
-    if (i >= nf + nt + nw) return;
-    int64_t nid = i < nf ? beg0 + i : (i < nf + nt ? beg + (i - nf) : a.n_trows + wbeg + (i - nf - nt));
+    int64_t nid = -1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t n = rr.end[k] - rr.beg[k];
+        if (nid < 0 && i >= 0 && i < n) nid = rr.beg[k] + i;
+        if (nid < 0) i -= n;
+    }
+    if (nid < 0) {
+        if (i >= rr.wend - rr.wbeg) return;
+        nid = a.n_trows + rr.wbeg + i;
+    }
     const uint32_t meta = a.vmeta[nid];
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;
@@ -590,13 +603,18 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
     NB_TRY(nb_alloc(g, &d_max, 1));
     for (int c = 0; c < g->n_colors; c++) {
         const NbColorRange &cr = g->colors[(size_t)c];
-        int64_t n = (cr.f_end - cr.p_beg) + (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
+        RowRanges rr;
+        rr.beg[0] = cr.p_beg; rr.end[0] = cr.p_end; rr.beg[1] = cr.f_beg; rr.end[1] = cr.f_end;
+        rr.beg[2] = cr.c_beg; rr.end[2] = cr.c_end; rr.beg[3] = cr.t_beg; rr.end[3] = cr.t_end;
+        rr.wbeg = cr.w_beg; rr.wend = cr.w_end;
+        int64_t n = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.c_end - cr.c_beg) + (cr.t_end - cr.t_beg) +
+                    (cr.w_end - cr.w_beg);
         if (n == 0) continue;
         NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
         NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
         unsigned grid = (unsigned)((n + 255) / 256);
-        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, cr.p_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
-        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, cr.p_beg, cr.f_end, cr.t_beg, cr.t_end, cr.w_beg, cr.w_end, g->d_nvis);
+        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, rr, g->d_nvis);
+        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, rr, g->d_nvis);
         k_max_u32<<<64, 256, 0, g->stream>>>(g->d_nvis, (int)g->W, d_max);
         uint32_t m = 0;
         NB_CUDA(cudaMemcpyAsync(&m, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
@@ -608,8 +626,8 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
 }
 
 template <bool WIDE, bool SMEM>
-static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int tb, int te, int wb, int we,
-                              bool long_rows)
+static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int cb, int ce, int tb, int te,
+                              int wb, int we, bool long_rows)
 {
     size_t smem = SMEM ? (size_t)g->W * 8 : 0;
     const unsigned apply_grid = (unsigned)((g->W + 255) / 256);
@@ -631,10 +649,10 @@ static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, i
         g->launches++;
         if (!SMEM) { k_apply_global_int<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
     }
-    if (te > tb) {
-        int64_t need = ((int64_t)(te - tb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
+    if (te > tb || ce > cb) {
+        int64_t need = ((int64_t)(te - tb) + (ce - cb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
         unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
-        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, 0, 0, tb, te);
+        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, cb, ce, tb, te);
         g->launches++;
         if (!SMEM) { k_apply_global<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
     }
@@ -678,23 +696,25 @@ static int learn_block_of_color(nb_graph *g, const LearnArgs &a, int c, int b, i
         beg = ws[w_lo];
         end = ws[w_hi];
     };
-    int pb, pe, fb, fe, tb, te, wb, we;
+    int pb, pe, fb, fe, cb, ce, tb, te, wb, we;
     range(NB_CLASS_PAIR, pb, pe);
     range(NB_CLASS_FAST, fb, fe);
+    range(NB_CLASS_CAT, cb, ce);      // categorical rows: learned by the generic thread kernel
     range(NB_CLASS_GEN, tb, te);
     range(NB_CLASS_WARP, wb, we);
     wb -= (int)g->n_trows;          // warp rows are addressed by their index
     we -= (int)g->n_trows;
-    if (pe <= pb && fe <= fb && te <= tb && we <= wb) return NB_OK;
-    const int64_t rows = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.t_end - cr.t_beg) + (cr.w_end - cr.w_beg);
+    if (pe <= pb && fe <= fb && ce <= cb && te <= tb && we <= wb) return NB_OK;
+    const int64_t rows = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.c_end - cr.c_beg) + (cr.t_end - cr.t_beg) +
+                         (cr.w_end - cr.w_beg);
     // truth-table rows of this colour average >= 16 incidences: spread each row over a warp
-    const bool long_rows = (cr.f_end - cr.p_beg) > 0 && cr.edges >= 16 * rows;
+    const bool long_rows = ((cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg)) > 0 && cr.edges >= 16 * rows;
     if (g->wide) {
-        if (smem) return launch_learn_range<true, true>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
-        return launch_learn_range<true, false>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
+        if (smem) return launch_learn_range<true, true>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
+        return launch_learn_range<true, false>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
     }
-    if (smem) return launch_learn_range<false, true>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
-    return launch_learn_range<false, false>(g, a, pb, pe, fb, fe, tb, te, wb, we, long_rows);
+    if (smem) return launch_learn_range<false, true>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
+    return launch_learn_range<false, false>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
 }
 
 // Mini-batch size: at most this many visits of any one weight between two applications.  The

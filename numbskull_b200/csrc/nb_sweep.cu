@@ -183,6 +183,72 @@ __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *_
     if (!a.burnin) a.count_b[nid] += k;                      // inference.py:30-31
 }
 
+// CAT rows: categorical variable (cardinality <= 32) with AND_CAT / EQUAL_CAT_CONST factors.  One
+// quad per incidence, uniform trip count per warp; the per-value energies live in a column of
+// shared memory private to the thread (no parsing, no divergence), then one inverse-CDF draw.
+__global__ void __launch_bounds__(256) k_gibbs_cat(SweepArgs a, const int64_t *__restrict__ cat_ptr,
+                                                   const uint4 *__restrict__ cat, int64_t first_id, int beg, int end)
+{
+    __shared__ float s_e[NB_CAT_MAX_CARD][256];
+    nb_wait_halo(a);
+    const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (nid >= end) return;
+    const uint32_t meta = a.vmeta[nid];
+    const uint32_t rid = a.rng_id[nid];
+    const uint32_t cs = a.cstart[nid];
+    const int card = NB_META_CARD(meta);
+    const int64_t s = (nid - first_id) >> 5;
+    const int64_t q0 = cat_ptr[s], q1 = cat_ptr[s + 1];
+    const int n = (int)((q1 - q0) >> 5);
+    const uint4 *qp = cat + q0 + (nid & 31);
+    const nb_val_t *__restrict__ vals = a.val;
+    const double *__restrict__ weight = a.weight;
+    const int tid = threadIdx.x;
+#pragma unroll 4
+    for (int k = 0; k < card; k++) s_e[k][tid] = 0.0f;
+    for (int j = 0; j < n; j += 2) {
+        uint4 q[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4((uint32_t)nid, (uint32_t)nid, nb_pack_cat(0, 0, 0, 3, 1), 0u);
+        int xa[2], xb[2];
+        float w[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            xa[t] = (int)vals[q[t].x];
+            xb[t] = (int)vals[q[t].y];
+            w[t] = (float)__ldg(weight + q[t].w);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const uint32_t m = q[t].z;
+            const int no = (int)((m >> 24) & 3u);
+            const bool sat = no < 3 && (no < 1 || xa[t] == (int)((m >> 8) & 0xFFu)) && (no < 2 || xb[t] == (int)((m >> 16) & 0xFFu));
+            if (sat) s_e[m & 0xFFu][tid] += w[t];
+        }
+    }
+    const int evid = NB_META_EVID(meta);
+    if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
+    if (!(evid == 0 || a.sample_evidence)) return;          // :24
+    // draw_sample (inference.py:36-52) with the maximum subtracted
+    float mx = s_e[0][tid];
+    for (int k = 1; k < card; k++) mx = fmaxf(mx, s_e[k][tid]);
+    float tot = 0.0f;
+    for (int k = 0; k < card; k++) { float z = __expf(s_e[k][tid] - mx); s_e[k][tid] = z; tot += z; }
+    const float t = (float)nb_philox2x32_u53(rid, (uint32_t)a.epoch, nb_fold_key(a.seed, a.epoch, NB_TAG_FREE)) * tot;
+    float acc = 0.0f;
+    int pick = card - 1;
+    for (int k = 0; k < card; k++) {
+        acc += s_e[k][tid];
+        if (acc >= t) { pick = k; break; }
+    }
+    a.val[nid] = (nb_val_t)pick;
+    if (!a.burnin) {
+        if (card == 2) a.count[cs] += pick;                  // inference.py:30-31
+        else a.count[cs + pick] += 1;                        // :32-33
+    }
+}
+
 // ---------------------------------------------------------------------------
 // warp path
 // ---------------------------------------------------------------------------
@@ -327,6 +393,11 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
         unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
         k_gibbs_tt<<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
+        g->launches++;
+    }
+    if (c.c_end > c.c_beg) {
+        unsigned grid = (unsigned)((c.c_end - c.c_beg + 255) / 256);
+        k_gibbs_cat<<<grid, 256, 0, g->stream>>>(a, g->d_cat_ptr, g->d_cat, g->n_frows, c.c_beg, c.c_end);
         g->launches++;
     }
     if (c.t_end > c.t_beg) {

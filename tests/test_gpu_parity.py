@@ -251,6 +251,23 @@ def test_hub_row_is_split_into_warp_tasks(oracle):
     assert np.abs(fg.marginals[1:].mean() - og.marginals[1:].mean()) < 0.005
 
 
+def test_categorical_record_rows_match_oracle(oracle):
+    """CAT row class (categorical records): AND_CAT / EQUAL_CAT_CONST factors, members may repeat
+    (a variable occurring twice, with equal or different dense_equal_to), mixed cardinalities."""
+    from numbskull_b200 import synth
+    g = synth.random_graph(40, 110, np.random.default_rng(33), funcs=(12, 15), card=5, categorical_frac=0.8,
+                           evidence_frac=0.2, allow_repeats=True, max_arity=3)
+    g[1]["cardinality"][g[1]["dataType"] == 1] = np.random.default_rng(1).integers(2, 8, int((g[1]["dataType"] == 1).sum()))
+    g[1]["initialValue"] = g[1]["initialValue"] % g[1]["cardinality"]
+    g[3]["dense_equal_to"] = g[3]["dense_equal_to"] % g[1]["cardinality"][g[3]["vid"]]
+    fg = _fg_from_synth(g, seed=21)
+    og = _oracle_of(oracle, fg, seed=7)
+    assert np.array_equal(fg.potentials(), og.potentials())
+    fg.inference(100, 150000, sample_evidence=False)
+    og.inference(100, 150000, sample_evidence=False)
+    assert np.abs(fg.marginals - og.marginals).max() < 0.01
+
+
 def test_count_is_cumulative_and_seeded_runs_repeat():
     z = golden("run_bool_l2")
     a = _fg_from_golden(z, seed=99)
