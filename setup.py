@@ -7,7 +7,7 @@ setup(
     name='numbskull_b200',
     version=__version__,
     description='B200-native Gibbs sampling / weight learning behind the numbskull API',
-    packages=find_packages(include=['numbskull_b200*']),
+    packages=find_packages(include=['numbskull_b200*', 'numbskull']),
     package_data={'numbskull_b200': ['libnumbskull_b200.so']},
     entry_points={'console_scripts': ['numbskull = numbskull_b200.numbskull:main']},
 )

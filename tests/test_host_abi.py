@@ -169,6 +169,18 @@ def test_option_table_matches_reference_defaults():
     assert len(nb.inference.FACTORS) == 25
 
 
+def test_import_numbskull_alias():
+    """`import numbskull` (the reference's package name) resolves to this implementation, with the
+    import forms the reference's own scripts use (test.py:5, loadfg.py:6-7, test_lf_learning.py:6-7)."""
+    import numbskull
+    from numbskull import numbskull as mod
+    from numbskull.numbskulltypes import Weight, Variable, Factor, FactorToVar  # noqa: F401
+    import numbskull_b200
+    assert numbskull.NumbSkull is numbskull_b200.NumbSkull is mod.NumbSkull
+    assert numbskull.inference.FACTORS["IMPLY_NATURAL"] == 0 and hasattr(mod, "load") and hasattr(mod, "main")
+    assert Weight.itemsize == 9
+
+
 def test_dump_formats(tmp_path):
     from numbskull_b200.factorgraph import FactorGraph
     z = golden("run_cat")
