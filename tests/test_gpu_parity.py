@@ -302,6 +302,36 @@ def test_empty_and_isolated():
     assert np.abs(fg.marginals - want).max() < 0.02
 
 
+def test_degenerate_graphs():
+    """No variables at all; cardinality-1 variables; a weight table nobody references."""
+    from numbskull_b200.numbskulltypes import Weight, Variable, Factor, FactorToVar
+    empty = (np.zeros(0, Weight), np.zeros(0, Variable), np.zeros(0, Factor), np.zeros(0, FactorToVar),
+             np.zeros(0, np.bool_), 0)
+    fg = _fg_from_synth(empty)
+    fg.inference(1, 3, sample_evidence=True)
+    fg.learn(0, 2, 0.01, 0.95, 2, 0.01, 1)
+    assert fg.count.shape == (0,) and fg.marginals.shape == (0,)
+    v = np.zeros(4, Variable)
+    v["cardinality"] = [1, 2, 1, 3]
+    w = np.zeros(3, Weight)
+    w["initialValue"] = [0.5, -1.0, 2.0]
+    f = np.zeros(2, Factor)
+    f["factorFunction"] = [4, 3]
+    f["weightId"] = [0, 1]
+    f["featureValue"] = 1
+    f["arity"] = [1, 2]
+    f["ftv_offset"] = [0, 1]
+    fm = np.zeros(3, FactorToVar)
+    fm["vid"] = [1, 0, 1]
+    fg = _fg_from_synth((w, v, f, fm, np.zeros(4, np.bool_), 3), seed=2)
+    fg.inference(10, 20000, sample_evidence=True)
+    # v0 is pinned to 0 (cardinality 1): EQUAL(v0, v1) with weight -1 favours v1 = 1, ISTRUE adds 0.5
+    p1 = 1.0 / (1.0 + np.exp(-(2 * 0.5 + 2 * 1.0)))
+    assert fg.count[0] == 20000 and fg.count[2] == 20000                  # single-value variables
+    assert abs(fg.marginals[1] - p1) < 0.01
+    assert np.abs(fg.marginals[3:6] - 1 / 3).max() < 0.02
+
+
 # --------------------------------------------------------------------------- learning
 def test_learning_coin_graph():
     """test/ graph: 9 evidence coins (8 heads) share one ISTRUE weight -> ln(8)/2."""
