@@ -288,11 +288,11 @@ struct nb_graph {
     uint8_t *d_wfixed = nullptr;     // [W]
 
     // ---- learning scratch ----
-    float *d_grad = nullptr;         // [W]
+    long long *d_grad = nullptr;     // [W] fixed-point gradient sums (generic rows, large weight tables)
     uint32_t *d_nvis = nullptr;      // [W] visits
     uint32_t *d_ntrunc = nullptr;    // [W] truncating visits (L1)
     int32_t *d_gradi = nullptr;      // [W] integer gradient sums (truth-table rows)
-    float *d_gpart = nullptr;        // block partials
+    long long *d_gpart = nullptr;    // block partials (64-bit fixed point; int32 view for truth-table rows)
     uint32_t *d_npart = nullptr;
     uint32_t *d_tpart = nullptr;
     int64_t part_blocks = 0;

@@ -14,7 +14,7 @@
 
 #include "nb_eval.cuh"
 
-#define NB_LEARN_SMEM_W 4096
+#define NB_LEARN_SMEM_W 2048
 #define NB_LEARN_MAX_BLOCKS (148 * 2)
 #define NB_LEARN_THREADS 256
 
@@ -38,9 +38,9 @@ struct LearnArgs {
     double step, reg_param, truncation;
     int regularization, learn_non_evidence;
     // reduction targets
-    float *g_grad;        // [W] global table (large-W path) or unused
+    long long *g_grad;    // [W] global fixed-point table (large-W path)
     uint32_t *g_cnt;      // [W]
-    float *p_grad;        // [blocks][W] per-block partials (shared-memory path; int32 for truth-table rows)
+    long long *p_grad;    // [blocks][W] per-block partials (shared-memory path; read as int32 by the truth-table kernels)
     uint32_t *p_cnt;
     uint32_t *done;       // completion counter
     // truth-table rows
@@ -75,13 +75,18 @@ __device__ __forceinline__ double nb_apply_update(double w, double G, uint32_t c
     return w;
 }
 
+// Generic rows accumulate gradients in 64-bit fixed point (2^-20 units): integer addition is
+// associative, so per-weight sums do not depend on the order in which threads, blocks or atomics
+// land -- the reduction by weight id is deterministic without sorting the incidences.
+#define NB_GRAD_UNIT 1048576.0
+typedef long long nb_fix_t;
 template <bool SMEM>
 struct GradSink {
-    float *grad;
+    nb_fix_t *grad;
     uint32_t *cnt;
-    __device__ __forceinline__ void add(uint32_t wid, float g, uint32_t c)
+    __device__ __forceinline__ void add(uint32_t wid, double g, uint32_t c)
     {
-        if (g != 0.0f) atomicAdd(grad + wid, g);
+        if (g != 0.0) atomicAdd((unsigned long long *)(grad + wid), (unsigned long long)__double2ll_rn(g * NB_GRAD_UNIT));
         if (c) atomicAdd(cnt + wid, c);
     }
 };
@@ -103,7 +108,7 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
                 double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
                 double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
                 double feat = h.feat ? nb_read_feature<WIDE>(r, h, pos) : 1.0;
-                sink.add(h.wid, (float)((f1 - f0) * feat), cnt_inc);
+                sink.add(h.wid, (f1 - f0) * feat, cnt_inc);
             }
             pos += nb_inc_words<WIDE>(h);
         }
@@ -117,7 +122,7 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
             double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
             double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
             double feat = h.feat ? nb_read_feature<WIDE>(r, h, pos) : 1.0;
-            sink.add(h.wid, (float)((f1 - f0) * feat), cnt_inc);
+            sink.add(h.wid, (f1 - f0) * feat, cnt_inc);
         }
     }
 }
@@ -127,7 +132,7 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
 // the last block to finish sum the partials in block order and apply the update
 // ---------------------------------------------------------------------------
 template <class T>
-__device__ inline void nb_flush_and_apply(const LearnArgs &a, T *s_grad, uint32_t *s_cnt)
+__device__ inline void nb_flush_and_apply(const LearnArgs &a, T *s_grad, uint32_t *s_cnt, double unit)
 {
     __shared__ bool s_last;
     __syncthreads();
@@ -145,11 +150,13 @@ __device__ inline void nb_flush_and_apply(const LearnArgs &a, T *s_grad, uint32_
         if (a.wfixed[w]) continue;
         double G = 0.0;
         uint32_t n = 0;
-        for (unsigned b = 0; b < gridDim.x; b++) {      // fixed block order: deterministic
-            G += (double)__ldcg(part + (size_t)b * a.W + w);
+        T Gi = 0;
+        for (unsigned b = 0; b < gridDim.x; b++) {      // integer sums: exact, order-independent
+            Gi += __ldcg(part + (size_t)b * a.W + w);
             n += __ldcg(a.p_cnt + (size_t)b * a.W + w);
         }
-        if (G != 0.0 || n != 0)
+        G = (double)Gi * unit;
+        if (Gi != 0 || n != 0)
             a.weight[w] = nb_apply_update(a.weight[w], G, n, a.regularization, a.step, a.reg_param, a.truncation);
     }
     if (threadIdx.x == 0) *a.done = 0;
@@ -162,10 +169,10 @@ template <bool WIDE, bool SMEM>
 __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, int beg0, int end0, int beg1, int end1)
 {
     extern __shared__ unsigned char s_raw[];
-    float *s_grad = (float *)s_raw;
-    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(float) * (size_t)(SMEM ? a.W : 0));
+    nb_fix_t *s_grad = (nb_fix_t *)s_raw;
+    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(nb_fix_t) * (size_t)(SMEM ? a.W : 0));
     if (SMEM) {
-        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0.0f; s_cnt[w] = 0u; }
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
         __syncthreads();
     }
     GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, 
         } else if (a.regularization != 2) cnt_inc = 0;
         nb_row_gradient<WIDE, SMEM>(r, len, self, meta, ev, prop, a, cnt_inc, sink, 0, 1, nullptr, 0);
     }
-    if (SMEM) nb_flush_and_apply<float>(a, s_grad, s_cnt);
+    if (SMEM) nb_flush_and_apply<nb_fix_t>(a, s_grad, s_cnt, 1.0 / NB_GRAD_UNIT);
 }
 
 // ---------------------------------------------------------------------------
@@ -268,10 +275,10 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, in
 {
     extern __shared__ unsigned char s_raw[];
     __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
-    float *s_grad = (float *)s_raw;
-    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(float) * (size_t)(SMEM ? a.W : 0));
+    nb_fix_t *s_grad = (nb_fix_t *)s_raw;
+    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(nb_fix_t) * (size_t)(SMEM ? a.W : 0));
     if (SMEM) {
-        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0.0f; s_cnt[w] = 0u; }
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
         __syncthreads();
     }
     GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, in
         } else if (a.regularization != 2) cnt_inc = 0;
         nb_row_gradient<WIDE, SMEM>(r, 0, self, meta, ev, prop, a, cnt_inc, sink, lane, 32, inc, n_inc);
     }
-    if (SMEM) nb_flush_and_apply<float>(a, s_grad, s_cnt);
+    if (SMEM) nb_flush_and_apply<nb_fix_t>(a, s_grad, s_cnt, 1.0 / NB_GRAD_UNIT);
 }
 
 // ---------------------------------------------------------------------------
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
             }
         }
     }
-    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt);
+    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt, 1.0);
 }
 
 // Same algorithm, one WARP per row with the lanes striding over the row's quads: used when the
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, 
             sink.add(q.w, fF - fE, cinc);
         }
     }
-    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt);
+    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt, 1.0);
 }
 
 __global__ void k_apply_global_int(LearnArgs a)
@@ -512,13 +519,14 @@ __global__ void k_apply_global(LearnArgs a)
 {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.W) return;
-    float G = a.g_grad[w];
+    long long G = a.g_grad[w];
     uint32_t n = a.g_cnt[w];
-    if (G == 0.0f && n == 0u) return;
-    a.g_grad[w] = 0.0f;
+    if (G == 0 && n == 0u) return;
+    a.g_grad[w] = 0;
     a.g_cnt[w] = 0u;
     if (a.wfixed[w]) return;
-    a.weight[w] = nb_apply_update(a.weight[w], (double)G, n, a.regularization, a.step, a.reg_param, a.truncation);
+    a.weight[w] = nb_apply_update(a.weight[w], (double)G * (1.0 / NB_GRAD_UNIT), n, a.regularization, a.step, a.reg_param,
+                                  a.truncation);
 }
 
 // visits per weight of one colour (upper bound: every incidence of a learnable row)
@@ -629,7 +637,8 @@ template <bool WIDE, bool SMEM>
 static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int cb, int ce, int tb, int te,
                               int wb, int we, bool long_rows)
 {
-    size_t smem = SMEM ? (size_t)g->W * 8 : 0;
+    const size_t smem_tt = SMEM ? (size_t)g->W * 8 : 0;     // int32 sums + counts
+    const size_t smem = SMEM ? (size_t)g->W * 12 : 0;       // 64-bit fixed-point sums + counts
     const unsigned apply_grid = (unsigned)((g->W + 255) / 256);
     const int tt_range[2][2] = {{pb, pe}, {fb, fe}};                // PAIR rows, then FAST rows: both have TT quads
     for (int pass = 0; pass < 2; pass++) {
@@ -640,11 +649,11 @@ static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, i
         if (long_rows) {     // one warp per row
             int64_t need = ((int64_t)(re - rb) + NB_LWARPS - 1) / NB_LWARPS;
             unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
-            k_learn_tt_row<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, rb, re, kf, ke, kt);
+            k_learn_tt_row<SMEM><<<grid, NB_LEARN_THREADS, smem_tt, g->stream>>>(a, rb, re, kf, ke, kt);
         } else {             // one thread per row, one warp per SELL slice
             int64_t need = ((((int64_t)re + 31) >> 5) - (rb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
             unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
-            k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, rb, re, kf, ke, kt);
+            k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem_tt, g->stream>>>(a, rb, re, kf, ke, kt);
         }
         g->launches++;
         if (!SMEM) { k_apply_global_int<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }

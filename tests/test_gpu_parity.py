@@ -399,6 +399,23 @@ def test_lf_model_learning_long_rows(oracle):
     assert np.corrcoef(wg.mean(0)[1:], acc)[0, 1] > 0.9
 
 
+@pytest.mark.parametrize("name", ["bool_l2", "cat", "lf", "allfuncs"])
+def test_learning_is_deterministic(name):
+    """Gradient sums are integers (truth-table rows) or 64-bit fixed point (generic rows): the
+    reduction by weight id does not depend on the order of accumulation, so two runs with the
+    same seed give bit-identical weights and chains."""
+    z = golden("run_" + name)
+    o = golden_opts(z)
+    runs = []
+    for _ in range(2):
+        fg = _fg_from_golden(z, seed=123)
+        fg.learn(2, 40, 0.01, 0.97, o.get("regularization", 2), 0.01, o.get("truncation", 1),
+                 learn_non_evidence=o.get("learn_non_evidence", False))
+        runs.append((fg.weight_value.copy(), fg.var_value.copy(), fg.var_value_evid.copy()))
+    for a, b in zip(runs[0], runs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_learning_large_weight_table_path():
     """W > shared-memory table -> global accumulation path."""
     from numbskull_b200 import synth
@@ -413,6 +430,9 @@ def test_learning_large_weight_table_path():
     got = fg.weight_value[0][:3]
     assert np.abs(got - [1.0, 1.0, 0.5]).max() < 0.2, got
     assert (fg.weight_value[0][3:] == 0).all()
+    fg2 = _fg_from_synth((w2, v, f, fm, dm, e), seed=6)
+    fg2.learn(0, 300, 0.001, 0.99, 2, 0.0001, 1)
+    assert np.array_equal(fg2.weight_value, fg.weight_value)      # integer global table: deterministic
 
 
 # --------------------------------------------------------------------------- API drop-in
