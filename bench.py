@@ -167,6 +167,10 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        # stdout carries ONE JSON line: keep NCCL's banner ("NCCL version ...", printed to stdout when
+        # NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
                                 timeout=datetime.timedelta(seconds=180))
