@@ -152,7 +152,7 @@ def run_reference(args):
             "var_samples_per_sec": r["var_samples_per_sec"],
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -304,14 +304,36 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_port_throughput(steps=3, warmup=1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
 
 
+class _QuietStdout(object):
+    """stdout carries exactly ONE JSON line: everything libraries print there while the benchmark
+    runs (e.g. the "NCCL version ..." banner at communicator creation) is routed to stderr."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
+
+OUT = None
+
+
 def main():
+    global OUT
+    OUT = _QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -257,49 +257,66 @@ class PartitionedGibbs(object):
         import os
         self.p2p_nowait = 16 if os.environ.get("NUMBSKULL_B200_P2P_NOWAIT", "1") != "0" else 0
         if (world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("NUMBSKULL_B200_P2P", "1") != "0"):
-            self._setup_p2p(colors)
+            # every rank must end up on the same transport: fall back to NCCL point-to-point
+            # everywhere if any rank could not map its neighbours' memory
+            ok = 1 if self._setup_p2p(colors) else 0
+            t = torch.tensor([ok], device=self.dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            self.p2p = bool(int(t.item()))
 
     def _setup_p2p(self, colors):
         """Peer-to-peer halo: owners store boundary values straight into the neighbours' ghost
-        slots over NVLink (CUDA IPC mappings) and synchronise with a flag barrier in the kernel."""
+        slots over NVLink (CUDA IPC mappings) and synchronise with a flag barrier in the kernel.
+        Returns False (after taking part in every collective) if this rank cannot set it up."""
         L, lib, dist, g = self.lib.lib(), self.lib, self.dist, self.fg._g
         world, rank = self.world, self.rank
-        handles = np.zeros(3 * 64, np.uint8)
-        lib.check(L.nb_p2p_export(g, world, rank, lib.ptr(handles)))
-        # slots (new ids) of my ghosts, per owner, in the order the owner sends them
-        my_slots = []
-        for p in range(world):
-            ids = np.ascontiguousarray(self.plan.recv_ids[p], dtype=np.int32)
-            out = np.zeros(len(ids), np.int32)
-            if len(ids):
-                lib.check(L.nb_p2p_local_slots(g, lib.ptr(ids), len(ids), lib.ptr(out)))
-            my_slots.append(out.tolist())
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (handles.tobytes(), my_slots), group=self.group)
-        neigh = [p for p in range(world) if p != rank and (len(self.plan.send_ids[p]) or len(self.plan.recv_ids[p]))]
-        allh = np.zeros((world, 3 * 64), np.uint8)
-        for p in range(world):
-            allh[p] = np.frombuffer(gathered[p][0], np.uint8)
-        nb_arr = np.asarray(neigh, np.int32)
-        lib.check(L.nb_p2p_open(g, lib.ptr(allh), lib.ptr(nb_arr) if len(neigh) else None, len(neigh)))
-        src, peer, dst, ptr = [], [], [], [0]
-        for c in range(self.n_colors):
+        payload = None
+        try:
+            handles = np.zeros(3 * 64, np.uint8)
+            lib.check(L.nb_p2p_export(g, world, rank, lib.ptr(handles)))
+            # slots (new ids) of my ghosts, per owner, in the order the owner sends them
+            my_slots = []
             for p in range(world):
-                ids = self.plan.send_ids[p]
-                if not len(ids):
-                    continue
-                sel = colors[ids] == c
-                remote = np.asarray(gathered[p][1][rank], np.int32)     # p's slots for what I send it
-                src.append(ids[sel].astype(np.int32))
-                dst.append(remote[sel])
-                peer.append(np.full(int(sel.sum()), p, np.int32))
-            ptr.append(ptr[-1] + (sum(len(x) for x in src) - ptr[-1]))
-        cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.int32), dtype=np.int32)  # noqa: E731
-        src, peer, dst = cat(src), cat(peer), cat(dst)
-        ptr = np.asarray(ptr, np.int64)
-        lib.check(L.nb_p2p_set_plan(g, self.n_colors, lib.ptr(ptr), lib.ptr(src), lib.ptr(peer), lib.ptr(dst)))
-        dist.barrier(group=self.group)
-        self.p2p = True
+                ids = np.ascontiguousarray(self.plan.recv_ids[p], dtype=np.int32)
+                out = np.zeros(len(ids), np.int32)
+                if len(ids):
+                    lib.check(L.nb_p2p_local_slots(g, lib.ptr(ids), len(ids), lib.ptr(out)))
+                my_slots.append(out.tolist())
+            payload = (handles.tobytes(), my_slots)
+        except Exception as exc:  # noqa: BLE001
+            self.p2p_error = str(exc)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload, group=self.group)
+        if any(x is None for x in gathered):
+            return False
+        try:
+            neigh = [p for p in range(world)
+                     if p != rank and (len(self.plan.send_ids[p]) or len(self.plan.recv_ids[p]))]
+            allh = np.zeros((world, 3 * 64), np.uint8)
+            for p in range(world):
+                allh[p] = np.frombuffer(gathered[p][0], np.uint8)
+            nb_arr = np.asarray(neigh, np.int32)
+            lib.check(L.nb_p2p_open(g, lib.ptr(allh), lib.ptr(nb_arr) if len(neigh) else None, len(neigh)))
+            src, peer, dst, ptr = [], [], [], [0]
+            for c in range(self.n_colors):
+                for p in range(world):
+                    ids = self.plan.send_ids[p]
+                    if not len(ids):
+                        continue
+                    sel = colors[ids] == c
+                    remote = np.asarray(gathered[p][1][rank], np.int32)     # p's slots for what I send it
+                    src.append(ids[sel].astype(np.int32))
+                    dst.append(remote[sel])
+                    peer.append(np.full(int(sel.sum()), p, np.int32))
+                ptr.append(sum(len(x) for x in src))
+            cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.int32), dtype=np.int32)  # noqa: E731
+            src, peer, dst = cat(src), cat(peer), cat(dst)
+            ptr = np.asarray(ptr, np.int64)
+            lib.check(L.nb_p2p_set_plan(g, self.n_colors, lib.ptr(ptr), lib.ptr(src), lib.ptr(peer), lib.ptr(dst)))
+        except Exception as exc:  # noqa: BLE001  (CUDA IPC unavailable, peer access denied, ...)
+            self.p2p_error = str(exc)
+            return False
+        return True
 
     # -- device helpers
     def _exchange(self, c, chain):
