@@ -211,6 +211,13 @@ int nb_learn_color_phase(nb_graph *g, int color, int block, int n_blocks, double
  * owned, still uncoloured variables; ghosts are consulted through the colours last scattered
  * in.  *remaining = owned variables still uncoloured after the round. */
 int nb_color_round(nb_graph *g, int64_t *remaining);
+/* (Re)start the colouring of a deferred graph: mode 0 = hashed priorities, 1 = natural order (the
+ * smaller global id first; rounds are counted exactly, a colour taken in a round becomes visible in
+ * the next).  The library's own policy, which partition.py reproduces across the ranks: hashed
+ * first; if that needs more than 2 colours, natural order for at most nb_color_natural_round_cap()
+ * rounds; keep the natural colouring only if it finished and uses fewer colours. */
+int nb_color_restart(nb_graph *g, int mode);
+int nb_color_natural_round_cap(void);
 int nb_gather_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, int32_t *dev_out);
 int nb_scatter_colors_dev(nb_graph *g, const int32_t *dev_local_ids, int64_t n, const int32_t *dev_in);
 /* Colour order = visiting order.  Single-GPU graphs are relabelled so that colours are visited in

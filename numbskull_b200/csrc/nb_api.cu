@@ -415,6 +415,14 @@ extern "C" int nb_color_round(nb_graph *g, int64_t *remaining)
     return nb_build_color_round(g, remaining);
 }
 
+extern "C" int nb_color_restart(nb_graph *g, int mode)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    return nb_build_color_restart(g, mode);
+}
+
+extern "C" int nb_color_natural_round_cap(void) { return nb_natural_round_cap(); }
+
 extern "C" int nb_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids)
 {
     NB_CUDA(cudaSetDevice(g->device));

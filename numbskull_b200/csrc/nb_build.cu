@@ -3,6 +3,7 @@
 // incidence streams resident in HBM.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <cub/cub.cuh>
@@ -157,13 +158,15 @@ __host__ __device__ inline uint64_t nb_jp_priority(uint64_t gid, uint64_t seed)
 // neighbours once every neighbour of higher priority is coloured; the outcome
 // equals a sequential greedy colouring in priority order, whatever the schedule.
 // Colours are searched in windows of 64 (cbase); a full window defers to the next round.
-__global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *cbase, unsigned long long *remaining)
+__global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *cbase, int32_t *cround, int round, int mode,
+                           unsigned long long *remaining)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= G.V) return;
     if (G.v_evid[v] == 4) return;   // ghosts are coloured by their owner
     if (color[v] != -1) return;     // already coloured
-    const uint64_t pv = nb_jp_priority(G.gid ? (uint64_t)G.gid[v] : (uint64_t)v, seed);
+    const uint64_t gv = G.gid ? (uint64_t)G.gid[v] : (uint64_t)v;
+    const uint64_t pv = nb_jp_priority(gv, seed);
     const int base = cbase[v];
     uint64_t used = 0;
     bool ready = true;
@@ -180,9 +183,14 @@ __global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *c
                 if (u == v) continue;
                 int cu = ((volatile int32_t *)color)[u];
                 if (cu == -2) continue;
+                // natural-order mode counts rounds exactly (a colour taken in this round is not
+                // visible before the next one), so that the round cap means the same thing on one
+                // GPU and on a partitioned graph
+                if (mode == 1 && cu >= 0 && ((volatile int32_t *)cround)[u] >= round) cu = -1;
                 if (cu == -1) {
-                    uint64_t pu = nb_jp_priority(G.gid ? (uint64_t)G.gid[u] : (uint64_t)u, seed);
-                    if (pu > pv) { ready = false; break; }
+                    const uint64_t gu = G.gid ? (uint64_t)G.gid[u] : (uint64_t)u;
+                    const bool higher = mode == 1 ? gu < gv : nb_jp_priority(gu, seed) > pv;
+                    if (higher) { ready = false; break; }
                 } else if (cu >= base && cu < base + 64) {
                     used |= 1ull << (cu - base);
                 }
@@ -191,14 +199,18 @@ __global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *c
     }
     if (!ready) { atomicAdd(remaining, 1ull); return; }
     if (used == ~0ull) { cbase[v] = base + 64; atomicAdd(remaining, 1ull); return; }
+    if (mode == 1) { ((volatile int32_t *)cround)[v] = round; __threadfence(); }
     ((volatile int32_t *)color)[v] = base + (__ffsll((long long)~used) - 1);
 }
 
 // single-GPU graphs ignore ghosts (-2); partitioned graphs wait for the owner's colour (-1)
-__global__ void k_init_color(int64_t V, const int8_t *v_evid, int32_t *color, int deferred)
+__global__ void k_init_color(int64_t V, const int8_t *v_evid, int32_t *color, int32_t *cbase, int32_t *cround, int deferred)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (v < V) color[v] = (v_evid[v] == 4 && !deferred) ? -2 : -1;
+    if (v >= V) return;
+    color[v] = (v_evid[v] == 4 && !deferred) ? -2 : -1;
+    cbase[v] = 0;
+    cround[v] = v_evid[v] == 4 ? -1 : 0x7FFFFFFF;   // ghost colours arrive between rounds: always visible
 }
 
 // conflicts = ordered pairs (v, u) of owned variables that share a factor and a colour
@@ -786,12 +798,62 @@ int nb_build_color_round(nb_graph *g, int64_t *remaining)
 {
     RawGraph G = raw_view(g);
     NB_CUDA(cudaMemsetAsync(g->d_jpcnt, 0, 8, g->stream));
-    k_jp_round<<<grid_for(g->V), 256, 0, g->stream>>>(G, g->color_seed, g->d_color, g->d_cbase, g->d_jpcnt);
+    k_jp_round<<<grid_for(g->V), 256, 0, g->stream>>>(G, g->color_seed, g->d_color, g->d_cbase, g->d_cround, g->jp_round_no,
+                                                      g->jp_mode, g->d_jpcnt);
     unsigned long long rem = 0;
     NB_CUDA(cudaMemcpyAsync(&rem, g->d_jpcnt, 8, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
     g->jp_rounds++;
+    g->jp_round_no++;
     *remaining = (int64_t)rem;
+    return NB_OK;
+}
+
+// (re)start the colouring: mode 0 = hashed priorities (few rounds), 1 = natural order (smaller
+// global id first: the sequential greedy colouring in id order; 2 colours on grids and other
+// bipartite structured graphs, but as many rounds as the longest increasing-id path)
+int nb_build_color_restart(nb_graph *g, int mode)
+{
+    if (g->finalized) NB_FAIL(NB_ERR_INVALID, "graph already finalized");
+    g->jp_mode = mode;
+    g->jp_round_no = 0;
+    k_init_color<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_v_evid, g->d_color, g->d_cbase, g->d_cround,
+                                                        g->deferred ? 1 : 0);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+static int count_colors(nb_graph *g, int *n_colors)
+{
+    int *d_max;
+    NB_CUDA(cudaMalloc(&d_max, 4));
+    cudaMemsetAsync(d_max, 0xFF, 4, g->stream);  // -1
+    k_max_color<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_color, d_max);
+    int maxc = -1;
+    cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, g->stream);
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_max);
+    NB_CUDA(e);
+    *n_colors = maxc + 1;
+    return NB_OK;
+}
+
+int nb_natural_round_cap(void)
+{
+    const char *env = getenv("NUMBSKULL_B200_NATURAL_ROUNDS");
+    return env ? atoi(env) : 65536;
+}
+
+static int run_jp(nb_graph *g, int mode, int64_t cap, bool *finished)
+{
+    NB_TRY(nb_build_color_restart(g, mode));
+    *finished = false;
+    for (int64_t r = 0; cap <= 0 || r < cap; r++) {
+        int64_t rem = 0;
+        NB_TRY(nb_build_color_round(g, &rem));
+        if (rem == 0) { *finished = true; break; }
+        if (r > 4000000) NB_FAIL(NB_ERR_CUDA, "Jones-Plassmann colouring did not converge");
+    }
     return NB_OK;
 }
 
@@ -802,6 +864,7 @@ static int color_graph(nb_graph *g, const nb_graph_desc *d)
     NB_TRY(nb_alloc(g, &g->d_color, (size_t)V, false));
     NB_TRY(nb_alloc(g, &g->d_jpcnt, 2));
     NB_TRY(nb_alloc(g, &g->d_cbase, (size_t)V));
+    NB_TRY(nb_alloc(g, &g->d_cround, (size_t)V));
     g->color_seed = d->color_seed;
     if (d->preset_color) {
         NB_CUDA(cudaMemcpyAsync(g->d_color, d->preset_color, (size_t)V * 4, cudaMemcpyHostToDevice, g->stream));
@@ -812,13 +875,28 @@ static int color_graph(nb_graph *g, const nb_graph_desc *d)
         if (bad) NB_FAIL(NB_ERR_INVALID, "preset colouring has %llu conflicts", bad);
         return NB_OK;
     }
-    k_init_color<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_v_evid, g->d_color, g->deferred ? 1 : 0);
-    if (g->deferred) return NB_OK;   // the caller drives nb_color_round + the ghost exchange
-    for (;;) {
-        int64_t rem = 0;
-        NB_TRY(nb_build_color_round(g, &rem));
-        if (rem == 0) break;
-        if (g->jp_rounds > 1000000) NB_FAIL(NB_ERR_CUDA, "Jones-Plassmann colouring did not converge");
+    if (g->deferred) return nb_build_color_restart(g, 0);   // the caller drives nb_color_round + the ghost exchange
+    // hashed priorities first (a dozen rounds); if that needs more than two colours, try the
+    // natural order under a round cap and keep whichever colouring is smaller
+    bool done = false;
+    NB_TRY(run_jp(g, 0, 0, &done));
+    int nc_hash = 0;
+    NB_TRY(count_colors(g, &nc_hash));
+    const int cap = nb_natural_round_cap();
+    if (nc_hash > 2 && cap > 0) {
+        int32_t *d_saved;
+        NB_CUDA(cudaMalloc(&d_saved, (size_t)std::max<int64_t>(V, 1) * 4));
+        cudaMemcpyAsync(d_saved, g->d_color, (size_t)V * 4, cudaMemcpyDeviceToDevice, g->stream);
+        int rc = run_jp(g, 1, cap, &done);
+        int nc_nat = 0;
+        if (rc == NB_OK && done) rc = count_colors(g, &nc_nat);
+        if (rc != NB_OK || !done || nc_nat >= nc_hash) {
+            cudaMemcpyAsync(g->d_color, d_saved, (size_t)V * 4, cudaMemcpyDeviceToDevice, g->stream);
+            g->jp_mode = 0;
+        }
+        cudaStreamSynchronize(g->stream);
+        cudaFree(d_saved);
+        NB_TRY(rc);
     }
     return NB_OK;
 }

@@ -232,6 +232,9 @@ struct nb_graph {
     uint32_t *d_ninc0 = nullptr;     // [V] incidences
     uint8_t *d_fast0 = nullptr;      // [V] FAST-class flag
     int32_t *d_cbase = nullptr;      // [V] JP colour window
+    int32_t *d_cround = nullptr;     // [V] round in which a variable took its colour (natural-order mode)
+    int jp_mode = 0;                 // 0 = hashed priorities, 1 = natural order
+    int jp_round_no = 0;
     unsigned long long *d_jpcnt = nullptr;
     uint64_t color_seed = 0;
     bool finalized = false;
@@ -332,6 +335,8 @@ void nb_p2p_wait_args(nb_graph *g, const volatile uint32_t **flags, const int32_
 // build steps (nb_build.cu)
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);
 int nb_build_color_round(nb_graph *g, int64_t *remaining);
+int nb_build_color_restart(nb_graph *g, int mode);
+int nb_natural_round_cap(void);
 int nb_build_finalize(nb_graph *g);
 int nb_build_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids);
 int nb_build_relabel_colors(nb_graph *g, const int32_t *map, int n);

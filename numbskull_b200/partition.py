@@ -213,25 +213,46 @@ class PartitionedGibbs(object):
 
         # ---- distributed Jones-Plassmann ----
         full = Exchange(self.plan.send_ids, self.plan.recv_ids, rank, world, torch.int32, self.dev, group)
-        rounds = 0
-        while True:
-            rem = C.c_int64(0)
-            _lib.check(L.nb_color_round(g, C.byref(rem)))
-            full.run(lambda ids, out: _lib.check(L.nb_gather_colors_dev(g, ids.data_ptr(), ids.numel(), out.data_ptr())),
-                     lambda ids, buf: _lib.check(L.nb_scatter_colors_dev(g, ids.data_ptr(), ids.numel(), buf.data_ptr())))
-            t = torch.tensor([rem.value], device=self.dev, dtype=torch.int64)
+        def run_jp(mode, cap):
+            """One distributed colouring attempt; returns (finished, rounds, global colour count)."""
+            _lib.check(L.nb_color_restart(g, mode))
+            rounds, finished = 0, False
+            while cap <= 0 or rounds < cap:
+                rem = C.c_int64(0)
+                _lib.check(L.nb_color_round(g, C.byref(rem)))
+                full.run(lambda ids, out: _lib.check(L.nb_gather_colors_dev(g, ids.data_ptr(), ids.numel(), out.data_ptr())),
+                         lambda ids, buf: _lib.check(L.nb_scatter_colors_dev(g, ids.data_ptr(), ids.numel(), buf.data_ptr())))
+                t = torch.tensor([rem.value], device=self.dev, dtype=torch.int64)
+                if world > 1:
+                    dist.all_reduce(t, group=group)
+                rounds += 1
+                if int(t.item()) == 0:
+                    finished = True
+                    break
+            torch.cuda.synchronize()
+            if not finished:
+                return False, rounds, 0
+            colors = fg.colors()
+            t = torch.tensor([int(colors.max()) + 1 if len(colors) else 0], device=self.dev, dtype=torch.int64)
             if world > 1:
-                dist.all_reduce(t, group=group)
-            rounds += 1
-            if int(t.item()) == 0:
-                break
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            return True, rounds, int(t.item())
+
+        # same policy as the single-GPU build (nb_build.cu color_graph): hashed priorities; if that
+        # needs more than two colours, the natural order under the round cap; keep the smaller one.
+        # Rounds are counted identically on one GPU and across ranks, so the choice is the same.
+        _, rounds, self.n_colors = run_jp(0, 0)
+        self.jp_mode = 0
+        cap = int(L.nb_color_natural_round_cap())
+        if self.n_colors > 2 and cap > 0:
+            done, r1, nc = run_jp(1, cap)
+            rounds += r1
+            if done and nc < self.n_colors:
+                self.n_colors, self.jp_mode = nc, 1
+            else:
+                _, r2, self.n_colors = run_jp(0, 0)
+                rounds += r2
         self.jp_rounds = rounds
-        torch.cuda.synchronize()
-        colors = fg.colors()
-        t = torch.tensor([int(colors.max()) + 1 if len(colors) else 0], device=self.dev, dtype=torch.int64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        self.n_colors = int(t.item())
         # visit colours in increasing order of their smallest global variable id (same rule as the
         # single-GPU build, decided globally so that every rank relabels identically)
         mins = np.full(max(self.n_colors, 1), np.iinfo(np.int64).max, np.int64)

@@ -127,7 +127,7 @@ def test_coloring_bit_exact_and_valid(oracle, name):
     z = golden("run_" + name)
     fg = _fg_from_golden(z)
     colors = fg.colors()
-    want = oracle.coloring.greedy_coloring(fg.variable, fg.factor, fg.fmap, fg.color_seed)
+    want, _ = oracle.coloring.policy_coloring(fg.variable, fg.factor, fg.fmap, fg.color_seed)
     assert np.array_equal(colors, want)
     assert oracle.coloring.conflicts(fg.variable, fg.factor, fg.fmap, colors) == 0
     import ctypes as C
@@ -145,9 +145,32 @@ def test_coloring_ghosts_and_global_ids(oracle):
     gid = np.random.default_rng(1).permutation(1000)[:200].astype(np.int64)
     fg = _fg_from_synth(tuple(g), global_vid=gid)
     colors = fg.colors()
-    want = oracle.coloring.greedy_coloring(fg.variable, fg.factor, fg.fmap, fg.color_seed, gid)
+    want, _ = oracle.coloring.policy_coloring(fg.variable, fg.factor, fg.fmap, fg.color_seed, gid)
     assert np.array_equal(colors, want)
     assert (colors[::7] == -1).all()
+
+
+def test_coloring_natural_order_policy(oracle, monkeypatch):
+    """Grids: hashed priorities need 4-5 colours, the natural order 2 in rows + cols - 1 rounds;
+    the library keeps the natural colouring iff it finishes under the round cap."""
+    from numbskull_b200 import synth
+    g = synth.ising_grid(24, 17)
+    fg = _fg_from_synth(g)
+    colors = fg.colors()
+    want, mode = oracle.coloring.policy_coloring(fg.variable, fg.factor, fg.fmap, fg.color_seed)
+    assert mode == 1 and np.array_equal(colors, want)
+    rr, cc = np.divmod(np.arange(24 * 17), 17)
+    assert np.array_equal(colors, (rr + cc) % 2)
+    assert fg.device_info()["n_colors"] == 2
+    adj = oracle.coloring.neighbours(fg.variable, fg.factor, fg.fmap)
+    assert oracle.coloring.natural_rounds(fg.variable, adj, np.arange(24 * 17)) == 24 + 17 - 1
+    for cap, exp_mode in ((24 + 17 - 1, 1), (24 + 17 - 2, 0), (0, 0)):
+        monkeypatch.setenv("NUMBSKULL_B200_NATURAL_ROUNDS", str(cap))
+        fg2 = _fg_from_synth(g)
+        want, mode = oracle.coloring.policy_coloring(fg2.variable, fg2.factor, fg2.fmap, fg2.color_seed, cap=cap)
+        assert mode == exp_mode
+        assert np.array_equal(fg2.colors(), want)
+        assert (fg2.device_info()["n_colors"] == 2) == (exp_mode == 1)
 
 
 # --------------------------------------------------------------------------- marginals
@@ -537,6 +560,7 @@ def test_ising_full_size_properties():
     bad = C.c_int64(-1)
     _lib.check(_lib.lib().nb_graph_check_coloring(fg._device_graph(), C.byref(bad)))
     assert bad.value == 0
+    assert info["n_colors"] == 2            # natural-order colouring: the checkerboard
     fg.inference(5, 20, sample_evidence=True)
     c1 = fg.count.copy()
     assert 0 <= c1.min() and c1.max() <= 20

@@ -126,3 +126,17 @@ def test_exact_marginals_three_var_graph(oracle):
     assert np.allclose(m, [0.8716, 0.7541, 0.6248], atol=5e-5)
     og.inference(100, 20000, sample_evidence=True)
     assert np.abs(og.marginals - m).max() < 0.01
+
+
+def test_coloring_policy_checker(oracle):
+    """The colouring checker itself: valid colourings, checkerboard on a grid under the cap,
+    hashed priorities above it."""
+    from numbskull_b200 import synth
+    _, v, f, fm, _, _ = synth.ising_grid(9, 7)
+    col, mode = oracle.coloring.policy_coloring(v, f, fm, 0x5EED)
+    rr, cc = np.divmod(np.arange(63), 7)
+    assert mode == 1 and np.array_equal(col, (rr + cc) % 2)
+    col, mode = oracle.coloring.policy_coloring(v, f, fm, 0x5EED, cap=14)
+    assert mode == 0 and col.max() >= 2
+    assert oracle.coloring.conflicts(v, f, fm, col) == 0
+    assert np.array_equal(col, oracle.coloring.greedy_coloring(v, f, fm, 0x5EED))
