@@ -285,9 +285,11 @@ def run_ours(args):
         "config": {"workload": "ising_%dx%d_equal_inference%s" % (rows * world, cols,
                                                                  "" if world == 1 else "_strips_of_%d_rows" % rows),
                    "variables": total_vars, "factor_edge_evals_per_sweep": total_edges,
-                   "colors": info["n_colors"], "l2_policy": "inputs larger than L2 (incidence stream %.0f MB vs 126 MB)"
+                   "colors": info["n_colors"] if runner is None else runner.n_colors, "l2_policy": "inputs larger than L2 (incidence stream %.0f MB vs 126 MB)"
                    % (info["stream_words"] * 4 / 1e6),
-                   "partition": "single GPU" if world == 1 else "row strips, per-colour halo exchange"},
+                   "partition": "single GPU" if world == 1 else
+                   ("row strips; per colour a boundary phase + NVLink halo push on a side stream, concurrent with "
+                    "the interior phase" if runner.p2p and runner.split else "row strips, per-colour halo exchange")},
         "var_samples_per_sec": total_vars * steps / (dev_ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(), "peak_source": peak_src,

@@ -243,9 +243,16 @@ int nb_p2p_set_plan(nb_graph *g, int n_colors, const int64_t *color_ptr, const i
 int nb_p2p_exchange(nb_graph *g, int color, int chain_mask);
 int nb_p2p_wait(nb_graph *g);   /* block the stream until every neighbour reached the latest phase */
 /* nb_gibbs_sweeps for a partitioned graph: per colour the sweep kernels and the halo push, launched
- * back to back from C (n_colors = the GLOBAL colour count). */
+ * back to back from C (n_colors = the GLOBAL phase count).  mode bit 0: split-phase exchange
+ * (NB_P2P_NOWAIT); bit 1: the colours were split with nb_split_colors -- the boundary phase 2c and
+ * its push run on a high-priority side stream concurrently with the interior phase 2c + 1, so the
+ * exchange is off the critical path. */
 int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, int sample_evidence, uint64_t seed,
-                        int n_colors, int nowait);
+                        int n_colors, int mode);
+/* Before nb_graph_finalize of a deferred graph: colour c becomes the phases 2c (ghosts and
+ * `boundary_ids`, the owned variables other ranks hold copies of) and 2c + 1 (interior variables,
+ * which never read a ghost).  Every rank must split (or none). */
+int nb_split_colors(nb_graph *g, const int32_t *boundary_ids, int64_t n);
 int nb_p2p_check(nb_graph *g);
 /* run the sweeps on a caller-owned CUDA stream (cudaStream_t as void*) */
 int nb_set_stream(nb_graph *g, void *cuda_stream);

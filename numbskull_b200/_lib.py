@@ -86,6 +86,7 @@ SIGNATURES = {
     "nb_learn_blocks": (C.c_int, [_P, _DBL, C.c_int, _I64, C.POINTER(C.c_int)]),
     "nb_color_round": (C.c_int, [_P, C.POINTER(_I64)]),
     "nb_color_restart": (C.c_int, [_P, C.c_int]),
+    "nb_split_colors": (C.c_int, [_P, _P, _I64]),
     "nb_color_natural_round_cap": (C.c_int, []),
     "nb_gather_colors_dev": (C.c_int, [_P, _P, _I64, _P]),
     "nb_scatter_colors_dev": (C.c_int, [_P, _P, _I64, _P]),

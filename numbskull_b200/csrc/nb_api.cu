@@ -435,6 +435,42 @@ extern "C" int nb_relabel_colors(nb_graph *g, const int32_t *map, int n)
     return nb_build_relabel_colors(g, map, n);
 }
 
+// Split every colour c of a partitioned (deferred) graph into the phases 2c (ghosts and the owned
+// variables some other rank holds a copy of: `boundary_ids`, local ids) and 2c + 1 (interior
+// variables, which never read a ghost).  The boundary phase is tiny; its halo push then travels
+// while the interior phase runs (nb_gibbs_sweeps_p2p mode 2).
+__global__ void k_split_all(int64_t V, const int8_t *evid, int32_t *color)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v < V && color[v] >= 0) color[v] = 2 * color[v] + (evid[v] == 4 ? 0 : 1);
+}
+__global__ void k_split_boundary(int64_t n, const int32_t *ids, int32_t *color)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && color[ids[i]] >= 0) color[ids[i]] &= ~1;
+}
+
+extern "C" int nb_split_colors(nb_graph *g, const int32_t *boundary_ids, int64_t n)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    if (g->finalized || !g->deferred) NB_FAIL(NB_ERR_INVALID, "nb_split_colors needs a deferred graph before nb_graph_finalize");
+    for (int64_t i = 0; i < n; i++)
+        if (boundary_ids[i] < 0 || boundary_ids[i] >= g->V) NB_FAIL(NB_ERR_INVALID, "boundary id out of range");
+    const unsigned grid = (unsigned)((std::max<int64_t>(g->V, 1) + 255) / 256);
+    k_split_all<<<grid, 256, 0, g->stream>>>(g->V, g->d_v_evid, g->d_color);
+    if (n) {
+        int32_t *d_ids;
+        NB_CUDA(cudaMalloc(&d_ids, (size_t)n * 4));
+        cudaMemcpyAsync(d_ids, boundary_ids, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream);
+        k_split_boundary<<<(unsigned)((n + 255) / 256), 256, 0, g->stream>>>(n, d_ids, g->d_color);
+        cudaError_t e = cudaStreamSynchronize(g->stream);
+        cudaFree(d_ids);
+        NB_CUDA(e);
+    }
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
 extern "C" int nb_graph_finalize(nb_graph *g)
 {
     NB_CUDA(cudaSetDevice(g->device));

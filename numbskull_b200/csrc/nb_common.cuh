@@ -310,6 +310,7 @@ struct nb_graph {
     size_t flush_bytes = 0;
 
     void *p2p = nullptr;               // NbP2P (nb_p2p.cu)
+    bool halo_wait_off = false;        // launches of phases that never read a ghost skip the halo wait
     int64_t n_win = 0;                 // id windows (original id >> sigma_shift)
     std::vector<int32_t> win_start;    // [NB_N_CLASSES * (n_colors + 1)][n_win + 1] first new id of each window per group
     std::vector<int64_t> learn_vmax;   // per colour: max gradient visits of one weight

@@ -25,6 +25,8 @@ struct NbP2P {
     uint32_t *d_done = nullptr;
     int *d_error = nullptr;
     uint32_t phase = 0;
+    cudaStream_t side = nullptr;           // high-priority stream of the boundary phases (split mode)
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 };
 
 static NbP2P *p2p_of(nb_graph *g) { return (NbP2P *)g->p2p; }
@@ -234,15 +236,62 @@ void nb_p2p_wait_args(nb_graph *g, const volatile uint32_t **flags, const int32_
                       int **error)
 {
     NbP2P *p = p2p_of(g);
-    if (!p || p->color_ptr.empty()) { *n_neigh = 0; *flags = nullptr; *neigh = nullptr; *phase = 0; *error = nullptr; return; }
+    if (!p || p->color_ptr.empty() || g->halo_wait_off) { *n_neigh = 0; *flags = nullptr; *neigh = nullptr; *phase = 0; *error = nullptr; return; }
     *flags = p->d_flags; *neigh = p->d_neigh; *n_neigh = p->n_neigh; *phase = p->phase; *error = p->d_error;
 }
 
+// Split mode: phases 2c (boundary) and 2c + 1 (interior) of colour c run concurrently -- they are
+// the same colour, so independent.  The boundary phase and its halo push go to a high-priority
+// side stream, the interior phase stays on the graph's stream:
+//   side:  wait(interior c-1) -> boundary c (waits for the peers' push of c-1) -> push c
+//   main:  wait(boundary c-1) -> interior c
+// so the push and the peers' signals travel while the interior kernel runs, and the main stream
+// never stalls on the exchange.
+static int sweeps_split(nb_graph *g, NbP2P *p, int64_t n_epochs, int burnin, int sample_evidence, uint64_t seed, int n_phases)
+{
+    if (!p->side) {
+        int lo = 0, hi = 0;
+        NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        NB_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi));
+        NB_CUDA(cudaEventCreateWithFlags(&p->ev_main, cudaEventDisableTiming));
+        NB_CUDA(cudaEventCreateWithFlags(&p->ev_side, cudaEventDisableTiming));
+    }
+    cudaStream_t main_s = g->stream, side = p->side;
+    int rc = NB_OK;
+    bool first = true;
+    NB_CUDA(cudaEventRecord(p->ev_main, main_s));
+    for (int64_t ep = 0; ep < n_epochs && rc == NB_OK; ep++) {
+        const uint64_t epoch = g->epoch_counter++;
+        for (int c = 0; c < n_phases && rc == NB_OK; c += 2) {
+            if (!first) NB_CUDA(cudaStreamWaitEvent(main_s, p->ev_side, 0));    // boundary of the previous colour
+            NB_CUDA(cudaStreamWaitEvent(side, p->ev_main, 0));                  // interior of the previous colour
+            first = false;
+            g->stream = side;
+            rc = nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch);
+            if (rc == NB_OK) rc = nb_p2p_exchange(g, c, 1 | 16);
+            g->stream = main_s;
+            if (rc != NB_OK) break;
+            NB_CUDA(cudaEventRecord(p->ev_side, side));
+            g->halo_wait_off = true;
+            rc = nb_launch_gibbs_color(g, c + 1, burnin, sample_evidence, seed, epoch);
+            g->halo_wait_off = false;
+            if (rc != NB_OK) break;
+            NB_CUDA(cudaEventRecord(p->ev_main, main_s));
+        }
+    }
+    g->stream = main_s;
+    g->halo_wait_off = false;
+    if (!first) NB_CUDA(cudaStreamWaitEvent(main_s, p->ev_side, 0));
+    return rc;
+}
+
 // n_epochs chromatic sweeps of a partitioned graph, launched back to back from C: per colour the
-// colour's kernels and the halo push; n_colors is the GLOBAL colour count (ranks that own nothing
-// of a colour still take part in its exchange).
+// colour's kernels and the halo push; n_colors is the GLOBAL phase count (ranks that own nothing
+// of a colour still take part in its exchange).  mode: bit 0 = split-phase exchange (signal only,
+// the next kernels wait in their prologue), bit 1 = the colours were split with nb_split_colors
+// (n_colors counts both phases of every colour; implies bit 0).
 extern "C" int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, int sample_evidence, uint64_t seed,
-                                   int n_colors, int nowait)
+                                   int n_colors, int mode)
 {
     NB_CUDA(cudaSetDevice(g->device));
     NbP2P *p = p2p_of(g);
@@ -250,11 +299,17 @@ extern "C" int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, in
     if (g->has_unknown_func)
         NB_FAIL(NB_ERR_NOT_IMPLEMENTED, "Error: Factor Function %d ( used in factor %lld ) is not implemented.",
                 g->unknown_func_id, (long long)g->unknown_func_factor);
-    for (int64_t ep = 0; ep < n_epochs; ep++) {
-        const uint64_t epoch = g->epoch_counter++;
-        for (int c = 0; c < n_colors; c++) {
-            NB_TRY(nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch));
-            NB_TRY(nb_p2p_exchange(g, c, 1 | (nowait ? 16 : 0)));
+    const int nowait = mode & 3;
+    if (mode & 2) {
+        if (n_colors & 1) NB_FAIL(NB_ERR_INVALID, "split mode needs an even phase count");
+        NB_TRY(sweeps_split(g, p, n_epochs, burnin, sample_evidence, seed, n_colors));
+    } else {
+        for (int64_t ep = 0; ep < n_epochs; ep++) {
+            const uint64_t epoch = g->epoch_counter++;
+            for (int c = 0; c < n_colors; c++) {
+                NB_TRY(nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch));
+                NB_TRY(nb_p2p_exchange(g, c, 1 | (nowait ? 16 : 0)));
+            }
         }
     }
     if (nowait && n_epochs > 0) NB_TRY(nb_p2p_wait(g));
@@ -277,6 +332,7 @@ void nb_p2p_destroy(nb_graph *g)
 {
     NbP2P *p = p2p_of(g);
     if (!p) return;
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_main); cudaEventDestroy(p->ev_side); }
     for (void *q : p->opened) cudaIpcCloseMemHandle(q);
     cudaFree(p->d_peer_val[0]); cudaFree(p->d_peer_val[1]); cudaFree(p->d_peer_flags); cudaFree(p->d_flags);
     cudaFree(p->d_neigh); cudaFree(p->d_src); cudaFree(p->d_peer); cudaFree(p->d_dst); cudaFree(p->d_done); cudaFree(p->d_error);

@@ -264,18 +264,31 @@ class PartitionedGibbs(object):
         cmap = np.empty(self.n_colors, np.int32)
         cmap[order] = np.arange(self.n_colors, dtype=np.int32)
         _lib.check(L.nb_relabel_colors(g, _lib.ptr(cmap), self.n_colors))
+        # Split every colour into a boundary phase (2c: the owned variables other ranks hold copies
+        # of, a few rows) and an interior phase (2c + 1: variables that never read a ghost), so the
+        # halo push of a colour travels while its interior is still being sampled.  Variables of
+        # one colour are independent, so the samples do not change.
+        import os
+        self.split = world > 1 and os.environ.get("NUMBSKULL_B200_SPLIT", "1") != "0"
+        if self.split:
+            sends = [ids for ids in self.plan.send_ids if len(ids)]
+            bnd = np.unique(np.concatenate(sends)).astype(np.int32) if sends else np.zeros(0, np.int32)
+            _lib.check(L.nb_split_colors(g, _lib.ptr(bnd) if len(bnd) else None, len(bnd)))
+        self.n_phases = self.n_colors * (2 if self.split else 1)
         _lib.check(L.nb_graph_finalize(g))
-        colors = fg.colors()
-        self.colors = colors
+        phases = fg.colors()
+        self.phases = phases
+        self.colors = phases >> 1 if self.split else phases
+        colors = phases
 
-        # ---- per-colour halo exchanges (uint8 values) ----
+        # ---- per-phase halo exchanges (uint8 values); interior phases have none ----
         self.halo = []
-        for c in range(self.n_colors):
+        for c in range(self.n_phases):
             send, recv = self.plan.restrict(colors == c)
+            assert not (self.split and c % 2 == 1 and (sum(map(len, send)) or sum(map(len, recv))))
             self.halo.append(Exchange(send, recv, rank, world, torch.uint8, self.dev, group))
         self.halo_bytes_per_sweep = sum(h.n_send for h in self.halo)
         self.p2p = False
-        import os
         self.p2p_nowait = 16 if os.environ.get("NUMBSKULL_B200_P2P_NOWAIT", "1") != "0" else 0
         if (world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("NUMBSKULL_B200_P2P", "1") != "0"):
             # every rank must end up on the same transport: fall back to NCCL point-to-point
@@ -319,7 +332,7 @@ class PartitionedGibbs(object):
             nb_arr = np.asarray(neigh, np.int32)
             lib.check(L.nb_p2p_open(g, lib.ptr(allh), lib.ptr(nb_arr) if len(neigh) else None, len(neigh)))
             src, peer, dst, ptr = [], [], [], [0]
-            for c in range(self.n_colors):
+            for c in range(self.n_phases):
                 for p in range(world):
                     ids = self.plan.send_ids[p]
                     if not len(ids):
@@ -333,13 +346,17 @@ class PartitionedGibbs(object):
             cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.int32), dtype=np.int32)  # noqa: E731
             src, peer, dst = cat(src), cat(peer), cat(dst)
             ptr = np.asarray(ptr, np.int64)
-            lib.check(L.nb_p2p_set_plan(g, self.n_colors, lib.ptr(ptr), lib.ptr(src), lib.ptr(peer), lib.ptr(dst)))
+            lib.check(L.nb_p2p_set_plan(g, self.n_phases, lib.ptr(ptr), lib.ptr(src), lib.ptr(peer), lib.ptr(dst)))
         except Exception as exc:  # noqa: BLE001  (CUDA IPC unavailable, peer access denied, ...)
             self.p2p_error = str(exc)
             return False
         return True
 
     # -- device helpers
+    def _has_halo(self, c):
+        """Interior phases (odd, split mode) exchange nothing on any rank."""
+        return not (self.split and c % 2 == 1)
+
     def _exchange(self, c, chain):
         L, g, lib = self.lib.lib(), self.fg._g, self.lib
         if self.p2p:
@@ -354,16 +371,17 @@ class PartitionedGibbs(object):
         L, g, lib = self.lib.lib(), self.fg._g, self.lib
         if self.world > 1 and self.p2p:
             # the whole launch sequence (colour kernels + halo pushes) is issued from C
+            mode = (1 if self.p2p_nowait else 0) | (2 if self.split and self.p2p_nowait else 0)
             lib.check(L.nb_gibbs_sweeps_p2p(g, int(n), int(bool(burnin)), int(bool(sample_evidence)), self.fg.seed,
-                                            self.n_colors, 1 if self.p2p_nowait else 0))
+                                            self.n_phases, mode))
             return
         for _ in range(n):
             ep = C.c_int64(0)
             lib.check(L.nb_begin_epoch(g, C.byref(ep)))
-            for c in range(self.n_colors):
+            for c in range(self.n_phases):
                 lib.check(L.nb_gibbs_color_phase(g, c, int(bool(burnin)), int(bool(sample_evidence)),
                                                  self.fg.seed, ep.value))
-                if self.world > 1:
+                if self.world > 1 and self._has_halo(c):
                     if self.p2p:
                         # push + signal only; the next colour's kernels wait for the neighbours' signal
                         lib.check(L.nb_p2p_exchange(g, c, 1 | self.p2p_nowait))
@@ -410,11 +428,11 @@ class PartitionedGibbs(object):
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
                 n_blocks = int(t.item())
             for b in range(n_blocks):
-                for c in range(self.n_colors):
+                for c in range(self.n_phases):
                     lib.check(L.nb_learn_color_phase(g, c, b, n_blocks, float(stepsize), int(regularization),
                                                      float(reg_param), float(truncation),
                                                      int(bool(learn_non_evidence)), fg.seed, ep.value))
-                    if self.world > 1:
+                    if self.world > 1 and self._has_halo(c):
                         if self.p2p:
                             lib.check(L.nb_p2p_exchange(g, c, 3))
                         else:

@@ -17,7 +17,7 @@ for mode, mask in (("blocking", 1), ("nowait", 1 | 16)):
     torch.cuda.synchronize(); dist.barrier()
     _lib.check(L.nb_timer_start(g))
     for i in range(n):
-        _lib.check(L.nb_p2p_exchange(g, i % run.n_colors, mask))
+        _lib.check(L.nb_p2p_exchange(g, (2 * i) % run.n_phases if run.split else i % run.n_phases, mask))
     _lib.check(L.nb_p2p_wait(g))
     ms = C.c_float(0); _lib.check(L.nb_timer_stop(g, C.byref(ms)))
     if rank == 0:
