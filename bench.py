@@ -260,10 +260,11 @@ def run_ours(args):
         barrier()
         e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     V, Wn = len(fg.variable), len(fg.weight)
-    # bytes that cross PCIe per step: values travel as 1 byte, counts as 4 (narrowed / widened
+    # bytes that cross PCIe per step: values travel as 1 byte, the tallies of a call of <= 255
+    # epochs as 1 byte too (4 otherwise) + the 4-byte maximum that decides it (narrowed / widened
     # on the host next to pinned staging buffers), weights as float64
     h2d = V * 1 + Wn * 8
-    d2h = V * 1 + len(fg.count) * 4
+    d2h = V * 1 + len(fg.count) * 1 + 4
 
     if rank != 0:
         if world > 1:

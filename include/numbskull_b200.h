@@ -209,7 +209,7 @@ int nb_learn_color_phase(nb_graph *g, int color, int block, int n_blocks, double
                          double reg_param, double truncation, int learn_non_evidence, uint64_t seed, int64_t epoch);
 /* Distributed Jones-Plassmann (graphs created with deferred_coloring): one round over the
  * owned, still uncoloured variables; ghosts are consulted through the colours last scattered
- * in.  *remaining = owned variables still uncoloured after the round. */
+ * in.  *remaining != 0 iff an owned variable is still uncoloured after the round. */
 int nb_color_round(nb_graph *g, int64_t *remaining);
 /* (Re)start the colouring of a deferred graph: mode 0 = hashed priorities, 1 = natural order (the
  * smaller global id first; rounds are counted exactly, a colour taken in a round becomes visible in

@@ -50,6 +50,8 @@ extern "C" void nb_graph_destroy(nb_graph *g)
     if (g->d_xfer) cudaFree(g->d_xfer);
     if (g->d_flush) cudaFree(g->d_flush);
     if (g->h_pinned) cudaFreeHost(g->h_pinned);
+    for (cudaEvent_t e : g->xfer_events) cudaEventDestroy(e);
+    nb_release_color_scratch(g);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->stream && g->own_stream) cudaStreamDestroy(g->stream);
@@ -90,19 +92,60 @@ extern "C" int nb_graph_color_edges(const nb_graph *g, int64_t *edges_per_color)
 // next to pinned staging buffers, so only 1 byte per variable and 4 bytes per
 // count entry cross PCIe.
 // ---------------------------------------------------------------------------
+// The host conversion runs chunk by chunk on a few threads and overlaps with the PCIe copies:
+// uploads are copied as soon as a chunk is narrowed, downloads are widened as soon as the chunk's
+// copy has landed (one event per chunk).
+static const int64_t NB_XFER_CHUNK = 1 << 18;   // elements
+
 template <class F>
-static void host_parallel(int64_t n, F fn)
+static int host_chunks(nb_graph *g, int64_t n, F fn)   // fn(chunk index, begin, end) -> cudaError_t
 {
-    int nt = n > (1 << 18) ? (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    if (nt == 1) { fn(0, n); return; }
-    std::vector<std::thread> th;
-    int64_t chunk = ((n + nt - 1) / nt + 63) & ~63ll;
-    for (int t = 0; t < nt; t++) {
-        int64_t a = t * chunk, b = std::min(n, a + chunk);
-        if (a >= b) break;
-        th.emplace_back([=] { fn(a, b); });
+    const int64_t nchunks = (n + NB_XFER_CHUNK - 1) / NB_XFER_CHUNK;
+    int nt = (int)std::min<int64_t>(nchunks, std::min(32u, std::max(1u, std::thread::hardware_concurrency())));
+    std::atomic<int64_t> next(0);
+    std::atomic<int> err(0);
+    auto work = [&](bool worker) {
+        if (worker && cudaSetDevice(g->device) != cudaSuccess) { err.store((int)cudaErrorInvalidDevice); return; }
+        for (;;) {
+            const int64_t k = next.fetch_add(1);
+            if (k >= nchunks) break;
+            cudaError_t e = fn(k, k * NB_XFER_CHUNK, std::min(n, (k + 1) * NB_XFER_CHUNK));
+            if (e != cudaSuccess) err.store((int)e);
+        }
+    };
+    if (nt <= 1) {
+        work(false);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, true);
+        for (auto &t : th) t.join();
     }
-    for (auto &t : th) t.join();
+    if (err.load()) NB_FAIL(NB_ERR_CUDA, "host <-> device transfer failed: %s", cudaGetErrorString((cudaError_t)err.load()));
+    return NB_OK;
+}
+
+static int ensure_events(nb_graph *g, int64_t n)
+{
+    while ((int64_t)g->xfer_events.size() < n) {
+        cudaEvent_t e;
+        NB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g->xfer_events.push_back(e);
+    }
+    return NB_OK;
+}
+
+// device -> pinned staging in chunks, one event per chunk
+static int download_chunks(nb_graph *g, const void *d_src, int64_t n, int elem)
+{
+    const int64_t nchunks = (n + NB_XFER_CHUNK - 1) / NB_XFER_CHUNK;
+    NB_TRY(ensure_events(g, nchunks));
+    for (int64_t k = 0; k < nchunks; k++) {
+        const int64_t a = k * NB_XFER_CHUNK, b = std::min(n, a + NB_XFER_CHUNK);
+        NB_CUDA(cudaMemcpyAsync((char *)g->h_pinned + a * elem, (const char *)d_src + a * elem, (size_t)(b - a) * elem,
+                                cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaEventRecord(g->xfer_events[(size_t)k], g->stream));
+    }
+    return NB_OK;
 }
 
 __global__ void k_scatter_values_u8(int64_t V, const uint8_t *in, const int32_t *old2new, const int32_t *v_card,
@@ -132,7 +175,7 @@ extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
     NB_TRY(nb_ensure_xfer(g, (size_t)V + 64));
     uint8_t *stage = (uint8_t *)g->h_pinned;
     std::atomic<int> out_of_range(0);
-    host_parallel(V, [&](int64_t a, int64_t b) {
+    int rc = host_chunks(g, V, [&](int64_t, int64_t a, int64_t b) {
         int bad = 0;
         for (int64_t i = a; i < b; i++) {
             int64_t x = values[i];
@@ -140,10 +183,14 @@ extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
             stage[i] = (uint8_t)x;
         }
         if (bad) out_of_range.store(1);
+        return cudaMemcpyAsync((uint8_t *)g->d_xfer + a, stage + a, (size_t)(b - a), cudaMemcpyHostToDevice, g->stream);
     });
-    if (out_of_range.load()) NB_FAIL(NB_ERR_INVALID, "var_value holds entries outside [0, cardinality)");
+    if (rc != NB_OK || out_of_range.load()) {
+        cudaStreamSynchronize(g->stream);
+        if (rc != NB_OK) return rc;
+        NB_FAIL(NB_ERR_INVALID, "var_value holds entries outside [0, cardinality)");
+    }
     int *d_bad = (int *)((char *)g->d_xfer + (((size_t)V + 15) & ~(size_t)15));
-    NB_CUDA(cudaMemcpyAsync(g->d_xfer, stage, (size_t)V, cudaMemcpyHostToDevice, g->stream));
     NB_CUDA(cudaMemsetAsync(d_bad, 0, 4, g->stream));
     k_scatter_values_u8<<<grid_for(V), 256, 0, g->stream>>>(V, (const uint8_t *)g->d_xfer, g->d_old2new, g->d_v_card,
                                                             g->d_val[chain], d_bad);
@@ -164,11 +211,17 @@ extern "C" int nb_get_var_values(nb_graph *g, int chain, int64_t *values)
     NB_TRY(nb_ensure_pinned(g, (size_t)V + 64));
     NB_TRY(nb_ensure_xfer(g, (size_t)V + 64));
     k_gather_values_u8<<<grid_for(V), 256, 0, g->stream>>>(V, g->d_val[chain], g->d_old2new, (uint8_t *)g->d_xfer);
-    NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)V, cudaMemcpyDeviceToHost, g->stream));
-    NB_CUDA(cudaStreamSynchronize(g->stream));
+    int rc = download_chunks(g, g->d_xfer, V, 1);
+    if (rc != NB_OK) { cudaStreamSynchronize(g->stream); return rc; }
     const uint8_t *stage = (const uint8_t *)g->h_pinned;
-    host_parallel(V, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; i++) values[i] = (int64_t)stage[i]; });
-    return NB_OK;
+    rc = host_chunks(g, V, [&](int64_t k, int64_t a, int64_t b) {
+        cudaError_t e = cudaEventSynchronize(g->xfer_events[(size_t)k]);
+        if (e != cudaSuccess) return e;
+        for (int64_t i = a; i < b; i++) values[i] = (int64_t)stage[i];
+        return cudaSuccess;
+    });
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return rc;
 }
 
 extern "C" int nb_set_weights(nb_graph *g, const double *weights)
@@ -198,17 +251,49 @@ extern "C" int nb_reset_counts(nb_graph *g)
 
 // new-order tallies -> reference cstart layout (still int32; widened on the host)
 // (Boolean rows sampled by the truth-table kernels tally into count_b[new id].)
+// Also records the largest tally: tallies of a short call fit one byte and then cross PCIe as such.
 __global__ void k_counts_to_old(int64_t V, const int32_t *count, const int32_t *count_b, const uint32_t *cstart_new,
-                                const int64_t *cstart_old, const int32_t *old2new, const int32_t *v_card, int32_t *out)
+                                const int64_t *cstart_old, const int32_t *old2new, const int32_t *v_card, int32_t *out,
+                                int *max_out)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    int n = v_card[v] == 2 ? 1 : v_card[v];
-    int nid = old2new[v];
-    uint32_t s = cstart_new[nid];
-    int64_t d = cstart_old[v];
-    for (int j = 0; j < n; j++) out[d + j] = count[s + j];
-    if (v_card[v] == 2) out[d] += count_b[nid];
+    int m = 0;
+    if (v < V) {
+        int n = v_card[v] == 2 ? 1 : v_card[v];
+        int nid = old2new[v];
+        uint32_t s = cstart_new[nid];
+        int64_t d = cstart_old[v];
+        for (int j = 0; j < n; j++) {
+            int c = count[s + j];
+            if (j == 0 && v_card[v] == 2) c += count_b[nid];
+            out[d + j] = c;
+            m = max(m, c);
+        }
+    }
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0 && m > *(volatile int *)max_out) atomicMax(max_out, m);
+}
+
+__global__ void k_narrow_u8(int64_t n, const int32_t *in, uint8_t *out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)in[i];
+}
+
+template <class T>
+static int merge_counts(nb_graph *g, int64_t n, int64_t *counts, int accumulate, double *marginals, double divisor)
+{
+    const T *src = (const T *)g->h_pinned;
+    return host_chunks(g, n, [&](int64_t k, int64_t a, int64_t b) {
+        cudaError_t e = cudaEventSynchronize(g->xfer_events[(size_t)k]);
+        if (e != cudaSuccess) return e;
+        for (int64_t i = a; i < b; i++) {
+            int64_t c = accumulate ? counts[i] + (int64_t)src[i] : (int64_t)src[i];
+            counts[i] = c;
+            if (marginals) marginals[i] = (double)c / divisor;
+        }
+        return cudaSuccess;
+    });
 }
 
 static int fetch_counts(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double divisor)
@@ -217,21 +302,28 @@ static int fetch_counts(nb_graph *g, int64_t *counts, int accumulate, double *ma
     NB_CUDA(cudaSetDevice(g->device));
     const int64_t n = g->count_entries;
     if (n == 0) return NB_OK;
-    NB_TRY(nb_ensure_xfer(g, (size_t)n * 4));
+    const size_t narrow_off = ((size_t)n * 4 + 255) & ~(size_t)255;
+    NB_TRY(nb_ensure_xfer(g, narrow_off + (size_t)n + 256));
     NB_TRY(nb_ensure_pinned(g, (size_t)n * 4));
+    int *d_max = (int *)((char *)g->d_xfer + narrow_off + (((size_t)n + 15) & ~(size_t)15));
+    NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
     k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
-                                                            g->d_old2new, g->d_v_card, (int32_t *)g->d_xfer);
-    NB_CUDA(cudaMemcpyAsync(g->h_pinned, g->d_xfer, (size_t)n * 4, cudaMemcpyDeviceToHost, g->stream));
+                                                            g->d_old2new, g->d_v_card, (int32_t *)g->d_xfer, d_max);
+    int maxc = 0;
+    NB_CUDA(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
-    const int32_t *src = (const int32_t *)g->h_pinned;
-    host_parallel(n, [&](int64_t a, int64_t b) {
-        for (int64_t i = a; i < b; i++) {
-            int64_t c = accumulate ? counts[i] + src[i] : (int64_t)src[i];
-            counts[i] = c;
-            if (marginals) marginals[i] = (double)c / divisor;
-        }
-    });
-    return NB_OK;
+    int rc;
+    if (maxc <= 255) {
+        uint8_t *d_u8 = (uint8_t *)g->d_xfer + narrow_off;
+        k_narrow_u8<<<grid_for(n), 256, 0, g->stream>>>(n, (const int32_t *)g->d_xfer, d_u8);
+        rc = download_chunks(g, d_u8, n, 1);
+        if (rc == NB_OK) rc = merge_counts<uint8_t>(g, n, counts, accumulate, marginals, divisor);
+    } else {
+        rc = download_chunks(g, g->d_xfer, n, 4);
+        if (rc == NB_OK) rc = merge_counts<int32_t>(g, n, counts, accumulate, marginals, divisor);
+    }
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return rc;
 }
 
 extern "C" int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate)

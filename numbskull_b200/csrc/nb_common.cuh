@@ -233,6 +233,7 @@ struct nb_graph {
     uint8_t *d_fast0 = nullptr;      // [V] FAST-class flag
     int32_t *d_cbase = nullptr;      // [V] JP colour window
     int32_t *d_cround = nullptr;     // [V] round in which a variable took its colour (natural-order mode)
+    int32_t *d_blocker = nullptr;    // [V] the uncoloured higher-priority neighbour seen last (-1: none yet)
     int jp_mode = 0;                 // 0 = hashed priorities, 1 = natural order
     int jp_round_no = 0;
     unsigned long long *d_jpcnt = nullptr;
@@ -306,6 +307,7 @@ struct nb_graph {
     size_t xfer_bytes = 0;
     void *h_pinned = nullptr;
     size_t pinned_bytes = 0;
+    std::vector<cudaEvent_t> xfer_events;   // one per download chunk (nb_api.cu)
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
 
@@ -338,6 +340,7 @@ int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);
 int nb_build_color_round(nb_graph *g, int64_t *remaining);
 int nb_build_color_restart(nb_graph *g, int mode);
 int nb_natural_round_cap(void);
+void nb_release_color_scratch(nb_graph *g);
 int nb_build_finalize(nb_graph *g);
 int nb_build_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids);
 int nb_build_relabel_colors(nb_graph *g, const int32_t *map, int n);
