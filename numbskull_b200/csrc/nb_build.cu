@@ -162,24 +162,18 @@ __host__ __device__ inline uint64_t nb_jp_priority(uint64_t gid, uint64_t seed)
 // remembers the neighbour that blocked it and looks at that one first in the next round: in the
 // natural order nearly every variable is blocked for thousands of rounds, and this keeps a round at
 // three coalesced loads per variable instead of a walk over its factors.
-__device__ __forceinline__ void jp_still_open(unsigned long long *remaining)
+// returns true iff v is still uncoloured after this round
+__device__ __forceinline__ bool jp_visit(const RawGraph &G, int64_t v, uint64_t seed, int32_t *color, int32_t *cbase,
+                                         int32_t *cround, int32_t *blocker, int round, int mode)
 {
-    if (*(volatile unsigned long long *)remaining == 0) *(volatile unsigned long long *)remaining = 1;
-}
-
-__global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *cbase, int32_t *cround, int32_t *blocker,
-                           int round, int mode, unsigned long long *remaining)
-{
-    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (v >= G.V) return;
-    if (color[v] != -1) return;     // already coloured
-    if (G.v_evid[v] == 4) return;   // ghosts are coloured by their owner
+    if (color[v] != -1) return false;     // already coloured
+    if (G.v_evid[v] == 4) return false;   // ghosts are coloured by their owner
     {
         const int bl = blocker[v];
         if (bl >= 0) {
             int cb = ((volatile int32_t *)color)[bl];
             if (mode == 1 && cb >= 0 && ((volatile int32_t *)cround)[bl] >= round) cb = -1;
-            if (cb == -1) { jp_still_open(remaining); return; }
+            if (cb == -1) return true;
         }
     }
     const uint64_t gv = G.gid ? (uint64_t)G.gid[v] : (uint64_t)v;
@@ -214,10 +208,20 @@ __global__ void k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *c
             }
         }
     }
-    if (!ready) { jp_still_open(remaining); return; }
-    if (used == ~0ull) { cbase[v] = base + 64; jp_still_open(remaining); return; }
+    if (!ready) return true;
+    if (used == ~0ull) { cbase[v] = base + 64; return true; }
     if (mode == 1) { ((volatile int32_t *)cround)[v] = round; __threadfence(); }
     ((volatile int32_t *)color)[v] = base + (__ffsll((long long)~used) - 1);
+    return false;
+}
+
+__global__ void __launch_bounds__(256) k_jp_round(RawGraph G, uint64_t seed, int32_t *color, int32_t *cbase, int32_t *cround,
+                                                  int32_t *blocker, int round, int mode, unsigned long long *remaining)
+{
+    const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool open = v < G.V && jp_visit(G, v, seed, color, cbase, cround, blocker, round, mode);
+    // one (L1-cached) look at the flag per block: a load per thread of the same word serialises in L2
+    if (__syncthreads_or(open) && threadIdx.x == 0 && *remaining == 0) *remaining = 1;
 }
 
 // single-GPU graphs ignore ghosts (-2); partitioned graphs wait for the owner's colour (-1)
@@ -819,21 +823,28 @@ void nb_release_color_scratch(nb_graph *g)
     g->d_cbase = g->d_cround = g->d_blocker = nullptr;
 }
 
-int nb_build_color_round(nb_graph *g, int64_t *remaining)
+// n_rounds (<= NB_JP_BATCH) rounds back to back, one host round trip; *remaining is the flag of the
+// last one.  Rounds after the last variable took its colour change nothing.
+#define NB_JP_BATCH 8
+static int color_rounds(nb_graph *g, int n_rounds, int64_t *remaining)
 {
     if (!g->d_cbase) NB_FAIL(NB_ERR_INVALID, "the graph is already coloured");
     RawGraph G = raw_view(g);
-    NB_CUDA(cudaMemsetAsync(g->d_jpcnt, 0, 8, g->stream));
-    k_jp_round<<<grid_for(g->V), 256, 0, g->stream>>>(G, g->color_seed, g->d_color, g->d_cbase, g->d_cround, g->d_blocker,
-                                                      g->jp_round_no, g->jp_mode, g->d_jpcnt);
+    NB_CUDA(cudaMemsetAsync(g->d_jpcnt, 0, 8 * NB_JP_BATCH, g->stream));
+    for (int i = 0; i < n_rounds; i++) {
+        k_jp_round<<<grid_for(g->V), 256, 0, g->stream>>>(G, g->color_seed, g->d_color, g->d_cbase, g->d_cround, g->d_blocker,
+                                                          g->jp_round_no, g->jp_mode, g->d_jpcnt + i);
+        g->jp_rounds++;
+        g->jp_round_no++;
+    }
     unsigned long long rem = 0;
-    NB_CUDA(cudaMemcpyAsync(&rem, g->d_jpcnt, 8, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaMemcpyAsync(&rem, g->d_jpcnt + (n_rounds - 1), 8, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
-    g->jp_rounds++;
-    g->jp_round_no++;
     *remaining = (int64_t)rem;
     return NB_OK;
 }
+
+int nb_build_color_round(nb_graph *g, int64_t *remaining) { return color_rounds(g, 1, remaining); }
 
 // (re)start the colouring: mode 0 = hashed priorities (few rounds), 1 = natural order (smaller
 // global id first: the sequential greedy colouring in id order; 2 colours on grids and other
@@ -874,9 +885,12 @@ static int run_jp(nb_graph *g, int mode, int64_t cap, bool *finished)
 {
     NB_TRY(nb_build_color_restart(g, mode));
     *finished = false;
-    for (int64_t r = 0; cap <= 0 || r < cap; r++) {
+    for (int64_t r = 0; cap <= 0 || r < cap;) {
+        // the natural order needs thousands of cheap rounds: look at the flag once per batch
+        const int n = (int)std::min<int64_t>(mode == 1 ? NB_JP_BATCH : 1, cap <= 0 ? NB_JP_BATCH : cap - r);
         int64_t rem = 0;
-        NB_TRY(nb_build_color_round(g, &rem));
+        NB_TRY(color_rounds(g, n, &rem));
+        r += n;
         if (rem == 0) { *finished = true; break; }
         if (r > 4000000) NB_FAIL(NB_ERR_CUDA, "Jones-Plassmann colouring did not converge");
     }
@@ -888,7 +902,7 @@ static int color_graph(nb_graph *g, const nb_graph_desc *d)
     const int64_t V = g->V;
     RawGraph G = raw_view(g);
     NB_TRY(nb_alloc(g, &g->d_color, (size_t)V, false));
-    NB_TRY(nb_alloc(g, &g->d_jpcnt, 2));
+    NB_TRY(nb_alloc(g, &g->d_jpcnt, 2 * NB_JP_BATCH));
     // colouring scratch (released by nb_build_finalize): colour window, round stamp, last blocker
     NB_CUDA(cudaMalloc(&g->d_cbase, (size_t)std::max<int64_t>(V, 1) * 12));
     g->d_cround = g->d_cbase + std::max<int64_t>(V, 1);
