@@ -41,6 +41,35 @@ def test_extract_local_covers_the_graph():
     assert (seen_factors[f["arity"] > 0] >= 1).all()
 
 
+def test_interior_variables_never_touch_a_ghost():
+    """The invariant behind the boundary / interior phases (nb_split_colors): an owned variable
+    that shares a factor with a ghost is itself a ghost on the ghost's owner, i.e. it is in the
+    set of variables this rank sends -- so everything outside that set only reads owned values."""
+    from numbskull_b200 import partition, synth
+    w, v, f, fm, dm, e = synth.random_graph(90, 260, np.random.default_rng(11), max_arity=4, categorical_frac=0.2,
+                                            funcs=(0, 1, 2, 3, 12), card=3)
+    world = 3
+    b = partition.block_bounds(len(v), world)
+    owner = np.searchsorted(b, np.arange(len(v)), side="right") - 1
+    locs = [partition.extract_local(w, v, f, fm, int(b[r]), int(b[r + 1])) for r in range(world)]
+    for r, loc in enumerate(locs):
+        gv, n_owned = loc["global_vid"], loc["n_owned"]
+        # what the other ranks hold as ghosts of r = what r must send (HaloPlan.send_ids, without the collective)
+        sent = set()
+        for q, other in enumerate(locs):
+            if q != r:
+                ghosts = other["global_vid"][other["n_owned"]:]
+                sent.update(int(x) for x in ghosts[owner[ghosts] == r])
+        n_boundary_checked = 0
+        for lf in loc["factor"]:
+            mem = loc["fmap"]["vid"][lf["ftv_offset"]:lf["ftv_offset"] + lf["arity"]]
+            if (mem >= n_owned).any():                      # the factor has a ghost member
+                for m in mem[mem < n_owned]:
+                    assert int(gv[m]) in sent
+                    n_boundary_checked += 1
+        assert n_boundary_checked > 0
+
+
 def test_ising_strip_matches_global_partition():
     from numbskull_b200 import partition, synth
     rows, cols, world = 3, 5, 3

@@ -50,7 +50,10 @@ def _worker(rank, world, port, out_dir, kind, mode):
     w, v, f, fm, dm, e = _graph(kind)
     run = partition.partition_graph(w, v, f, fm, rank, world, device, seed=31)
     out = dict(global_vid=run.global_vid, n_owned=run.n_owned, colors=run.colors, n_colors=run.n_colors)
-    if mode == "inference":
+    if mode == "inference_short":
+        run.inference(1, 5, sample_evidence=True)
+        out.update(var_value=run.fg.var_value[0].copy())
+    elif mode == "inference":
         run.inference(3, 40, sample_evidence=True)
         out.update(count=run.fg.count.copy(), var_value=run.fg.var_value[0].copy(), cstart=run.fg.cstart)
     else:
@@ -94,6 +97,21 @@ def test_partitioned_inference_is_bit_identical_to_single_gpu(tmp_path, kind):
             assert np.array_equal(r["count"][lc[i]:lc[i + 1]], fg.count[gc[own[i]]:gc[own[i] + 1]])
         assert np.array_equal(r["count"][:lc[n]], fg.count[gc[own[0]]:gc[own[-1] + 1]])
     assert seen.all()
+
+
+def test_partitioned_coloring_fallback_matches_single_gpu(tmp_path, monkeypatch):
+    """Round cap below the grid's depth: every rank gives up the natural order in the same round
+    and returns to the hashed colouring, like the single-GPU build."""
+    monkeypatch.setenv("NUMBSKULL_B200_NATURAL_ROUNDS", "20")
+    fg = _single("ising")
+    colors = fg.colors()
+    assert colors.max() + 1 > 2
+    fg.inference(1, 5, sample_evidence=True)
+    res = _spawn(tmp_path, "ising", "inference_short")
+    for r in res:
+        gv, n = r["global_vid"], int(r["n_owned"])
+        assert np.array_equal(r["colors"], colors[gv])
+        assert np.array_equal(r["var_value"][:n], fg.var_value[0][gv[:n]])
 
 
 def test_partitioned_learning_matches_single_gpu(tmp_path):
