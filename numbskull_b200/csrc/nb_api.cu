@@ -124,6 +124,61 @@ static int host_chunks(nb_graph *g, int64_t n, F fn)   // fn(chunk index, begin,
     return NB_OK;
 }
 
+// Widening loops.  The int64 / float64 result arrays are written once and not read back here, so
+// on x86 they go out as 32-byte non-temporal stores (no read-for-ownership of 3 x 134 MB on the C2
+// graph); NUMBSKULL_B200_NT_STORES=0 selects the plain loops.
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define NB_HAVE_AVX2_PATH 1
+static bool nb_use_nt()
+{
+    static const bool on = [] {
+        const char *e = getenv("NUMBSKULL_B200_NT_STORES");
+        return (!e || atoi(e) != 0) && __builtin_cpu_supports("avx2");
+    }();
+    return on;
+}
+__attribute__((target("avx2"))) static void widen_u8_nt(const uint8_t *s, int64_t *d, int64_t a, int64_t b)
+{
+    int64_t i = a;
+    for (; i < b && ((uintptr_t)(d + i) & 31); i++) d[i] = (int64_t)s[i];
+    for (; i + 4 <= b; i += 4) {
+        uint32_t w;
+        memcpy(&w, s + i, 4);
+        _mm256_stream_si256((__m256i *)(d + i), _mm256_cvtepu8_epi64(_mm_cvtsi32_si128((int)w)));
+    }
+    for (; i < b; i++) d[i] = (int64_t)s[i];
+    _mm_sfence();
+}
+template <class T>
+__attribute__((target("avx2"))) static void merge_nt(const T *s, int64_t *c, int accumulate, double *m, double div, int64_t a,
+                                                     int64_t b)
+{
+    // counts are read-modify-write when accumulating (plain stores), marginals are write-only
+    int64_t i = a;
+    auto one = [&](int64_t k) {
+        int64_t x = accumulate ? c[k] + (int64_t)s[k] : (int64_t)s[k];
+        c[k] = x;
+        m[k] = (double)x / div;
+    };
+    for (; i < b && ((uintptr_t)(m + i) & 31); i++) one(i);
+    for (; i + 4 <= b; i += 4) {
+        alignas(32) double t[4];
+        for (int j = 0; j < 4; j++) {
+            int64_t x = accumulate ? c[i + j] + (int64_t)s[i + j] : (int64_t)s[i + j];
+            c[i + j] = x;
+            t[j] = (double)x / div;
+        }
+        _mm256_stream_pd(m + i, _mm256_load_pd(t));
+    }
+    for (; i < b; i++) one(i);
+    _mm_sfence();
+}
+#else
+#define NB_HAVE_AVX2_PATH 0
+static bool nb_use_nt() { return false; }
+#endif
+
 static int ensure_events(nb_graph *g, int64_t n)
 {
     while ((int64_t)g->xfer_events.size() < n) {
@@ -217,6 +272,9 @@ extern "C" int nb_get_var_values(nb_graph *g, int chain, int64_t *values)
     rc = host_chunks(g, V, [&](int64_t k, int64_t a, int64_t b) {
         cudaError_t e = cudaEventSynchronize(g->xfer_events[(size_t)k]);
         if (e != cudaSuccess) return e;
+#if NB_HAVE_AVX2_PATH
+        if (nb_use_nt()) { widen_u8_nt(stage, values, a, b); return cudaSuccess; }
+#endif
         for (int64_t i = a; i < b; i++) values[i] = (int64_t)stage[i];
         return cudaSuccess;
     });
@@ -287,6 +345,9 @@ static int merge_counts(nb_graph *g, int64_t n, int64_t *counts, int accumulate,
     return host_chunks(g, n, [&](int64_t k, int64_t a, int64_t b) {
         cudaError_t e = cudaEventSynchronize(g->xfer_events[(size_t)k]);
         if (e != cudaSuccess) return e;
+#if NB_HAVE_AVX2_PATH
+        if (marginals && nb_use_nt()) { merge_nt<T>(src, counts, accumulate, marginals, divisor, a, b); return cudaSuccess; }
+#endif
         for (int64_t i = a; i < b; i++) {
             int64_t c = accumulate ? counts[i] + (int64_t)src[i] : (int64_t)src[i];
             counts[i] = c;
