@@ -224,3 +224,63 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 src = open(os.path.join(root, f)).read()
                 assert not bad.search(src), os.path.join(root, f)
+
+
+# --------------------------------------------------------------------------- edge cases of the host side
+def test_empty_graph_host_side():
+    """No variables / no factors: offsets, index build and the loaders are no-ops, not crashes."""
+    from numbskull_b200 import dataloading
+    from numbskull_b200.numbskulltypes import Weight, Variable, Factor, FactorToVar, VarToFactor
+    variable, factor, fmap = np.zeros(0, Variable), np.zeros(0, Factor), np.zeros(0, FactorToVar)
+    assert dataloading.assign_vtf_offsets(variable) == 0
+    vmap, findex = np.zeros(0, VarToFactor), np.zeros(0, np.int64)
+    dataloading.compute_var_map(variable, factor, fmap, vmap, findex, np.zeros(0, bool))
+    empty = np.zeros(0, np.uint8)
+    dataloading.load_weights(empty, 0, np.zeros(0, Weight))
+    dataloading.load_variables(empty, 0, variable)
+    dataloading.load_factors(empty, 0, factor, fmap, np.zeros(0, bool), variable, vmap)
+
+
+def test_isolated_variables_and_zero_arity_factors(oracle):
+    """Variables no factor touches get empty buckets; a factor without members contributes nothing."""
+    from numbskull_b200 import dataloading, synth
+    from numbskull_b200.numbskulltypes import VarToFactor
+    w, v, f, fm, dm, e = synth.random_graph(12, 9, np.random.default_rng(4), max_arity=3)
+    f = f.copy()
+    f["arity"][4] = 0                                  # its fmap slots are simply never referenced
+    used = np.zeros(len(v), bool)
+    for x in f:
+        used[fm["vid"][x["ftv_offset"]:x["ftv_offset"] + x["arity"]]] = True
+    n_vtf = dataloading.assign_vtf_offsets(v)
+    vmap, findex = np.zeros(n_vtf, VarToFactor), np.zeros(len(fm), np.int64)
+    dataloading.compute_var_map(v, f, fm, vmap, findex, dm)
+    want_vmap, want_index = np.zeros(n_vtf, VarToFactor), np.zeros(len(fm), np.int64)
+    oracle.compute_var_map(v.copy(), f, fm, want_vmap, want_index, dm)
+    assert np.array_equal(vmap, want_vmap)
+    for b in vmap:
+        s0, k = b["factor_index_offset"], b["factor_index_length"]
+        assert np.array_equal(findex[s0:s0 + k], want_index[s0:s0 + k])
+    assert 4 not in findex[:int(vmap["factor_index_length"].sum())]
+    for i in np.nonzero(~used)[0]:
+        assert vmap["factor_index_length"][v["vtf_offset"][i]] == 0
+
+
+@pytest.mark.parametrize("which", ["weights", "variables", "factors"])
+def test_truncated_files_are_rejected(which):
+    """A short buffer is an error (the reference would read past the end of the array)."""
+    from numbskull_b200 import dataloading
+    from numbskull_b200.numbskulltypes import Weight, Variable, Factor, FactorToVar, VarToFactor
+    z = golden("coin")
+    raw = {n: z["raw_" + n] for n in ("weights", "variables", "factors")}
+    nw, nv, nf, ne = len(z["weight"]), len(z["variable"]), len(z["factor"]), len(z["fmap"])
+    data = raw[which][:len(raw[which]) - 3]
+    with pytest.raises(Exception):
+        if which == "weights":
+            dataloading.load_weights(data, nw, np.zeros(nw, Weight))
+        elif which == "variables":
+            dataloading.load_variables(data, nv, np.zeros(nv, Variable))
+        else:
+            variable = z["variable"].copy()
+            vmap = np.zeros(len(z["vmap"]), VarToFactor)
+            dataloading.load_factors(data, nf, np.zeros(nf, Factor), np.zeros(ne, FactorToVar),
+                                     np.zeros(nv, bool), variable, vmap)
