@@ -2,7 +2,10 @@
 // binary parsers and the (bit-exact) variable-to-factor index builder.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -87,6 +90,182 @@ static void host_threads(int64_t n, F fn)
 
 static inline int64_t atomic_fetch_add_i64(int64_t *p, int64_t x) { return __atomic_fetch_add(p, x, __ATOMIC_RELAXED); }
 
+// ---------------------------------------------------------------------------
+// Atomics-free index build for the usual layout (factors tile fmap in order, nothing skipped):
+// the variable ids are cut into one range per thread with about the same number of fmap entries;
+// every thread stages the (bucket, factor) pairs of its contiguous factor chunk per destination
+// range (8 bytes each, factor order kept), then every thread owns one range and counts / fills
+// its buckets from the staged pairs alone -- local writes, no shared cursors, buckets come out
+// ascending.  Returns false (nothing written) when the layout or the sizes do not qualify; the
+// caller then takes the general path.  Identical output to the general path by construction.
+// ---------------------------------------------------------------------------
+struct NbStaged { uint32_t bucket_rel, fid; };
+
+template <class F>
+static void run_threads(int nt, F fn)
+{
+    if (nt == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([=] { fn(t); });
+    for (auto &t : th) t.join();
+}
+
+static bool var_map_partitioned(const nb_variable_rec *variable, int64_t n_variable, const nb_factor_rec *factor,
+                                int64_t n_factor, const nb_ftv_rec *fmap, int64_t n_fmap, nb_vtf_rec *vmap, int64_t n_vmap,
+                                int64_t *factor_index, int64_t n_factor_index, int *bad_out, char *msg, size_t msg_len)
+{
+    if (n_fmap < (1 << 20) || n_factor >= (1ll << 32) || n_variable < 64 || n_factor_index < n_fmap) return false;
+    const bool timing = getenv("NUMBSKULL_B200_HOST_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  partitioned %-8s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
+    const int nt = (int)std::min<int64_t>(32, std::max(1u, std::thread::hardware_concurrency()));
+    if (nt < 2) return false;
+    // contiguous factor chunks and the fmap positions they start at
+    std::vector<int64_t> fbeg((size_t)nt + 1), ebeg((size_t)nt + 1, 0), esum((size_t)nt, 0);
+    for (int t = 0; t <= nt; t++) fbeg[(size_t)t] = n_factor * t / nt;
+    run_threads(nt, [&](int t) {
+        int64_t s = 0;
+        for (int64_t f = fbeg[(size_t)t]; f < fbeg[(size_t)t + 1]; f++) s += factor[f].arity;
+        esum[(size_t)t] = s;
+    });
+    for (int t = 0; t < nt; t++) ebeg[(size_t)t + 1] = ebeg[(size_t)t] + esum[(size_t)t];
+    if (ebeg[(size_t)nt] != n_fmap) return false;
+    std::atomic<int> canonical(1), bad(0);
+    auto fail = [&](const char *what, int64_t idx) {
+        int expected = 0;
+        if (bad.compare_exchange_strong(expected, 1)) snprintf(msg, msg_len, "%s (index %lld)", what, (long long)idx);
+    };
+    // coarse histogram of the variable ids (also: layout check, vid validation)
+    int shift = 0;
+    while ((n_variable >> shift) > 65536) shift++;
+    const int64_t nbins = ((n_variable - 1) >> shift) + 1;
+    std::vector<std::vector<int64_t>> hist((size_t)nt);
+    run_threads(nt, [&](int t) {
+        std::vector<int64_t> &h = hist[(size_t)t];
+        h.assign((size_t)nbins, 0);
+        int64_t e = ebeg[(size_t)t];
+        for (int64_t f = fbeg[(size_t)t]; f < fbeg[(size_t)t + 1]; f++) {
+            if (factor[f].ftv_offset != e) { canonical.store(0); return; }
+            e += factor[f].arity;
+        }
+        for (int64_t j = ebeg[(size_t)t]; j < ebeg[(size_t)t + 1]; j++) {
+            const int64_t vid = fmap[j].vid;
+            if (vid < 0 || vid >= n_variable) { fail("fmap vid out of range", j); return; }
+            h[(size_t)(vid >> shift)]++;
+        }
+    });
+    if (!canonical.load()) return false;
+    if (bad.load()) { *bad_out = 1; return true; }
+    lap("hist");
+    // ranges of whole bins with ~n_fmap / nt entries each
+    std::vector<int64_t> total((size_t)nbins, 0);
+    for (int t = 0; t < nt; t++)
+        for (int64_t b = 0; b < nbins; b++) total[(size_t)b] += hist[(size_t)t][(size_t)b];
+    std::vector<int32_t> range_of_bin((size_t)nbins);
+    std::vector<int64_t> range_first_bin((size_t)nt + 1, nbins);
+    {
+        int64_t acc = 0;
+        int r = 0;
+        range_first_bin[0] = 0;
+        for (int64_t b = 0; b < nbins; b++) {
+            while (r + 1 < nt && acc >= n_fmap * (int64_t)(r + 1) / nt) range_first_bin[(size_t)++r] = b;
+            range_of_bin[(size_t)b] = r;
+            acc += total[(size_t)b];
+        }
+        for (int q = r + 1; q <= nt; q++) range_first_bin[(size_t)q] = nbins;
+    }
+    // bucket span of every range (vtf_offset is increasing in the variable id; the caller checked the bounds)
+    std::vector<int64_t> bucket_base((size_t)nt + 1);
+    for (int r = 0; r <= nt; r++) {
+        const int64_t v0 = std::min(n_variable, range_first_bin[(size_t)r] << shift);
+        bucket_base[(size_t)r] = v0 < n_variable ? variable[v0].vtf_offset : n_vmap;
+    }
+    for (int r = 0; r < nt; r++) {
+        if (bucket_base[(size_t)r + 1] < bucket_base[(size_t)r]) return false;          // offsets not monotone: general path
+        if (bucket_base[(size_t)r + 1] - bucket_base[(size_t)r] >= (1ll << 32)) return false;
+    }
+    // staging positions: range-major, then source thread (= factor order inside a range)
+    std::vector<int64_t> pos((size_t)nt * nt), range_beg((size_t)nt + 1, 0);
+    for (int r = 0; r < nt; r++) {
+        int64_t acc = range_beg[(size_t)r];
+        for (int t = 0; t < nt; t++) {
+            int64_t c = 0;
+            for (int64_t b = range_first_bin[(size_t)r]; b < range_first_bin[(size_t)r + 1]; b++) c += hist[(size_t)t][(size_t)b];
+            pos[(size_t)t * nt + r] = acc;
+            acc += c;
+        }
+        range_beg[(size_t)r + 1] = acc;
+    }
+    NbStaged *staged = (NbStaged *)malloc((size_t)n_fmap * sizeof(NbStaged));
+    if (!staged) return false;
+    run_threads(nt, [&](int t) {
+        std::vector<int64_t> cur(pos.begin() + (size_t)t * nt, pos.begin() + (size_t)(t + 1) * nt);
+        for (int64_t f = fbeg[(size_t)t]; f < fbeg[(size_t)t + 1]; f++) {
+            const int64_t a = factor[f].ftv_offset, n = factor[f].arity;
+            for (int64_t j = a; j < a + n; j++) {
+                const nb_ftv_rec &m = fmap[j];
+                const nb_variable_rec &v = variable[m.vid];
+                if (v.dataType == 1 && (m.dense_equal_to < 0 || m.dense_equal_to >= v.cardinality)) {
+                    fail("fmap dense_equal_to outside the variable's cardinality", j);
+                    return;
+                }
+                const int r = range_of_bin[(size_t)(m.vid >> shift)];
+                const int64_t bucket = v.vtf_offset + (v.dataType == 1 ? m.dense_equal_to : 0);
+                if (bucket < bucket_base[(size_t)r] || bucket >= bucket_base[(size_t)r + 1]) { canonical.store(0); return; }
+                staged[cur[(size_t)r]++] = NbStaged{(uint32_t)(bucket - bucket_base[(size_t)r]), (uint32_t)f};
+            }
+        }
+    });
+    if (bad.load() || !canonical.load()) {
+        free(staged);
+        if (bad.load()) { *bad_out = 1; return true; }
+        return false;   // (nothing was written to vmap / factor_index yet)
+    }
+    lap("stage");
+    // bucket lengths, per range
+    run_threads(nt, [&](int r) {
+        const int64_t base = bucket_base[(size_t)r];
+        for (int64_t i = range_beg[(size_t)r]; i < range_beg[(size_t)r + 1]; i++)
+            vmap[base + staged[i].bucket_rel].factor_index_length += 1;
+    });
+    lap("count");
+    int64_t last_len = 0, last_off = 0;
+    for (int64_t i = 0; i < n_vmap; i++) {
+        vmap[i].factor_index_offset = last_off + last_len;
+        last_len = vmap[i].factor_index_length;
+        last_off = vmap[i].factor_index_offset;
+    }
+    lap("scan");
+    // fill (ascending factor ids per bucket) and drop duplicates in place, like dataloading.py:67-81
+    run_threads(nt, [&](int r) {
+        const int64_t base = bucket_base[(size_t)r], nb = bucket_base[(size_t)r + 1] - base;
+        std::vector<uint32_t> filled((size_t)nb, 0);
+        for (int64_t i = range_beg[(size_t)r]; i < range_beg[(size_t)r + 1]; i++) {
+            const NbStaged e = staged[i];
+            factor_index[vmap[base + e.bucket_rel].factor_index_offset + filled[e.bucket_rel]++] = (int64_t)e.fid;
+        }
+        for (int64_t b = base; b < base + nb; b++) {
+            int64_t *p = factor_index + vmap[b].factor_index_offset;
+            const int64_t len = vmap[b].factor_index_length;
+            int64_t n = 0, last = -1;
+            for (int64_t k = 0; k < len; k++) {
+                if (p[k] == last) continue;
+                last = p[k];
+                p[n++] = last;
+            }
+            vmap[b].factor_index_length = n;
+        }
+    });
+    lap("fill");
+    free(staged);
+    return true;
+}
+
 extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                                   const nb_factor_rec *factor, int64_t n_factor,
                                   const nb_ftv_rec *fmap, int64_t n_fmap, nb_vtf_rec *vmap,
@@ -94,6 +273,14 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                                   const uint8_t *domain_mask, const int64_t *factors_to_skip,
                                   int64_t n_skip)
 {
+    const bool timing = getenv("NUMBSKULL_B200_HOST_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "compute_var_map %-10s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     std::atomic<int> bad(0);
     char msg[200] = "";
     auto fail = [&](const char *what, int64_t idx) {
@@ -112,6 +299,7 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
         if (domain_mask && domain_mask[i]) continue;
         for (int64_t k = 0; k < v.cardinality; k++) vmap[v.vtf_offset + k].value = k;
     }
+    lap("domains");
     // skip list -> flag per factor
     std::vector<uint8_t> skip;
     if (n_skip > 0) {
@@ -130,6 +318,15 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
     for (int64_t f = 0; f < n_factor; f++)
         if (factor[f].ftv_offset < 0 || factor[f].arity < 0 || factor[f].ftv_offset + factor[f].arity > n_fmap)
             NB_FAIL(NB_ERR_INVALID, "factor %lld: fmap range out of bounds", (long long)f);
+    if (n_skip == 0 && !getenv("NUMBSKULL_B200_VARMAP_GENERAL")) {
+        int bad_graph = 0;
+        if (var_map_partitioned(variable, n_variable, factor, n_factor, fmap, n_fmap, vmap, n_vmap, factor_index,
+                                n_factor_index, &bad_graph, msg, sizeof(msg))) {
+            if (bad_graph) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+            lap("partitioned");
+            return NB_OK;
+        }
+    }
     host_threads(n_fmap, [&](int64_t a, int64_t b) {
         for (int64_t j = a; j < b; j++) {
             const nb_ftv_rec &m = fmap[j];
@@ -143,6 +340,7 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
         }
     });
     if (bad.load()) NB_FAIL(NB_ERR_INVALID, "invalid factor graph: %s", msg);
+    lap("count");
     if (n_skip > 0)
         for (int64_t s = 0; s < n_skip; s++) {
             const nb_factor_rec &f = factor[factors_to_skip[s]];
@@ -161,6 +359,7 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                 "factor_index holds %lld entries but the buckets need %lld (the reference overruns "
                 "here when factors_to_skip is non-empty)",
                 (long long)n_factor_index, (long long)(last_off + last_len));
+    lap("scan");
     // :48-65 scatter (bucket cursors advanced atomically; order inside a bucket is fixed by the sort below)
     std::vector<int64_t> cursor((size_t)n_vmap);
     for (int64_t i = 0; i < n_vmap; i++) cursor[(size_t)i] = vmap[i].factor_index_offset;
@@ -172,6 +371,7 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
                 factor_index[atomic_fetch_add_i64(&cursor[(size_t)bucket_of(variable, fmap[j])], 1)] = i;
         }
     });
+    lap("scatter");
     // :67-81 sort + unique each bucket; offsets are not compacted
     host_threads(n_vmap, [&](int64_t a, int64_t b) {
         for (int64_t i = a; i < b; i++) {
@@ -187,6 +387,7 @@ extern "C" int nb_compute_var_map(nb_variable_rec *variable, int64_t n_variable,
             vmap[i].factor_index_length = n;
         }
     });
+    lap("sort");
     return NB_OK;
 }
 

@@ -111,6 +111,57 @@ def test_compute_var_map_threaded_path_matches_oracle(oracle):
     assert np.array_equal(fi1[pos], fi2[pos])
 
 
+@pytest.mark.parametrize("kind", ["kbc", "categorical", "repeats"])
+def test_compute_var_map_partitioned_path_is_bit_exact(oracle, kind, monkeypatch):
+    """>= 2^20 fmap entries with factors tiling fmap in order: the atomics-free partitioned build
+    (nb_host.cpp var_map_partitioned) must equal the general path byte for byte, gaps included,
+    and the sequential oracle on every bucket."""
+    from numbskull_b200 import synth
+    from numbskull_b200.dataloading import assign_vtf_offsets, compute_var_map
+    from numbskull_b200.numbskulltypes import VarToFactor
+    rng = np.random.default_rng(5)
+    if kind == "kbc":
+        w, v, f, fm, dm, e = synth.kbc(230000, rng=rng, n_weights=1000)
+    elif kind == "categorical":
+        w, v, f, fm, dm, e = synth.categorical(180000, card=7, rng=rng, n_weights=1000)
+    else:   # the same variable several times in one factor: duplicates inside a bucket
+        w, v, f, fm, dm, e = synth.kbc(230000, rng=rng, n_weights=1000, window=2)
+    assert len(fm) >= (1 << 20)
+    v = v.copy()
+    n = assign_vtf_offsets(v)
+    out = {}
+    for mode in ("partitioned", "general"):
+        if mode == "general":
+            monkeypatch.setenv("NUMBSKULL_B200_VARMAP_GENERAL", "1")
+        vm, fi = np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64)
+        compute_var_map(v, f, fm, vm, fi, dm)
+        out[mode] = (vm, fi)
+    assert np.array_equal(out["partitioned"][0], out["general"][0])
+    assert np.array_equal(out["partitioned"][1], out["general"][1])
+    vm2, fi2 = np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64)
+    oracle.compute_var_map(v.copy(), f, fm, vm2, fi2, dm)
+    vm1, fi1 = out["partitioned"]
+    assert np.array_equal(vm1, vm2)
+    lens = vm1["factor_index_length"]
+    pos = np.repeat(vm1["factor_index_offset"], lens) + (np.arange(lens.sum()) - np.repeat(np.cumsum(lens) - lens, lens))
+    assert np.array_equal(fi1[pos], fi2[pos])
+    if kind == "repeats":
+        assert (vm1["factor_index_length"].sum() < len(fm))       # duplicates were dropped
+
+
+def test_compute_var_map_partitioned_path_reports_bad_graphs():
+    from numbskull_b200 import synth
+    from numbskull_b200.dataloading import assign_vtf_offsets, compute_var_map
+    from numbskull_b200.numbskulltypes import VarToFactor
+    w, v, f, fm, dm, e = synth.kbc(230000, rng=np.random.default_rng(6), n_weights=1000)
+    v = v.copy()
+    n = assign_vtf_offsets(v)
+    fm = fm.copy()
+    fm["vid"][len(fm) // 2] = len(v) + 5
+    with pytest.raises(Exception, match="vid out of range"):
+        compute_var_map(v, f, fm, np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64), dm)
+
+
 def test_factors_to_skip_is_bounds_checked():
     """The reference overruns factor_index here; we size it safely and skip correctly."""
     import numbskull_b200 as nb
