@@ -123,7 +123,9 @@ static bool var_map_partitioned(const nb_variable_rec *variable, int64_t n_varia
         fprintf(stderr, "  partitioned %-8s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
         t_last = now;
     };
-    const int nt = (int)std::min<int64_t>(32, std::max(1u, std::thread::hardware_concurrency()));
+    const char *nt_env = getenv("NUMBSKULL_B200_HOST_THREADS");
+    const int nt = nt_env ? std::max(1, std::min(64, atoi(nt_env)))
+                          : (int)std::min<int64_t>(32, std::max(1u, std::thread::hardware_concurrency()));
     if (nt < 2) return false;
     // contiguous factor chunks and the fmap positions they start at
     std::vector<int64_t> fbeg((size_t)nt + 1), ebeg((size_t)nt + 1, 0), esum((size_t)nt, 0);

@@ -130,14 +130,17 @@ def test_compute_var_map_partitioned_path_is_bit_exact(oracle, kind, monkeypatch
     v = v.copy()
     n = assign_vtf_offsets(v)
     out = {}
-    for mode in ("partitioned", "general"):
+    for mode in ("partitioned", "3 threads", "16 threads", "61 threads", "general"):
         if mode == "general":
             monkeypatch.setenv("NUMBSKULL_B200_VARMAP_GENERAL", "1")
+        elif mode != "partitioned":
+            monkeypatch.setenv("NUMBSKULL_B200_HOST_THREADS", mode.split()[0])     # the range count follows it
         vm, fi = np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64)
         compute_var_map(v, f, fm, vm, fi, dm)
         out[mode] = (vm, fi)
-    assert np.array_equal(out["partitioned"][0], out["general"][0])
-    assert np.array_equal(out["partitioned"][1], out["general"][1])
+    for mode in out:
+        assert np.array_equal(out[mode][0], out["general"][0]), mode
+        assert np.array_equal(out[mode][1], out["general"][1]), mode
     vm2, fi2 = np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64)
     oracle.compute_var_map(v.copy(), f, fm, vm2, fi2, dm)
     vm1, fi1 = out["partitioned"]
@@ -147,6 +150,34 @@ def test_compute_var_map_partitioned_path_is_bit_exact(oracle, kind, monkeypatch
     assert np.array_equal(fi1[pos], fi2[pos])
     if kind == "repeats":
         assert (vm1["factor_index_length"].sum() < len(fm))       # duplicates were dropped
+
+
+def test_compute_var_map_partitioned_path_with_fewer_variables_than_threads(monkeypatch):
+    """70 variables, 1.1 M fmap entries: most ranges are empty, every bucket is a hub."""
+    from numbskull_b200.dataloading import assign_vtf_offsets, compute_var_map
+    from numbskull_b200.numbskulltypes import Variable, Factor, FactorToVar, VarToFactor
+    rng = np.random.default_rng(0)
+    nv, nf = 70, 550000
+    v = np.zeros(nv, Variable)
+    v["cardinality"] = rng.integers(2, 5, nv)
+    v["dataType"] = rng.integers(0, 2, nv)
+    f = np.zeros(nf, Factor)
+    f["arity"], f["ftv_offset"], f["factorFunction"] = 2, np.arange(nf) * 2, 12
+    fm = np.zeros(2 * nf, FactorToVar)
+    fm["vid"] = rng.integers(0, nv, 2 * nf)
+    fm["dense_equal_to"] = rng.integers(0, 2, 2 * nf)
+    n = assign_vtf_offsets(v)
+    res = {}
+    for mode in ("default", "33", "general"):
+        if mode == "general":
+            monkeypatch.setenv("NUMBSKULL_B200_VARMAP_GENERAL", "1")
+        elif mode != "default":
+            monkeypatch.setenv("NUMBSKULL_B200_HOST_THREADS", mode)
+        vm, fi = np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64)
+        compute_var_map(v, f, fm, vm, fi, np.zeros(nv, bool))
+        res[mode] = (vm, fi)
+    for mode in res:
+        assert np.array_equal(res[mode][0], res["general"][0]) and np.array_equal(res[mode][1], res["general"][1]), mode
 
 
 def test_compute_var_map_partitioned_path_reports_bad_graphs():
