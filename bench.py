@@ -1,21 +1,37 @@
 #!/usr/bin/env python
-"""Benchmark of the Gibbs-sweep hot path (BASELINE.json metric: factor-edge
-evaluations / s and variable samples / s per sweep).
+"""Benchmark of the Gibbs-sweep / weight-learning hot path (BASELINE.json metric:
+factor-edge evaluations / s and variable samples / s per sweep).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workloads c2,c4,c3] [--blocks R]
 
-A "step" is one full chromatic Gibbs sweep (every colour once) over the
-workload: BASELINE config 2, the 4096 x 4096 Boolean Ising grid with EQUAL
-pairwise factors, inference only.  With N > 1 every rank owns a 4096-row strip
-of a (4096*N) x 4096 grid (weak scaling) and exchanges its boundary rows after
-every colour.
+Headline workload (``value``, ``e2e``, ``roofline``): BASELINE config 2, the
+4096 x 4096 Boolean Ising grid with EQUAL pairwise factors, inference only; a
+"step" is one full chromatic Gibbs sweep (every colour once).  The timed block
+of K steps is repeated R times back to back (each bracketed by CUDA events on
+the library's stream, barrier + synchronize on both sides) and the MEDIAN block
+is reported -- one 3.6 ms block is too fragile a sample.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput timed
-with CUDA events on the library's stream; `e2e` is the same metric through
-FactorGraph.inference() with host arrays, host<->device copies inside the
-timed region; `roofline` relates the algorithmic bytes of a sweep (SURVEY.md
-section 8d) to the measured HBM peak; `cpu_baseline` times the CPU oracle port
-of the reference algorithm on a bounded sample on this box's cores.
+With N = 1 two more blocks ride in the same JSON line:
+  ``c4``     BASELINE config 4 at full size (200 M Boolean variables / 1 B edges,
+             mixed ISTRUE / IMPLY / AND / OR factors): the configuration the
+             north-star target (>= 1e10 edge evals/s at >= 60 % of the HBM
+             roofline) is stated on, with its own ``roofline``;
+  ``learn``  BASELINE config 3 shape (1 M candidates x 100 labelling functions):
+             weight-learning epochs with the B_learn roofline.
+With N > 1 every rank owns a 4096-row strip of a (4096*N) x 4096 grid (weak
+scaling) and exchanges its boundary rows after every colour; before timing the
+ranks prove on a small strip problem that the partitioned run reproduces the
+single-GPU tallies bit for bit (``p2p_bit_identical``).
+
+``roofline.frac`` follows SURVEY.md 8(d) (algorithmic bytes / time / measured
+copy peak) and can exceed 1 for the Ising kernel, whose 4-byte records move far
+fewer bytes than the formula's 30 per edge; ``roofline.frac_dram`` is the same
+ratio on the DRAM bytes ncu measured for the kernel (profiles/traffic.json).
+
+``--impl reference`` times the UNMODIFIED numba reference (baseline/_ref, see
+baseline/install_ref.sh) on this box's host cores; its inputs are built with
+numpy and its own compute_var_map -- no library of this repo is loaded.
 """
 import argparse
 import ctypes as C
@@ -29,21 +45,19 @@ import time
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, REPO)
 
 GRID = int(os.environ.get("NB_BENCH_GRID", 4096))          # rows per GPU and columns
-CPU_GRID = int(os.environ.get("NB_BENCH_CPU_GRID", 1024))   # bounded sample for the CPU arm
+CPU_GRID = int(os.environ.get("NB_BENCH_CPU_GRID", 1024))   # bounded sample for the cpu_baseline leg
+C4_VARS = int(os.environ.get("NB_BENCH_C4_VARS", 200_000_000))
+C3_COPIES = int(os.environ.get("NB_BENCH_C3_COPIES", 1_000_000))
 METRIC = "factor_edge_evals_per_sec"
 UNIT = "factor-edge evals/s"
+SEED = 20261017
 
 
 # --------------------------------------------------------------------------- helpers
-def algorithmic_bytes_per_sweep(n_sampled, arities_of_edge_evals):
-    """SURVEY.md section 8(d): B_inf = N_v*16 + sum over edge evals (20 + 5*arity)."""
-    return 16.0 * n_sampled + float((20 + 5 * arities_of_edge_evals).sum())
-
-
 def ising_algorithmic_bytes(rows, cols):
+    """SURVEY.md section 8(d): B_inf = N_v*16 + sum over edge evals (20 + 5*arity)."""
     nvar = rows * cols
     edge_evals = 2 * (rows * (cols - 1) + (rows - 1) * cols)   # every factor is seen from both ends
     return 16.0 * nvar + edge_evals * (20 + 5 * 2), nvar, edge_evals
@@ -59,15 +73,29 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (or null)."""
+def ncu_traffic(key):
+    """DRAM bytes per sweep of a kernel from the committed ncu capture (or None)."""
     p = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_gibbs_tt2_bytes_per_sweep")
+            return json.load(open(p)).get(key)
         except Exception:
             pass
     return None
+
+
+def roofline(bytes_per_step, ms_per_step, kernel, traffic_key):
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    traffic = ncu_traffic(traffic_key)
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_per_step,
+           "kernel": kernel,
+           "frac_note": "frac = SURVEY 8(d) algorithmic bytes / time / peak (may exceed 1 when the record layout moves "
+                        "fewer bytes than the formula); frac_dram = ncu dram bytes of the same kernel / time / peak"}
+    if traffic:
+        out["frac_dram"] = traffic / (ms_per_step * 1e-3) / 1e9 / peak
+    return out
 
 
 class ClockSampler(object):
@@ -112,19 +140,141 @@ class ClockSampler(object):
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------- CPU arm
+# --------------------------------------------------------------------------- reference arm (numba, CPU)
+def _ref_ising_arrays(n, m, types, coupling=0.1):
+    """The config-2 grid in the REFERENCE's record dtypes (same construction as numbskull_b200/synth.py
+    ising_grid; restated here so that this arm imports nothing of the repo's package)."""
+    Weight, Variable, Factor, FactorToVar = types
+    weight = np.zeros(1, Weight)
+    weight["isFixed"] = True
+    weight["initialValue"] = coupling
+    variable = np.zeros(n * m, Variable)
+    variable["cardinality"] = 2
+    ii, jj = np.divmod(np.arange(n * m, dtype=np.int64), m)
+    has_up, has_left = ii != 0, jj != 0
+    nf = has_up.astype(np.int64) + has_left
+    first = np.zeros(n * m, np.int64)
+    np.cumsum(nf[:-1], out=first[1:])
+    nfac = int(nf.sum())
+    vid = np.arange(n * m, dtype=np.int64)
+    self_id, other = np.empty(nfac, np.int64), np.empty(nfac, np.int64)
+    self_id[first[has_up]] = vid[has_up]
+    other[first[has_up]] = vid[has_up] - m
+    ls = first[has_left] + has_up[has_left]
+    self_id[ls] = vid[has_left]
+    other[ls] = vid[has_left] - 1
+    factor = np.zeros(nfac, Factor)
+    factor["factorFunction"] = 3
+    factor["featureValue"] = 1.0
+    factor["arity"] = 2
+    factor["ftv_offset"] = 2 * np.arange(nfac, dtype=np.int64)
+    fmap = np.zeros(2 * nfac, FactorToVar)
+    fmap["vid"][0::2] = self_id
+    fmap["vid"][1::2] = other
+    return weight, variable, factor, fmap, np.zeros(n * m, np.bool_), int(2 * nfac)
+
+
+def _import_reference():
+    ref = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "numbskull")):
+        raise RuntimeError("baseline/_ref is missing: run baseline/install_ref.sh where /root/reference exists")
+    sys.path[:0] = [ref, os.path.join(REPO, "baseline", "shims")]
+    import numbskull
+    assert os.path.abspath(numbskull.__file__).startswith(ref), numbskull.__file__
+    from numbskull.numbskulltypes import Weight, Variable, Factor, FactorToVar
+    return numbskull, (Weight, Variable, Factor, FactorToVar)
+
+
+def _ref_graph(numbskull, types, grid, threads):
+    ns = numbskull.NumbSkull(nthreads=threads, quiet=True)
+    ns.loadFactorGraph(*_ref_ising_arrays(grid, grid, types))       # the reference's public loader
+    return ns.factorGraphs[0]
+
+
+def reference_throughput(steps, warmup, grid=None, threads=None, budget_s=150.0):
+    """Times fg.inference() of the unmodified numba reference with nthreads = all host cores and
+    reads the reference's own accumulator fg.inference_total_time (factorgraph.py:156-168).  The grid
+    is the 4096^2 config when warm-up + K sweeps fit the time budget, else the largest power-of-two
+    fraction of it that does (stated in the line)."""
+    numbskull, types = _import_reference()
+    threads = threads or os.cpu_count() or 1
+    if grid is None:
+        probe = _ref_graph(numbskull, types, 256, threads)
+        probe.inference(0, 1, sample_evidence=True)                 # JIT compilation happens here
+        t0 = probe.inference_total_time
+        probe.inference(0, 2, sample_evidence=True)
+        per_var = (probe.inference_total_time - t0) / 2 / (256 * 256)
+        per_var_load = 8e-6                                         # loadFactorGraph's Python loop (numbskull.py:222-227)
+        grid = GRID
+        while grid > 256 and grid * grid * (per_var * (steps + warmup) + per_var_load) > budget_s:
+            grid //= 2
+    fg = _ref_graph(numbskull, types, grid, threads)
+    fg.inference(0, max(1, warmup), sample_evidence=True)
+    t0 = fg.inference_total_time
+    fg.inference(0, steps, sample_evidence=True)
+    dt = fg.inference_total_time - t0
+    _, nvar, edges = ising_algorithmic_bytes(grid, grid)
+    return {"value": edges * steps / dt, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "%dx%d Ising grid, %d sweeps of the unmodified numba reference (baseline/_ref, numba gibbsthread), "
+                      "nthreads=%d, time = fg.inference_total_time" % (grid, grid, steps, threads),
+            "grid": grid, "var_samples_per_sec": nvar * steps / dt, "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    try:
+        r = reference_throughput(steps, warmup, grid=args.ref_grid or None)
+    except Exception as exc:  # noqa: BLE001
+        OUT.emit(json.dumps({"impl": "reference", "unavailable": "%s: %s" % (type(exc).__name__, exc)}))
+        return
+    g = r["grid"]
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "ising_%dx%d_equal_inference" % (g, g) +
+                                   ("" if g == GRID else " (bounded sample of the %dx%d config: the full grid does not "
+                                                         "finish %d sweeps within the time budget on %d cores)"
+                                                         % (GRID, GRID, steps + warmup, r["cores"]))},
+            "var_samples_per_sec": r["var_samples_per_sec"],
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    OUT.emit(json.dumps(line))
+
+
+def cpu_baselines(no_port=False):
+    """cpu_baseline leg of our arm: the numba reference in a child process (it must not share a
+    process with this repo's `numbskull` alias package) on a bounded 1024^2 grid, plus the C port."""
+    out = {}
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
+                              "--warmup", "1", "--ref-grid", str(CPU_GRID)], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=600)
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+        out = dict(line.get("cpu_baseline") or {"unavailable": line.get("unavailable")})
+    except Exception as exc:  # noqa: BLE001
+        out = {"unavailable": "numba reference: %s" % exc}
+    if not no_port:
+        try:
+            out["port"] = cpu_port_throughput(steps=3, warmup=1)
+        except Exception as exc:  # noqa: BLE001
+            out["port"] = {"unavailable": str(exc)}
+    return out
+
+
 def cpu_port_throughput(steps, warmup, grid=CPU_GRID, threads=None):
-    """The CPU oracle (C port of the reference's gibbsthread sweep, Hogwild over
-    contiguous variable ranges like run_pool) on a bounded grid."""
+    """The CPU oracle (C port of the reference's gibbsthread sweep, Hogwild over contiguous variable
+    ranges like run_pool) on a bounded grid -- second cpu_baseline entry, kind "port"."""
     import oracle
     from numbskull_b200 import synth
-    from numbskull_b200.dataloading import assign_vtf_offsets, compute_var_map
-    from numbskull_b200.numbskulltypes import VarToFactor
     threads = threads or os.cpu_count() or 1
+    from numbskull_b200.numbskulltypes import VarToFactor
     w, v, f, fm, dm, e = synth.ising_grid(grid, grid)
-    n = assign_vtf_offsets(v)
-    vm, fi = np.zeros(n, VarToFactor), np.zeros(len(fm), np.int64)
-    compute_var_map(v, f, fm, vm, fi, dm)
+    v["vtf_offset"] = np.arange(len(v))                  # Boolean variables: one bucket each (numbskull.py:222-227)
+    vm, fi = np.zeros(len(v), VarToFactor), np.zeros(len(fm), np.int64)
+    oracle.compute_var_map(v, f, fm, vm, fi, dm)
     og = oracle.OracleGraph(w, v, f, fm, vm, fi, nthreads=threads, seed=1)
     _, nvar, edges = ising_algorithmic_bytes(grid, grid)
     og.inference(0, warmup, sample_evidence=True)
@@ -132,31 +282,186 @@ def cpu_port_throughput(steps, warmup, grid=CPU_GRID, threads=None):
     og.inference(0, steps, sample_evidence=True)
     dt = time.perf_counter() - t0
     return {"value": edges * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%dx%d Ising grid, %d sweeps, C port of gibbsthread, %d Hogwild threads"
-                      % (grid, grid, steps, threads),
-            "var_samples_per_sec": nvar * steps / dt, "ms_per_step": 1e3 * dt / steps}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    steps, warmup = max(1, args.steps), max(1, args.warmup)
-    r = cpu_port_throughput(steps, warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "ising_%dx%d_equal_inference (bounded sample of the %dx%d config)"
-                                   % (CPU_GRID, CPU_GRID, GRID, GRID)},
-            "var_samples_per_sec": r["var_samples_per_sec"],
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    OUT.emit(json.dumps(line))
+            "sample": "%dx%d Ising grid, %d sweeps, C port of gibbsthread (oracle/nb_oracle.c), %d Hogwild threads"
+                      % (grid, grid, steps, threads)}
 
 
 # --------------------------------------------------------------------------- GPU arm
+class Dev(object):
+    """Timing helpers on the library's stream."""
+
+    def __init__(self, fg, world):
+        import torch
+        from numbskull_b200 import _lib
+        self.torch, self.lib, self.L = torch, _lib, _lib.lib()
+        self.fg, self.g, self.world = fg, fg._device_graph(), world
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+        self.lib.check(self.L.nb_synchronize(self.g))
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def launches(self):
+        n = C.c_int64(0)
+        self.L.nb_launch_count(self.g, C.byref(n))
+        return n.value
+
+    def timed_blocks(self, fn, steps, blocks):
+        """`blocks` back-to-back blocks of `steps` steps; per block: barrier + sync, CUDA events on
+        the launching stream, max over ranks.  Returns the per-block milliseconds."""
+        out = []
+        for _ in range(blocks):
+            self.barrier()
+            self.lib.check(self.L.nb_timer_start(self.g))
+            fn(steps)
+            ms = C.c_float(0)
+            self.lib.check(self.L.nb_timer_stop(self.g, C.byref(ms)))
+            self.barrier()
+            out.append(self.max_over_ranks(ms.value))
+        return out
+
+
+def block_c4(args, local_rank):
+    """BASELINE config 4 at full size on one GPU."""
+    import numbskull_b200 as nb
+    from numbskull_b200 import _lib, synth
+    t0 = time.perf_counter()
+    g = synth.kbc_fast(C4_VARS, seed=1004)
+    t1 = time.perf_counter()
+    ns = nb.NumbSkull(quiet=True)
+    ns.loadFactorGraph(*g)
+    del g
+    fg = ns.factorGraphs[0]
+    fg.device, fg.seed = local_rank, SEED
+    t2 = time.perf_counter()
+    dev = Dev(fg, 1)
+    t3 = time.perf_counter()
+    info = fg.device_info()
+    ar = fg.factor["arity"].astype(np.int64)
+    nvar, edges = len(fg.variable), int(info["n_edges"])
+    # every variable is sampled (sample_evidence) and no hub repeats inside a factor often enough to matter:
+    # B_inf = 16 N_v + sum_f arity_f (20 + 5 arity_f)
+    bytes_sweep = 16.0 * nvar + float((ar * (20 + 5 * ar)).sum())
+    del ar
+    L = dev.L
+    steps = max(3, min(args.steps, 10))
+
+    def sweeps(n):
+        _lib.check(L.nb_gibbs_sweeps(dev.g, n, 0, 1, fg.seed))
+    sweeps(3)
+    l0 = dev.launches()
+    ms = dev.timed_blocks(sweeps, steps, 3)
+    l1 = dev.launches()
+    med = float(np.median(ms)) / steps
+    bad = C.c_int64(-1)
+    _lib.check(L.nb_graph_check_coloring(dev.g, C.byref(bad)))
+    t4 = time.perf_counter()
+    fg.inference(0, 1, sample_evidence=True)
+    m = fg.marginals
+    e2e_ms = 1e3 * (time.perf_counter() - t4)
+    out = {"workload": "kbc_%d_vars_%d_edges_mixed_istrue_imply_and_or_inference (BASELINE config 4%s)"
+                       % (nvar, edges, "" if C4_VARS == 200_000_000 else ", scaled"),
+           "metric": METRIC, "value": edges / (med * 1e-3), "unit": UNIT, "ms_per_step": med,
+           "var_samples_per_sec": nvar / (med * 1e-3), "steps": steps, "timed_blocks_ms": ms,
+           "variables": nvar, "factor_edge_evals_per_sweep": edges, "colors": int(info["n_colors"]),
+           "color_conflicts": int(bad.value), "device_GB": round(info["device_bytes"] / 1e9, 2),
+           "gpu_launches": int(l1 - l0),
+           "rows": {"pair": int(info["n_pair_rows"]), "fast": int(info["n_fast_rows"]), "warp": int(info["n_warp_rows"])},
+           "roofline": roofline(bytes_sweep, med, "k_gibbs_tt (FAST rows: 16-byte truth-table quads with the weight "
+                                "inlined; one launch per colour)", "k_gibbs_tt_c4_bytes_per_sweep"),
+           "e2e_first_call_ms": e2e_ms, "mean_marginal": float(m.mean()),
+           "build_s": {"generate": round(t1 - t0, 1), "host_index": round(t2 - t1, 1), "device": round(t3 - t2, 1)}}
+    fg.clear()
+    del fg, ns, dev
+    return out
+
+
+def block_learn(args, local_rank):
+    """BASELINE config 3 shape: weight learning on the labelling-function model (L1, learn_non_evidence,
+    step 1e-4 as test_lf_learning.py:129-137)."""
+    import numbskull_b200 as nb
+    from numbskull_b200 import _lib, synth
+    n_lf = 100
+    g = synth.lf_model(C3_COPIES, n_lf, np.random.default_rng(1003))
+    ns = nb.NumbSkull(quiet=True)
+    ns.loadFactorGraph(*g)
+    del g
+    fg = ns.factorGraphs[0]
+    fg.device, fg.seed = local_rank, SEED
+    dev = Dev(fg, 1)
+    L = dev.L
+    copies = C3_COPIES
+    # B_learn (SURVEY 8d) = B_inf(free chain, all variables) + B_inf(evid chain, non-evidence variables, no count
+    # term) + 12 per gradient visit.  Per candidate: y (Boolean, 1 + n_lf incidences) and n_lf evidence LFs.
+    edges = copies * (1 + 2 * n_lf)
+    per_edge_y = 25.0 + n_lf * 30.0                       # y's incidences: arity 1 prior + n_lf arity-2 factors
+    b_free = copies * (16.0 * (1 + n_lf) + per_edge_y + n_lf * 30.0)
+    b_evid = copies * (8.0 + per_edge_y)                   # only y is non-evidence
+    b_learn = b_free + b_evid + 12.0 * edges
+    fg._sync_device(0, 0)
+
+    def epochs(n):
+        s = C.c_double(1e-4)
+        _lib.check(L.nb_learn_sweeps(dev.g, n, C.byref(s), 1.0, 1, 0.01, 1.0, 1, fg.seed, 0))
+    epochs(1)
+    l0 = dev.launches()
+    ms = dev.timed_blocks(epochs, 3, 3)
+    l1 = dev.launches()
+    med = float(np.median(ms)) / 3
+    fg._stale.add("weight_value")
+    w = fg.weight_value[0]
+    out = {"workload": "lf_model_%dx%d_learning_L1_learn_non_evidence_step1e-4 (BASELINE config 3 shape, %s of its size)"
+                       % (copies, n_lf, "%.0f%%" % (100.0 * copies / 1e7)),
+           "metric": METRIC, "value": edges / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "step": "one learning epoch",
+           "timed_blocks_ms": ms, "variables": int(len(fg.variable)), "factor_edge_evals_per_epoch": int(edges),
+           "gpu_launches_per_epoch": (l1 - l0) / 9.0,
+           "roofline": roofline(b_learn, med, "learning epoch (both chains + gradient reduction by weight id)",
+                                "learn_c3_bytes_per_epoch"),
+           "weights_head": [round(float(x), 4) for x in w[:6]], "weights_finite": bool(np.isfinite(w).all())}
+    fg.clear()
+    return out
+
+
+def p2p_identity_check(rank, world, local_rank):
+    """Before timing: a (256*world) x 256 strip problem sampled partitioned (this launch, the same
+    transport the timed sweeps use) and unpartitioned (every rank, its own GPU) must give the same
+    tallies bit for bit."""
+    import torch
+    import torch.distributed as dist
+    import numbskull_b200 as nb
+    from numbskull_b200 import _lib, partition, synth
+    rows, cols, epochs = 256, 256, 20
+    run = partition.ising_strip_runner(rows, cols, rank, world, local_rank, seed=77)
+    marg = run.inference(2, epochs, sample_evidence=True)
+    if run.p2p:
+        _lib.check(_lib.lib().nb_p2p_check(run.fg._g))
+    ns = nb.NumbSkull(quiet=True)
+    ns.loadFactorGraph(*synth.ising_grid(rows * world, cols))
+    fg = ns.factorGraphs[0]
+    fg.device, fg.seed = local_rank, 77
+    fg.inference(2, epochs, sample_evidence=True)
+    want = fg.marginals[rank * rows * cols:(rank + 1) * rows * cols]
+    same = bool(np.array_equal(np.asarray(marg), want))
+    t = torch.tensor([1 if same else 0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    fg.clear()
+    p2p, split = bool(run.p2p), bool(run.split)
+    run.close()
+    return bool(int(t.item())), p2p, split
+
+
 def run_ours(args):
+    sys.path.insert(0, REPO)
     import torch
     from numbskull_b200 import _lib, synth
     import numbskull_b200 as nb
@@ -167,30 +472,37 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        # stdout carries ONE JSON line: keep NCCL's banner ("NCCL version ...", printed to stdout when
-        # NCCL_DEBUG=VERSION) out of it
+        # stdout carries ONE JSON line: keep NCCL's banner out of it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
-                                timeout=datetime.timedelta(seconds=180))
+                                timeout=datetime.timedelta(seconds=300))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     L = _lib.lib()
-    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    steps, warmup, blocks = max(1, args.steps), max(3, args.warmup), max(1, args.blocks)
+    workloads = [w for w in args.workloads.split(",") if w]
+
+    identical = None
+    if world > 1:
+        identical = p2p_identity_check(rank, world, local_rank)
+        if not identical[0]:
+            raise RuntimeError("partitioned run does not reproduce the single-GPU tallies")
 
     rows, cols = GRID, GRID
     if world == 1:
         ns = nb.NumbSkull(quiet=True)
         ns.loadFactorGraph(*synth.ising_grid(rows, cols))
         fg = ns.factorGraphs[0]
-        fg.device, fg.seed = local_rank, 20261017
+        fg.device, fg.seed = local_rank, SEED
         runner = None
     else:
         from numbskull_b200 import partition
-        runner = partition.ising_strip_runner(rows, cols, rank, world, local_rank, seed=20261017)
+        runner = partition.ising_strip_runner(rows, cols, rank, world, local_rank, seed=SEED)
         fg = runner.fg
-    g = fg._device_graph()
+    dev = Dev(fg, world)
+    g = dev.g
     info = fg.device_info()
     bytes_sweep, nvar, edges = ising_algorithmic_bytes(rows, cols)
     if world == 1:
@@ -202,76 +514,89 @@ def run_ours(args):
         else:
             runner.sweeps(n, burnin=False, sample_evidence=True)
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-        _lib.check(L.nb_synchronize(g))
-
-    fg._upload(0, 0)
-    _lib.check(L.nb_reset_counts(g))
+    fg._sync_device(0, 0)
     sweeps(warmup)
-    barrier()
-    l0 = C.c_int64(0)
-    L.nb_launch_count(g, C.byref(l0))
-    def max_over_ranks(x):
-        if world == 1:
-            return float(x)
-        import torch.distributed as dist
-        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    dev.barrier()
     # `ncu --profile-from-start off` then lists exactly the launches of the timed region and of the
     # end-to-end steps (no-ops without a profiler)
     cudart = torch.cuda.cudart()
     with ClockSampler(local_rank) as clocks:
-        barrier()
+        l0 = dev.launches()
         cudart.cudaProfilerStart()
-        _lib.check(L.nb_timer_start(g))
         t0 = time.perf_counter()
-        sweeps(steps)
-        ms = C.c_float(0)
-        _lib.check(L.nb_timer_stop(g, C.byref(ms)))
-        cudart.cudaProfilerStop()
-        barrier()
+        block_ms = dev.timed_blocks(sweeps, steps, blocks)
         wall = time.perf_counter() - t0
-        dev_ms = max_over_ranks(ms.value)                      # max over ranks, device clock
-        l1 = C.c_int64(0)
-        L.nb_launch_count(g, C.byref(l1))
+        cudart.cudaProfilerStop()
+        l1 = dev.launches()
+        dev_ms = float(np.median(block_ms))
         # keep the GPUs busy a little longer so that the sampler sees clocks under load
         # (same count on every rank: it is derived from the rank-agreed dev_ms)
-        if dev_ms < 1500:
+        if sum(block_ms) < 1500:
             sweeps(max(1, int(steps * 1500 / max(dev_ms, 1e-3)) // 4))
-            barrier()
+            dev.barrier()
 
-    # ---- end to end through the public API with host arrays ----
-    e2e_steps = max(1, min(steps, 5))
-    if runner is None:
-        fg.inference(0, 1, sample_evidence=True)            # warm the transfer buffers
-        barrier()
-        cudart.cudaProfilerStart()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+    # ---- end to end through the public API with host buffers ----
+    # step = new weights in (host float64 array, uploaded because it changed) -> FactorGraph.inference(0, 1)
+    # -> the step's result out: the float64 marginals the reference API returns (device tallies cross PCIe
+    # as 1 byte each, widened by host threads).  var_value stays resident in HBM: nobody touched the host array.
+    e2e_steps = max(3, min(steps, 10))
+    target = fg if runner is None else runner
+
+    def e2e_step(i):
+        if runner is None:
+            fg.weight_value[0][0] = 0.1 + 1e-9 * (i & 1)
             fg.inference(0, 1, sample_evidence=True)
-        barrier()
-        e2e_dt = (time.perf_counter() - t0) / e2e_steps
-        cudart.cudaProfilerStop()
-    else:
-        runner.inference_e2e(1)
-        barrier()
+            return fg.marginals
+        return runner.inference_e2e(1)
+
+    e2e_step(0)
+    e2e_step(1)
+    dev.barrier()
+    cudart.cudaProfilerStart()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        m = e2e_step(i)
+    dev.barrier()
+    e2e_dt = dev.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    cudart.cudaProfilerStop()
+    e2e_extra = {}
+    if runner is None:
+        # the scalable read: compact tallies DMA-ed into pinned host memory, no host conversion
+        fg.counts_compact()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            runner.inference_e2e(1)
-        barrier()
-        e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        for i in range(e2e_steps):
+            fg.weight_value[0][0] = 0.1 + 1e-9 * (i & 1)
+            fg.inference(0, 1, sample_evidence=True)
+            cc = fg.counts_compact()
+        e2e_extra["compact_tallies_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / e2e_steps
+        e2e_extra["compact_tally_bytes"] = int(cc.nbytes)
+        # the reference's round trip: the caller holds var_value / count (edits possible), so both are
+        # uploaded on entry and refreshed on exit, as int64
+        _ = fg.var_value, fg.count
+        fg.inference(0, 1, sample_evidence=True)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            fg.inference(0, 1, sample_evidence=True)
+            m = fg.marginals
+        e2e_extra["state_roundtrip_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / e2e_steps
     V, Wn = len(fg.variable), len(fg.weight)
-    # bytes that cross PCIe per step: values travel as 1 byte, the tallies of a call of <= 255
-    # epochs as 1 byte too (4 otherwise) + the 4-byte maximum that decides it (narrowed / widened
-    # on the host next to pinned staging buffers), weights as float64
-    h2d = V * 1 + Wn * 8
-    d2h = V * 1 + len(fg.count) * 1 + 4
+    h2d = Wn * 8                                  # the float64 weights (changed every step)
+    d2h = len(fg._count) * 1                      # tallies of a 1-epoch call travel as 1 byte each
+
+    c4 = learn = None
+    if world == 1 and rank == 0:
+        fg.clear()
+        del dev
+        if "c4" in workloads:
+            try:
+                c4 = block_c4(args, local_rank)
+            except Exception as exc:  # noqa: BLE001
+                c4 = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+        if "c3" in workloads:
+            try:
+                learn = block_learn(args, local_rank)
+            except Exception as exc:  # noqa: BLE001
+                learn = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank != 0:
         if world > 1:
@@ -283,37 +608,41 @@ def run_ours(args):
     ms_per_step = dev_ms / steps
     total_edges, total_vars = edges * world, nvar * world
     value = total_edges * steps / (dev_ms * 1e-3)
-    peak, peak_src = measured_peak()
-    launches = l1.value - l0.value
-    achieved = bytes_sweep * steps / (dev_ms * 1e-3) / 1e9          # per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64 energy accumulation (f32 weights in the 16-byte quads, f32 exp for the draw)", "data": "synthetic",
         "config": {"workload": "ising_%dx%d_equal_inference%s" % (rows * world, cols,
                                                                  "" if world == 1 else "_strips_of_%d_rows" % rows),
                    "variables": total_vars, "factor_edge_evals_per_sweep": total_edges,
-                   "colors": info["n_colors"] if runner is None else runner.n_colors, "l2_policy": "inputs larger than L2 (incidence stream %.0f MB vs 126 MB)"
-                   % (info["stream_words"] * 4 / 1e6),
+                   "colors": info["n_colors"] if runner is None else runner.n_colors,
+                   "l2_policy": "inputs larger than L2 (record stream + per-variable state %.0f MB vs 126 MB)"
+                                % ((info["tt2_quads"] * 16 + nvar * 17) / 1e6),
                    "partition": "single GPU" if world == 1 else
                    ("row strips; per colour a boundary phase + NVLink halo push on a side stream, concurrent with "
                     "the interior phase" if runner.p2p and runner.split else "row strips, per-colour halo exchange")},
+        "timed_blocks": blocks, "timed_blocks_ms": block_ms, "block_statistic": "median",
         "var_samples_per_sec": total_vars * steps / (dev_ms * 1e-3),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "algorithmic_bytes_per_sweep": bytes_sweep,
-                     "kernel": "k_gibbs_tt2 (one launch per colour; duration = CUDA-event time of the "
-                               "timed region / sweeps)"},
-        "gpu_launches": int(launches if runner is None else launches),
+        "roofline": roofline(bytes_sweep, ms_per_step, "k_gibbs_tt2 (PAIR rows, uniform slices: 4-byte records; one launch "
+                             "per colour; duration = CUDA-event time of the median block / sweeps)",
+                             "k_gibbs_tt2_bytes_per_sweep"),
+        "gpu_launches": int(l1 - l0),
         "clocks": clocks.summary(),
-        "e2e": {"value": total_edges / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_dt,
-                "api": "FactorGraph.inference(0, 1) with int64/float64 host arrays"},
+        "e2e": dict({"value": total_edges / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_dt,
+                     "api": "weight_value[0][:] = w; FactorGraph.inference(0, 1); FactorGraph.marginals (float64) -- "
+                            "var_value is HBM-resident (host array untouched since the last call)"}, **e2e_extra),
         "wall_ms_timed_region": 1e3 * wall,
     }
+    if identical is not None:
+        line["p2p_bit_identical"] = identical[0]
+        line["p2p_transport"] = {"peer_stores": identical[1], "boundary_interior_split": identical[2]}
+    if c4 is not None:
+        line["c4"] = c4
+    if learn is not None:
+        line["learn"] = learn
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_throughput(steps=3, warmup=1)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = cpu_baselines()
     OUT.emit(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -346,9 +675,13 @@ def main():
     OUT = _QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--blocks", type=int, default=7, help="timed blocks of --steps steps (median reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workloads", default=os.environ.get("NB_BENCH_WORKLOADS", "c2,c4,c3"),
+                    help="N = 1 only: extra blocks next to the c2 headline")
+    ap.add_argument("--ref-grid", type=int, default=0, help="reference arm: force the grid size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

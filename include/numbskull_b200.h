@@ -79,6 +79,9 @@ typedef struct {
     int64_t device_bytes;              /* total device allocation                           */
     int64_t count_entries;             /* == cstart[n_variable]                              */
     int64_t jp_rounds;
+    int64_t max_arity;                 /* largest factor arity (the natural-order colouring is only tried when <= 2) */
+    int64_t n_pair_rows, n_fast_rows, n_cat_rows;   /* padded id ranges of the record row classes */
+    int64_t tt_quads, tt2_quads;       /* 16-byte quads in the FAST / PAIR record streams   */
 } nb_graph_info;
 
 const char *nb_last_error(void);
@@ -115,6 +118,15 @@ int nb_load_factors(const uint8_t *data, int64_t n_bytes, int64_t n_factor, nb_f
                     const nb_variable_rec *variable, int64_t n_variable, const nb_vtf_rec *vmap,
                     int64_t n_vmap);
 
+/* Benchmark input generator: the KBC-style Boolean graph of BASELINE config 4 (SURVEY.md 8d;
+ * numbskull_b200/synth.py kbc) written by host threads into caller-allocated record arrays --
+ * the role ising/ising.cpp:88-200 plays for the reference.  mix3 = IMPLY / AND / OR factors per
+ * variable; n_factor = nvar * (1 + sum mix3), n_fmap = nvar + 3 n_imp + 2 n_and + 3 n_or. */
+int nb_synth_kbc(int64_t nvar, uint64_t seed, int64_t n_weights, double evidence_frac, int64_t window,
+                 double far_frac, double hub_frac, double fixed_frac, const double *mix3,
+                 nb_weight_rec *weight, nb_variable_rec *variable, nb_factor_rec *factor, int64_t n_factor,
+                 nb_ftv_rec *fmap, int64_t n_fmap);
+
 /* -------------------------- graph lifecycle -------------------------- */
 
 /* FactorGraph.__init__ (factorgraph.py:30-73): builds the device-resident
@@ -150,6 +162,21 @@ int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate);
 /* Same, and in the same host pass marginals[i] = counts[i] / epochs (factorgraph.py:172-173). */
 int nb_get_counts_marginals(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double epochs);
 
+/* marginals[i] = device tally / epochs without materialising the int64 count array
+ * (factorgraph.py:172-173 when the caller only reads `marginals`). */
+int nb_get_marginals(nb_graph *g, double *marginals, double epochs);
+/* The device tallies in the reference's cstart layout at their natural width: *elem_bytes = 1, 2 or 4
+ * (no tally exceeds the number of tallying sweeps since the last reset); `out` should be pinned
+ * (nb_host_alloc) -- no host-side conversion at all. */
+int nb_get_counts_compact(nb_graph *g, void *out, int64_t out_bytes, int32_t *elem_bytes);
+/* Install `counts` (int64, cstart layout) as the device tallies: callers that edit `count` between
+ * calls.  The device tallies are CUMULATIVE like the reference's count array (factorgraph.py:30-31
+ * is never re-zeroed by inference()); nb_reset_counts zeroes them (FactorGraph.clear). */
+int nb_set_counts(nb_graph *g, const int64_t *counts);
+/* page-locked host memory for result arrays the library fills by DMA */
+int nb_host_alloc(void **ptr, int64_t bytes);
+int nb_host_free(void *ptr);
+
 /* ------------------------------ hot path ------------------------------ */
 
 /* inference.py:55-71 potential(), for parity tests: energies of every value of
@@ -157,6 +184,15 @@ int nb_get_counts_marginals(nb_graph *g, int64_t *counts, int accumulate, double
  * writes cardinality entries starting at out[out_offsets[i]]. */
 int nb_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
                   const int64_t *out_offsets, double *out, int64_t n_out);
+
+/* The same energies as the RECORD kernels compute them.  Boolean variables of the PAIR / FAST row
+ * classes (sampled by k_gibbs_tt2 / k_gibbs_tt from 8- and 16-byte truth-table records) write
+ * {0, potential(v,1) - potential(v,0)}; categorical variables of the CAT class (k_gibbs_cat) write
+ * their fp32 per-value energies; variables of the generic classes write nothing.  row_class[i]
+ * receives the class of var_ids[i] (0 PAIR, 1 FAST, 2 CAT, 3 GEN, 4 WARP).  The device code is the
+ * very function each sweep kernel calls, so this pins the hot kernels to inference.py:55-71. */
+int nb_potentials_records(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
+                          const int64_t *out_offsets, double *out, int64_t n_out, int32_t *row_class);
 
 /* run_pool(gibbsthread) x n_epochs (factorgraph.py:135-141 burnIn with
  * burnin != 0, :156-163 inference with burnin == 0): one chromatic Gibbs sweep
@@ -254,6 +290,8 @@ int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, int sample_ev
  * which never read a ghost).  Every rank must split (or none). */
 int nb_split_colors(nb_graph *g, const int32_t *boundary_ids, int64_t n);
 int nb_p2p_check(nb_graph *g);
+/* unmap the peers' arrays; call on every rank, synchronise the ranks, then nb_graph_destroy */
+int nb_p2p_close(nb_graph *g);
 /* run the sweeps on a caller-owned CUDA stream (cudaStream_t as void*) */
 int nb_set_stream(nb_graph *g, void *cuda_stream);
 int nb_begin_epoch(nb_graph *g, int64_t *epoch); /* returns and advances the sweep counter */

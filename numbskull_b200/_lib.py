@@ -40,6 +40,8 @@ class GraphInfo(C.Structure):
         ("n_edges", C.c_int64), ("n_colors", C.c_int32), ("wide_headers", C.c_int32),
         ("n_thread_rows", C.c_int64), ("n_warp_rows", C.c_int64), ("stream_words", C.c_int64),
         ("device_bytes", C.c_int64), ("count_entries", C.c_int64), ("jp_rounds", C.c_int64),
+        ("max_arity", C.c_int64), ("n_pair_rows", C.c_int64), ("n_fast_rows", C.c_int64),
+        ("n_cat_rows", C.c_int64), ("tt_quads", C.c_int64), ("tt2_quads", C.c_int64),
     ]
 
     def as_dict(self):
@@ -58,6 +60,7 @@ SIGNATURES = {
     "nb_load_variables": (C.c_int, [_P, _I64, _I64, _P]),
     "nb_load_domains": (C.c_int, [_P, _I64, _P, _P, _I64, _P, _I64]),
     "nb_load_factors": (C.c_int, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _I64]),
+    "nb_synth_kbc": (C.c_int, [_I64, _U64, _I64, _DBL, _I64, _DBL, _DBL, _DBL, _P, _P, _P, _P, _I64, _P, _I64]),
     "nb_graph_create": (C.c_int, [C.POINTER(GraphDesc), C.POINTER(_P)]),
     "nb_graph_destroy": (None, [_P]),
     "nb_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),
@@ -71,7 +74,13 @@ SIGNATURES = {
     "nb_reset_counts": (C.c_int, [_P]),
     "nb_get_counts": (C.c_int, [_P, _P, C.c_int]),
     "nb_get_counts_marginals": (C.c_int, [_P, _P, C.c_int, _P, _DBL]),
+    "nb_get_marginals": (C.c_int, [_P, _P, _DBL]),
+    "nb_get_counts_compact": (C.c_int, [_P, _P, _I64, C.POINTER(_I32)]),
+    "nb_set_counts": (C.c_int, [_P, _P]),
+    "nb_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
+    "nb_host_free": (C.c_int, [_P]),
     "nb_potentials": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P, _I64]),
+    "nb_potentials_records": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P, _I64, _P]),
     "nb_gibbs_sweeps": (C.c_int, [_P, _I64, C.c_int, C.c_int, _U64]),
     "nb_learn_sweeps": (C.c_int, [_P, _I64, C.POINTER(_DBL), _DBL, C.c_int, _DBL, _DBL, C.c_int, _U64, _I64]),
     "nb_timer_start": (C.c_int, [_P]),
@@ -101,6 +110,7 @@ SIGNATURES = {
     "nb_p2p_wait": (C.c_int, [_P]),
     "nb_gibbs_sweeps_p2p": (C.c_int, [_P, _I64, C.c_int, C.c_int, _U64, C.c_int, C.c_int]),
     "nb_p2p_check": (C.c_int, [_P]),
+    "nb_p2p_close": (C.c_int, [_P]),
     "nb_set_stream": (C.c_int, [_P, _P]),
     "nb_begin_epoch": (C.c_int, [_P, C.POINTER(_I64)]),
 }

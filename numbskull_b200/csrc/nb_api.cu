@@ -66,6 +66,8 @@ extern "C" int nb_graph_get_info(const nb_graph *g, nb_graph_info *info)
     info->n_thread_rows = g->n_trows; info->n_warp_rows = g->n_wrows;
     info->stream_words = g->n_twords + g->n_wwords;
     info->device_bytes = g->device_bytes; info->count_entries = g->count_entries; info->jp_rounds = g->jp_rounds;
+    info->max_arity = g->max_arity; info->n_pair_rows = g->n_prows; info->n_fast_rows = g->n_frows - g->n_prows;
+    info->n_cat_rows = g->n_crows - g->n_frows; info->tt_quads = g->n_tt_quads; info->tt2_quads = g->n_tt2_quads;
     return NB_OK;
 }
 
@@ -97,11 +99,27 @@ extern "C" int nb_graph_color_edges(const nb_graph *g, int64_t *edges_per_color)
 // copy has landed (one event per chunk).
 static const int64_t NB_XFER_CHUNK = 1 << 18;   // elements
 
+// Conversion threads of one process: at most 32, and the box's cores are shared by the ranks of a
+// torchrun launch (LOCAL_WORLD_SIZE) -- 8 ranks x 32 threads on a 32-core host was what made the
+// end-to-end step collapse at N = 8.  NUMBSKULL_B200_HOST_THREADS overrides.
+static int nb_host_threads()
+{
+    static const int n = [] {
+        const char *e = getenv("NUMBSKULL_B200_HOST_THREADS");
+        if (e && atoi(e) > 0) return atoi(e);
+        int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+        const char *lw = getenv("LOCAL_WORLD_SIZE");
+        int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+        return std::max(1, std::min(32, cores / ranks));
+    }();
+    return n;
+}
+
 template <class F>
 static int host_chunks(nb_graph *g, int64_t n, F fn)   // fn(chunk index, begin, end) -> cudaError_t
 {
     const int64_t nchunks = (n + NB_XFER_CHUNK - 1) / NB_XFER_CHUNK;
-    int nt = (int)std::min<int64_t>(nchunks, std::min(32u, std::max(1u, std::thread::hardware_concurrency())));
+    int nt = (int)std::min<int64_t>(nchunks, nb_host_threads());
     std::atomic<int64_t> next(0);
     std::atomic<int> err(0);
     auto work = [&](bool worker) {
@@ -172,6 +190,19 @@ __attribute__((target("avx2"))) static void merge_nt(const T *s, int64_t *c, int
         _mm256_stream_pd(m + i, _mm256_load_pd(t));
     }
     for (; i < b; i++) one(i);
+    _mm_sfence();
+}
+template <class T>
+__attribute__((target("avx2"))) static void marginals_nt(const T *s, double *m, double div, int64_t a, int64_t b)
+{
+    int64_t i = a;
+    for (; i < b && ((uintptr_t)(m + i) & 31); i++) m[i] = (double)s[i] / div;
+    const __m256d vdiv = _mm256_set1_pd(div);
+    for (; i + 4 <= b; i += 4) {
+        const __m256d x = _mm256_set_pd((double)s[i + 3], (double)s[i + 2], (double)s[i + 1], (double)s[i]);
+        _mm256_stream_pd(m + i, _mm256_div_pd(x, vdiv));
+    }
+    for (; i < b; i++) m[i] = (double)s[i] / div;
     _mm_sfence();
 }
 #else
@@ -287,6 +318,7 @@ extern "C" int nb_set_weights(nb_graph *g, const double *weights)
     NB_CUDA(cudaSetDevice(g->device));
     NB_CUDA(cudaMemcpyAsync(g->d_weight, weights, (size_t)g->W * 8, cudaMemcpyHostToDevice, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
+    g->weights_version++;
     return NB_OK;
 }
 
@@ -304,38 +336,43 @@ extern "C" int nb_reset_counts(nb_graph *g)
     NB_CUDA(cudaSetDevice(g->device));
     NB_CUDA(cudaMemsetAsync(g->d_count, 0, (size_t)g->count_entries * 4, g->stream));
     NB_CUDA(cudaMemsetAsync(g->d_count_b, 0, (size_t)g->Vn * 4, g->stream));
+    g->tally_bound = 0;
     return NB_OK;
 }
 
-// new-order tallies -> reference cstart layout (still int32; widened on the host)
+// new-order tallies -> reference cstart layout, narrowed on the fly: no tally exceeds the number of
+// tallying sweeps since the last reset (g->tally_bound, tracked on the host), so a short call's tallies
+// cross PCIe as one byte each (two up to 65535 sweeps).
 // (Boolean rows sampled by the truth-table kernels tally into count_b[new id].)
-// Also records the largest tally: tallies of a short call fit one byte and then cross PCIe as such.
+template <class T>
 __global__ void k_counts_to_old(int64_t V, const int32_t *count, const int32_t *count_b, const uint32_t *cstart_new,
-                                const int64_t *cstart_old, const int32_t *old2new, const int32_t *v_card, int32_t *out,
-                                int *max_out)
+                                const int64_t *cstart_old, const int32_t *old2new, const int32_t *v_card, T *out)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int m = 0;
-    if (v < V) {
-        int n = v_card[v] == 2 ? 1 : v_card[v];
-        int nid = old2new[v];
-        uint32_t s = cstart_new[nid];
-        int64_t d = cstart_old[v];
-        for (int j = 0; j < n; j++) {
-            int c = count[s + j];
-            if (j == 0 && v_card[v] == 2) c += count_b[nid];
-            out[d + j] = c;
-            m = max(m, c);
-        }
+    if (v >= V) return;
+    int n = v_card[v] == 2 ? 1 : v_card[v];
+    int nid = old2new[v];
+    uint32_t s = cstart_new[nid];
+    int64_t d = cstart_old[v];
+    for (int j = 0; j < n; j++) {
+        int c = count[s + j];
+        if (j == 0 && v_card[v] == 2) c += count_b[nid];
+        out[d + j] = (T)c;
     }
-    m = __reduce_max_sync(0xFFFFFFFFu, m);
-    if ((threadIdx.x & 31) == 0 && m > *(volatile int *)max_out) atomicMax(max_out, m);
 }
 
-__global__ void k_narrow_u8(int64_t n, const int32_t *in, uint8_t *out)
+// reference cstart layout -> new-order tallies (nb_set_counts)
+__global__ void k_counts_from_old(int64_t V, int32_t *count, int32_t *count_b, const uint32_t *cstart_new,
+                                  const int64_t *cstart_old, const int32_t *old2new, const int32_t *v_card, const int32_t *in)
 {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint8_t)in[i];
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int n = v_card[v] == 2 ? 1 : v_card[v];
+    int nid = old2new[v];
+    uint32_t s = cstart_new[nid];
+    int64_t d = cstart_old[v];
+    for (int j = 0; j < n; j++) count[s + j] = in[d + j];
+    count_b[nid] = 0;
 }
 
 template <class T>
@@ -345,6 +382,13 @@ static int merge_counts(nb_graph *g, int64_t n, int64_t *counts, int accumulate,
     return host_chunks(g, n, [&](int64_t k, int64_t a, int64_t b) {
         cudaError_t e = cudaEventSynchronize(g->xfer_events[(size_t)k]);
         if (e != cudaSuccess) return e;
+        if (!counts) {      // marginals only: the int64 count array is not materialised
+#if NB_HAVE_AVX2_PATH
+            if (nb_use_nt()) { marginals_nt<T>(src, marginals, divisor, a, b); return cudaSuccess; }
+#endif
+            for (int64_t i = a; i < b; i++) marginals[i] = (double)src[i] / divisor;
+            return cudaSuccess;
+        }
 #if NB_HAVE_AVX2_PATH
         if (marginals && nb_use_nt()) { merge_nt<T>(src, counts, accumulate, marginals, divisor, a, b); return cudaSuccess; }
 #endif
@@ -357,31 +401,41 @@ static int merge_counts(nb_graph *g, int64_t n, int64_t *counts, int accumulate,
     });
 }
 
+// element width the tallies travel with
+static int tally_bytes(const nb_graph *g) { return g->tally_bound <= 255 ? 1 : (g->tally_bound <= 65535 ? 2 : 4); }
+
+static int stage_counts(nb_graph *g, int elem)
+{
+    const int64_t n = g->count_entries;
+    NB_TRY(nb_ensure_xfer(g, (size_t)n * elem + 256));
+    const unsigned grid = grid_for(g->V);
+    if (elem == 1)
+        k_counts_to_old<uint8_t><<<grid, 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
+                                                               g->d_old2new, g->d_v_card, (uint8_t *)g->d_xfer);
+    else if (elem == 2)
+        k_counts_to_old<uint16_t><<<grid, 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
+                                                                g->d_old2new, g->d_v_card, (uint16_t *)g->d_xfer);
+    else
+        k_counts_to_old<int32_t><<<grid, 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
+                                                               g->d_old2new, g->d_v_card, (int32_t *)g->d_xfer);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
 static int fetch_counts(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double divisor)
 {
     if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
     NB_CUDA(cudaSetDevice(g->device));
     const int64_t n = g->count_entries;
     if (n == 0) return NB_OK;
-    const size_t narrow_off = ((size_t)n * 4 + 255) & ~(size_t)255;
-    NB_TRY(nb_ensure_xfer(g, narrow_off + (size_t)n + 256));
-    NB_TRY(nb_ensure_pinned(g, (size_t)n * 4));
-    int *d_max = (int *)((char *)g->d_xfer + narrow_off + (((size_t)n + 15) & ~(size_t)15));
-    NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
-    k_counts_to_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
-                                                            g->d_old2new, g->d_v_card, (int32_t *)g->d_xfer, d_max);
-    int maxc = 0;
-    NB_CUDA(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
-    NB_CUDA(cudaStreamSynchronize(g->stream));
-    int rc;
-    if (maxc <= 255) {
-        uint8_t *d_u8 = (uint8_t *)g->d_xfer + narrow_off;
-        k_narrow_u8<<<grid_for(n), 256, 0, g->stream>>>(n, (const int32_t *)g->d_xfer, d_u8);
-        rc = download_chunks(g, d_u8, n, 1);
-        if (rc == NB_OK) rc = merge_counts<uint8_t>(g, n, counts, accumulate, marginals, divisor);
-    } else {
-        rc = download_chunks(g, g->d_xfer, n, 4);
-        if (rc == NB_OK) rc = merge_counts<int32_t>(g, n, counts, accumulate, marginals, divisor);
+    const int elem = tally_bytes(g);
+    NB_TRY(nb_ensure_pinned(g, (size_t)n * elem));
+    NB_TRY(stage_counts(g, elem));
+    int rc = download_chunks(g, g->d_xfer, n, elem);
+    if (rc == NB_OK) {
+        if (elem == 1) rc = merge_counts<uint8_t>(g, n, counts, accumulate, marginals, divisor);
+        else if (elem == 2) rc = merge_counts<uint16_t>(g, n, counts, accumulate, marginals, divisor);
+        else rc = merge_counts<int32_t>(g, n, counts, accumulate, marginals, divisor);
     }
     NB_CUDA(cudaStreamSynchronize(g->stream));
     return rc;
@@ -395,6 +449,76 @@ extern "C" int nb_get_counts(nb_graph *g, int64_t *counts, int accumulate)
 extern "C" int nb_get_counts_marginals(nb_graph *g, int64_t *counts, int accumulate, double *marginals, double epochs)
 {
     return fetch_counts(g, counts, accumulate, marginals, epochs);
+}
+
+extern "C" int nb_get_marginals(nb_graph *g, double *marginals, double epochs)
+{
+    if (!marginals) NB_FAIL(NB_ERR_INVALID, "null marginals");
+    return fetch_counts(g, nullptr, 0, marginals, epochs);
+}
+
+extern "C" int nb_get_counts_compact(nb_graph *g, void *out, int64_t out_bytes, int32_t *elem_bytes)
+{
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
+    NB_CUDA(cudaSetDevice(g->device));
+    const int elem = tally_bytes(g);
+    *elem_bytes = elem;
+    const int64_t n = g->count_entries;
+    if (n == 0) return NB_OK;
+    if (out_bytes < n * elem) NB_FAIL(NB_ERR_INVALID, "buffer of %lld bytes is too small for %lld tallies of %d bytes", (long long)out_bytes, (long long)n, elem);
+    NB_TRY(stage_counts(g, elem));
+    NB_CUDA(cudaMemcpyAsync(out, g->d_xfer, (size_t)n * elem, cudaMemcpyDeviceToHost, g->stream));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_host_alloc(void **ptr, int64_t bytes)
+{
+    cudaError_t e = cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 16));
+    if (e != cudaSuccess) NB_FAIL(NB_ERR_NOMEM, "cudaMallocHost(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    return NB_OK;
+}
+
+extern "C" int nb_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+    return NB_OK;
+}
+
+extern "C" int nb_set_counts(nb_graph *g, const int64_t *counts)
+{
+    if (!g->finalized) NB_FAIL(NB_ERR_INVALID, "graph not finalized");
+    NB_CUDA(cudaSetDevice(g->device));
+    const int64_t n = g->count_entries;
+    if (n == 0) return NB_OK;
+    NB_TRY(nb_ensure_pinned(g, (size_t)n * 4));
+    NB_TRY(nb_ensure_xfer(g, (size_t)n * 4 + 256));
+    int32_t *stage = (int32_t *)g->h_pinned;
+    std::atomic<long long> mx(0);
+    std::atomic<int> bad(0);
+    int rc = host_chunks(g, n, [&](int64_t, int64_t a, int64_t b) {
+        long long m = 0;
+        for (int64_t i = a; i < b; i++) {
+            const int64_t c = counts[i];
+            if (c < 0 || c > 0x7FFFFFFF) bad.store(1);
+            stage[i] = (int32_t)c;
+            m = std::max<long long>(m, c);
+        }
+        long long cur = mx.load();
+        while (m > cur && !mx.compare_exchange_weak(cur, m)) {}
+        return cudaMemcpyAsync((int32_t *)g->d_xfer + a, stage + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, g->stream);
+    });
+    if (rc != NB_OK || bad.load()) {
+        cudaStreamSynchronize(g->stream);
+        if (rc != NB_OK) return rc;
+        NB_FAIL(NB_ERR_INVALID, "count holds entries outside [0, 2^31)");
+    }
+    k_counts_from_old<<<grid_for(g->V), 256, 0, g->stream>>>(g->V, g->d_count, g->d_count_b, g->d_cstart, g->d_cstart_old,
+                                                              g->d_old2new, g->d_v_card, (const int32_t *)g->d_xfer);
+    NB_CUDA(cudaGetLastError());
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    g->tally_bound = mx.load();
+    return NB_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -417,6 +541,14 @@ extern "C" int nb_potentials(nb_graph *g, int chain, const int64_t *var_ids, int
     return nb_run_potentials(g, chain, var_ids, n, out_offsets, out, n_out);
 }
 
+extern "C" int nb_potentials_records(nb_graph *g, int chain, const int64_t *var_ids, int64_t n, const int64_t *out_offsets,
+                                     double *out, int64_t n_out, int32_t *row_class)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_TRY(check_runnable(g));
+    return nb_run_potentials_records(g, chain, var_ids, n, out_offsets, out, n_out, row_class);
+}
+
 extern "C" int nb_begin_epoch(nb_graph *g, int64_t *epoch)
 {
     *epoch = (int64_t)g->epoch_counter++;
@@ -434,6 +566,7 @@ extern "C" int nb_gibbs_sweeps(nb_graph *g, int64_t n_epochs, int burnin, int sa
 {
     NB_CUDA(cudaSetDevice(g->device));
     NB_TRY(check_runnable(g));
+    NB_TRY(nb_refresh_inlined_weights(g));
     for (int64_t ep = 0; ep < n_epochs; ep++) {
         uint64_t epoch = g->epoch_counter++;
         for (int c = 0; c < g->n_colors; c++) NB_TRY(nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch));

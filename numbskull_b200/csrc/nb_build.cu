@@ -467,14 +467,19 @@ __global__ void k_tt_slice_width(int64_t n_slices, const int32_t *new2old, const
     quads[s] = (int64_t)w * 32;
 }
 
-__global__ void k_tt_pad(uint4 *tt, uint32_t *base, int64_t n)
+__global__ void k_tt_pad(uint4 *tt, uint32_t *base, uint32_t *wid, int64_t n)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) { tt[i] = make_uint4(0u, 0u, NB_TT_NEUTRAL | NB_TT_FIXED_BIT, 0u); base[i] = NB_TT_BASE_NEUTRAL; }
+    if (i < n) { tt[i] = make_uint4(0u, 0u, NB_TT_NEUTRAL | NB_TT_FIXED_BIT, 0u); base[i] = NB_TT_BASE_NEUTRAL; wid[i] = 0u; }
 }
 
-__global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, const int64_t *tt_ptr, uint4 *tt,
-                          uint32_t *tt_base, const uint8_t *wfixed)
+// The tables are produced by nb_tabulate (nb_eval.cuh), i.e. by nb_eval_incidence_v run on the
+// variable's own generic row with the other members' values forced: one source of truth for
+// factor semantics.  k_fill_rows must have run.
+template <bool WIDE>
+__global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, const int64_t *slice_ptr,
+                          const uint32_t *twords, const int64_t *tt_ptr, uint4 *tt, uint32_t *tt_base, uint32_t *tt_wid,
+                          const uint8_t *wfixed, const double *weight)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= G.V || G.v_evid[v] == 4) return;
@@ -482,65 +487,110 @@ __global__ void k_fill_tt(RawGraph G, const int32_t *old2new, int64_t n_frows, c
     if (nid >= n_frows) return;
     uint4 *row = tt + tt_ptr[nid >> 5] + (nid & 31);
     uint32_t *brow = tt_base + tt_ptr[nid >> 5] + (nid & 31);
-    const int64_t off = G.b_off[G.v_vtf[v]];
+    uint32_t *wrow = tt_wid + tt_ptr[nid >> 5] + (nid & 31);
     const int len = G.b_len[G.v_vtf[v]];
+    const NbRow r = nb_thread_row(twords, slice_ptr, nid);
+    int pos = 0;
     for (int e = 0; e < len; e++) {
-        const int f = G.fi[off + e];
-        const int code = G.f_code[f], a = G.f_arity[f];
-        const int64_t mo = G.f_off[f];
-        // which "other" slot (0 = A, 1 = B) each member reads; -1 = the variable itself
-        int slot[3] = {-1, -1, -1};
-        uint32_t other[2] = {(uint32_t)nid, (uint32_t)nid};
-        int n_other = 0;
-        for (int j = 0; j < a; j++) {
-            int u = G.m_vid[mo + j];
-            if (u != v) { slot[j] = n_other; other[n_other++] = (uint32_t)old2new[u]; }
-        }
-        int extra = 0;
-        if (nb_code_has_extra(code)) {
-            int m = nb_code_abstain_member(code);
-            extra = m < a ? G.v_card[G.m_vid[mo + m]] - 1 : 0;
-        }
-        uint32_t table = 0, base = 0;
-        for (int xa = 0; xa < 3; xa++)
-            for (int xb = 0; xb < 3; xb++) {
-                NbFastStats st;
-                st.reset();
-                st.extra = extra;
-                for (int j = 0; j < a; j++) st.member(j, a, slot[j] < 0, slot[j] < 0 ? 0 : (slot[j] == 0 ? xa : xb));
-                int f0 = (int)st.value(code, 0);
-                int d = (int)st.value(code, 1) - f0;
-                table |= (uint32_t)(d + 2) << (3 * (3 * xa + xb));
-                base |= (uint32_t)(f0 + 1) << (2 * (3 * xa + xb));
-            }
-        const uint32_t wid = (uint32_t)G.f_wid[f];
-        if (wfixed[wid]) table |= NB_TT_FIXED_BIT;
-        row[(size_t)e * 32] = make_uint4(other[0], other[1], table, wid);
+        uint32_t other[2], table, base;
+        const NbHdr h = nb_tabulate<WIDE>(r, pos, (uint32_t)nid, other, table, base);
+        if (wfixed[h.wid]) table |= NB_TT_FIXED_BIT;
+        row[(size_t)e * 32] = make_uint4(other[0], other[1], table, __float_as_uint((float)weight[h.wid]));
         brow[(size_t)e * 32] = base;
+        wrow[(size_t)e * 32] = h.wid;
+        pos += nb_inc_words<WIDE>(h);
     }
+}
+
+// (re)inline the current weight values into the quads
+__global__ void k_tt_refresh(int64_t n, uint4 *tt, const uint32_t *tt_wid, const double *weight)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) reinterpret_cast<uint32_t *>(tt + i)[3] = __float_as_uint((float)__ldg(weight + tt_wid[i]));
+}
+
+int nb_refresh_inlined_weights(nb_graph *g)
+{
+    if (g->tt_weights_version == g->weights_version) return NB_OK;
+    if (g->n_tt_quads) {
+        k_tt_refresh<<<(unsigned)((g->n_tt_quads + 255) / 256), 256, 0, g->stream>>>(g->n_tt_quads, g->d_tt, g->d_tt_wid, g->d_weight);
+        NB_CUDA(cudaGetLastError());
+    }
+    g->tt_weights_version = g->weights_version;
+    return NB_OK;
 }
 
 // ---- pair stream of the PAIR rows -----------------------------------------------------------
-__global__ void k_tt2_slice_width(int64_t n_slices, const int32_t *new2old, const uint32_t *ninc, int64_t *quads)
+// second word {table:9 | fixed:1 | wid:22} of the PAIR incidence at `pos`, and its other member
+template <bool WIDE>
+__device__ inline uint32_t nb_pair_word(const NbRow &r, int &pos, uint32_t self, const uint8_t *wfixed, uint32_t &other)
+{
+    uint32_t o2[2], table, base;
+    const NbHdr h = nb_tabulate<WIDE>(r, pos, self, o2, table, base);
+    // only xb = 0 matters: a PAIR incidence has at most one other member (slot A)
+    uint32_t t3 = 0;
+    for (int x = 0; x < 3; x++) t3 |= ((table >> (3 * (3 * x))) & 7u) << (3 * x);
+    other = o2[0];
+    pos += nb_inc_words<WIDE>(h);
+    return nb_pack_pair(t3, wfixed[h.wid], h.wid);
+}
+
+// per PAIR row: the second word shared by all its records (NB_PAIR_ANY: no record, NB_PAIR_NONE: mixed)
+template <bool WIDE>
+__global__ void k_tt2_row_word(RawGraph G, const int32_t *old2new, int64_t n_prows, const int64_t *slice_ptr,
+                               const uint32_t *twords, const uint8_t *wfixed, uint32_t *row_word)
+{
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= G.V || G.v_evid[v] == 4) return;
+    const int64_t nid = old2new[v];
+    if (nid >= n_prows) return;
+    const int len = G.b_len[G.v_vtf[v]];
+    const NbRow r = nb_thread_row(twords, slice_ptr, nid);
+    uint32_t common = NB_PAIR_ANY;
+    int pos = 0;
+    for (int e = 0; e < len; e++) {
+        uint32_t other;
+        const uint32_t w = nb_pair_word<WIDE>(r, pos, (uint32_t)nid, wfixed, other);
+        if (common == NB_PAIR_ANY) common = w;
+        else if (common != w) common = NB_PAIR_NONE;
+    }
+    row_word[nid] = common;
+}
+
+// slice width in quads and the slice's common word (NB_PAIR_NONE = two 8-byte records per quad)
+__global__ void k_tt2_slice_width(int64_t n_slices, const int32_t *new2old, const uint32_t *ninc, const uint32_t *row_word,
+                                  int uniform_ok, int64_t *quads, uint32_t *common_out)
 {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_slices) return;
-    uint32_t w = 0;
+    uint32_t w = 0, common = NB_PAIR_ANY;
     for (int l = 0; l < 32; l++) {
         int v = new2old[s * 32 + l];
-        if (v >= 0) w = max(w, ninc[v]);
+        if (v < 0) continue;
+        w = max(w, ninc[v]);
+        const uint32_t rw = row_word[s * 32 + l];
+        if (rw == NB_PAIR_ANY) continue;
+        if (common == NB_PAIR_ANY) common = rw;
+        else if (common != rw) common = NB_PAIR_NONE;
     }
-    quads[s] = (int64_t)((w + 1) / 2) * 32;
+    if (common == NB_PAIR_ANY || !uniform_ok) common = NB_PAIR_NONE;
+    common_out[s] = common;
+    quads[s] = (common != NB_PAIR_NONE ? (int64_t)((w + 3) / 4) : (int64_t)((w + 1) / 2)) * 32;
 }
 
-__global__ void k_tt2_pad(uint4 *tt2, int64_t n)
+__global__ void k_tt2_pad(uint4 *tt2, const int64_t *tt2_ptr, const uint32_t *common, int64_t n_slices)
 {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t s = blockIdx.x;
+    if (s >= n_slices) return;
     const uint32_t w = nb_pack_pair(NB_PAIR_NEUTRAL, 1, 0u);
-    if (i < n) tt2[i] = make_uint4(0u, w, 0u, w);
+    const uint4 pad = common[s] != NB_PAIR_NONE ? make_uint4(NB_PAIR_NONE, NB_PAIR_NONE, NB_PAIR_NONE, NB_PAIR_NONE)
+                                               : make_uint4(0u, w, 0u, w);
+    for (int64_t i = tt2_ptr[s] + threadIdx.x; i < tt2_ptr[s + 1]; i += blockDim.x) tt2[i] = pad;
 }
 
-__global__ void k_fill_tt2(RawGraph G, const int32_t *old2new, int64_t n_prows, const int64_t *tt2_ptr, uint4 *tt2,
+template <bool WIDE>
+__global__ void k_fill_tt2(RawGraph G, const int32_t *old2new, int64_t n_prows, const int64_t *slice_ptr,
+                           const uint32_t *twords, const int64_t *tt2_ptr, const uint32_t *tt2_common, uint4 *tt2,
                            const uint8_t *wfixed)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -548,35 +598,15 @@ __global__ void k_fill_tt2(RawGraph G, const int32_t *old2new, int64_t n_prows, 
     const int64_t nid = old2new[v];
     if (nid >= n_prows) return;
     uint4 *row = tt2 + tt2_ptr[nid >> 5] + (nid & 31);
-    const int64_t off = G.b_off[G.v_vtf[v]];
+    const bool uniform = tt2_common[nid >> 5] != NB_PAIR_NONE;
     const int len = G.b_len[G.v_vtf[v]];
+    const NbRow r = nb_thread_row(twords, slice_ptr, nid);
+    int pos = 0;
     for (int e = 0; e < len; e++) {
-        const int f = G.fi[off + e];
-        const int code = G.f_code[f], a = G.f_arity[f];
-        const int64_t mo = G.f_off[f];
-        bool isself[3] = {true, true, true};
-        uint32_t other = (uint32_t)nid;
-        for (int j = 0; j < a; j++) {
-            int u = G.m_vid[mo + j];
-            if (u != v) { isself[j] = false; other = (uint32_t)old2new[u]; }
-        }
-        int extra = 0;
-        if (nb_code_has_extra(code)) {
-            int m = nb_code_abstain_member(code);
-            extra = m < a ? G.v_card[G.m_vid[mo + m]] - 1 : 0;
-        }
-        uint32_t table = 0;
-        for (int x = 0; x < 3; x++) {
-            NbFastStats st;
-            st.reset();
-            st.extra = extra;
-            for (int j = 0; j < a; j++) st.member(j, a, isself[j], isself[j] ? 0 : x);
-            int d = (int)st.value(code, 1) - (int)st.value(code, 0);
-            table |= (uint32_t)(d + 2) << (3 * x);
-        }
-        const uint32_t wid = (uint32_t)G.f_wid[f];
-        uint2 *slot = reinterpret_cast<uint2 *>(row + (size_t)(e >> 1) * 32) + (e & 1);
-        *slot = make_uint2(other, nb_pack_pair(table, wfixed[wid], wid));
+        uint32_t other;
+        const uint32_t w = nb_pair_word<WIDE>(r, pos, (uint32_t)nid, wfixed, other);
+        if (uniform) reinterpret_cast<uint32_t *>(row + (size_t)(e >> 2) * 32)[e & 3] = other;
+        else reinterpret_cast<uint2 *>(row + (size_t)(e >> 1) * 32)[e & 1] = make_uint2(other, w);
     }
 }
 
@@ -797,6 +827,7 @@ static int extract_and_upload(nb_graph *g, const nb_graph_desc *d)
 
     g->n_edges = edges.load();
     g->max_card = maxcard.load();
+    g->max_arity = maxarity.load();
     g->any_categorical = need_eq;
     g->wide = (W > (int64_t)NB_COMPACT_MAX_WID + 1) || (maxarity.load() > NB_COMPACT_MAX_ARITY);
     if (unknown.load() >= 0) {
@@ -924,8 +955,10 @@ static int color_graph(nb_graph *g, const nb_graph_desc *d)
     NB_TRY(run_jp(g, 0, 0, &done));
     int nc_hash = 0;
     NB_TRY(count_colors(g, &nc_hash));
+    // (a factor with three or more members is a clique of the conflict graph: the natural order
+    // then needs as many rounds as the longest increasing-id path and gains little -- not tried)
     const int cap = nb_natural_round_cap();
-    if (nc_hash > 2 && cap > 0) {
+    if (nc_hash > 2 && cap > 0 && g->max_arity <= 2) {
         int32_t *d_saved;
         NB_CUDA(cudaMalloc(&d_saved, (size_t)std::max<int64_t>(V, 1) * 4));
         cudaMemcpyAsync(d_saved, g->d_color, (size_t)V * 4, cudaMemcpyDeviceToDevice, g->stream);
@@ -1237,26 +1270,51 @@ int nb_build_finalize(nb_graph *g)
         NB_CUDA(cudaStreamSynchronize(g->stream));
         NB_TRY(nb_alloc(g, &g->d_tt, (size_t)g->n_tt_quads + 1, false));
         NB_TRY(nb_alloc(g, &g->d_tt_base, (size_t)g->n_tt_quads + 1, false));
+        NB_TRY(nb_alloc(g, &g->d_tt_wid, (size_t)g->n_tt_quads + 1, false));
         if (g->n_tt_quads) {
-            k_tt_pad<<<grid_for(g->n_tt_quads), 256, 0, g->stream>>>(g->d_tt, g->d_tt_base, g->n_tt_quads);
-            k_fill_tt<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_tt_ptr, g->d_tt, g->d_tt_base,
-                                                          g->d_wfixed);
+            k_tt_pad<<<grid_for(g->n_tt_quads), 256, 0, g->stream>>>(g->d_tt, g->d_tt_base, g->d_tt_wid, g->n_tt_quads);
+            if (g->wide)
+                k_fill_tt<true><<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_slice_ptr, g->d_twords, g->d_tt_ptr,
+                                                                    g->d_tt, g->d_tt_base, g->d_tt_wid, g->d_wfixed, g->d_weight);
+            else
+                k_fill_tt<false><<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->d_slice_ptr, g->d_twords, g->d_tt_ptr,
+                                                                     g->d_tt, g->d_tt_base, g->d_tt_wid, g->d_wfixed, g->d_weight);
         }
+        g->tt_weights_version = g->weights_version;
     }
     // ---- pair stream (PAIR rows = new ids [0, n_prows)) ----
     {
         const int64_t nps = g->n_prows / 32;
         int64_t *d_q;
+        uint32_t *d_row_word;
+        const char *env = getenv("NUMBSKULL_B200_UNIFORM_SLICES");
+        const int uniform_ok = (env && atoi(env) == 0) ? 0 : 1;
         NB_TRY(nb_alloc(g, &d_q, (size_t)nps + 1));
         NB_TRY(nb_alloc(g, &g->d_tt2_ptr, (size_t)nps + 1));
-        if (nps) k_tt2_slice_width<<<grid_for(nps), 256, 0, g->stream>>>(nps, g->d_new2old, d_ninc, d_q);
+        NB_TRY(nb_alloc(g, &g->d_tt2_common, (size_t)nps + 1, false));
+        NB_TRY(nb_alloc(g, &d_row_word, (size_t)g->n_prows + 1, false));
+        if (nps) {
+            if (g->wide)
+                k_tt2_row_word<true><<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_slice_ptr, g->d_twords,
+                                                                         g->d_wfixed, d_row_word);
+            else
+                k_tt2_row_word<false><<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_slice_ptr, g->d_twords,
+                                                                          g->d_wfixed, d_row_word);
+            k_tt2_slice_width<<<grid_for(nps), 256, 0, g->stream>>>(nps, g->d_new2old, d_ninc, d_row_word, uniform_ok, d_q,
+                                                                    g->d_tt2_common);
+        }
         NB_TRY(exclusive_scan(g, d_q, g->d_tt2_ptr, nps + 1));
         NB_CUDA(cudaMemcpyAsync(&g->n_tt2_quads, g->d_tt2_ptr + nps, 8, cudaMemcpyDeviceToHost, g->stream));
         NB_CUDA(cudaStreamSynchronize(g->stream));
         NB_TRY(nb_alloc(g, &g->d_tt2, (size_t)g->n_tt2_quads + 1, false));
         if (g->n_tt2_quads) {
-            k_tt2_pad<<<grid_for(g->n_tt2_quads), 256, 0, g->stream>>>(g->d_tt2, g->n_tt2_quads);
-            k_fill_tt2<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_tt2_ptr, g->d_tt2, g->d_wfixed);
+            k_tt2_pad<<<(unsigned)nps, 128, 0, g->stream>>>(g->d_tt2, g->d_tt2_ptr, g->d_tt2_common, nps);
+            if (g->wide)
+                k_fill_tt2<true><<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_slice_ptr, g->d_twords,
+                                                                     g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, g->d_wfixed);
+            else
+                k_fill_tt2<false><<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_prows, g->d_slice_ptr, g->d_twords,
+                                                                      g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, g->d_wfixed);
         }
     }
     // ---- categorical records (CAT rows = new ids [n_frows, n_crows)) ----

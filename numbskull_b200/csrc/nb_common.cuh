@@ -202,10 +202,13 @@ struct nb_graph {
     int unknown_func_id = 0;
     bool any_categorical = false;
     int max_card = 2;
+    int max_arity = 0;
     int64_t jp_rounds = 0;
     int64_t device_bytes = 0;
     int64_t launches = 0;
     uint64_t epoch_counter = 0;
+    int64_t tally_bound = 0;          // no tally exceeds this: tallying sweeps since the last reset (or max of nb_set_counts)
+    uint64_t last_tally_epoch = ~0ull;
     int warp_row_words = 1024;
     int sigma_shift = 12;
 
@@ -260,6 +263,7 @@ struct nb_graph {
     int64_t n_prows = 0;             // PAIR rows occupy new ids [0, n_prows)
     int64_t *d_tt2_ptr = nullptr;    // [n_prows/32 + 1] quad offsets into d_tt2
     uint4 *d_tt2 = nullptr;          // pair stream: two 8-byte incidences {other, table:9 fixed:1 wid:22} per quad
+    uint32_t *d_tt2_common = nullptr; // [n_prows/32] hoisted second word of a uniform slice (4 ids per quad), or NB_PAIR_NONE
     int64_t n_tt2_quads = 0;
     int32_t *d_count_b = nullptr;    // [Vn] tallies of the truth-table kernels (Boolean rows), indexed by new id
     int64_t n_frows = 0;             // PAIR + FAST rows occupy new ids [0, n_frows)
@@ -270,6 +274,9 @@ struct nb_graph {
     int64_t *d_tt_ptr = nullptr;     // [n_frows/32 + 1] quad offsets into d_tt
     uint4 *d_tt = nullptr;           // truth-table stream of the FAST rows (SELL-32, one quad per incidence)
     uint32_t *d_tt_base = nullptr;   // f(self = 0) tables, one word per quad (learning only)
+    uint32_t *d_tt_wid = nullptr;    // weight id of every quad (learning + weight refresh; the quads inline the VALUE)
+    uint64_t weights_version = 1;    // bumped whenever d_weight changes (nb_set_weights, learning)
+    uint64_t tt_weights_version = 0; // version of the weights inlined in d_tt
     int64_t n_tt_quads = 0;
     int64_t *d_wrow_ptr = nullptr;   // [n_wrows + 1] word offsets into d_wwords
     uint32_t *d_wwords = nullptr;    // contiguous warp-path rows
@@ -342,6 +349,7 @@ int nb_build_color_restart(nb_graph *g, int mode);
 int nb_natural_round_cap(void);
 void nb_release_color_scratch(nb_graph *g);
 int nb_build_finalize(nb_graph *g);
+int nb_refresh_inlined_weights(nb_graph *g);   // d_tt quads carry fp32 weight values: re-inline after a weight change
 int nb_build_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids);
 int nb_build_relabel_colors(nb_graph *g, const int32_t *map, int n);
 int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step, int regularization, double reg_param,
@@ -356,3 +364,5 @@ int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, 
                  int64_t batch_visits);
 int nb_run_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
                       const int64_t *out_offsets, double *out, int64_t n_out);
+int nb_run_potentials_records(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
+                              const int64_t *out_offsets, double *out, int64_t n_out, int32_t *row_class);

@@ -143,15 +143,30 @@ __device__ __forceinline__ double nb_read_feature(const NbRow &r, const NbHdr &h
 // value it is forced to; everything else is read from `vals`.  Loops run to the
 // end instead of returning early so the member gathers are independent loads.
 // ---------------------------------------------------------------------------
+// Where member values come from.  The sweeps read the chain's value array; the table builders
+// (nb_build.cu) force the values of the (at most two) other members of an incidence, so that the
+// truth tables of the record streams are tabulated by THIS evaluator and nothing else.
+struct NbValsGlobal {
+    const nb_val_t *__restrict__ v;
+    __device__ __forceinline__ int operator()(uint32_t vid) const { return (int)v[vid]; }
+};
+struct NbValsForced {
+    uint32_t ida, idb;
+    int xa, xb;
+    __device__ __forceinline__ int operator()(uint32_t vid) const { return vid == ida ? xa : (vid == idb ? xb : 0); }
+};
+
+template <class Vals>
 __device__ __forceinline__ int nb_member(const NbRow &r, int mpos, int step, int j, uint32_t self,
-                                         int k, const nb_val_t *__restrict__ vals)
+                                         int k, const Vals &vals)
 {
     uint32_t vid = r.w(mpos + j * step);
-    return vid == self ? k : (int)vals[vid];
+    return vid == self ? k : vals(vid);
 }
 
-__device__ inline double nb_eval_incidence(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
-                                           int k, const nb_val_t *__restrict__ vals)
+template <class Vals>
+__device__ inline double nb_eval_incidence_v(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
+                                             int k, const Vals &vals)
 {
     const int a = h.arity;
     const int step = nb_code_has_eq(h.code) ? 2 : 1;
@@ -204,7 +219,7 @@ __device__ inline double nb_eval_incidence(const NbRow &r, const NbHdr &h, int m
         }
         uint32_t last = r.w(mpos + (a - 1) * step);
         uint32_t alias = r.w(mpos + a * step);
-        int head = last == self ? k : (alias == 0xFFFFFFFFu ? 0 : (int)vals[alias]);
+        int head = last == self ? k : (alias == 0xFFFFFFFFu ? 0 : vals(alias));
         if (h.code == C_IMPLY_MLN) return !body ? 1.0 : (head ? 1.0 : 0.0);
         bool hit = head == (int)r.w(mpos + (a - 1) * step + 1);
         if (h.code == C_IMPLY_NATURAL_CAT) return !body ? 0.0 : (hit ? 1.0 : -1.0);
@@ -269,6 +284,12 @@ __device__ inline double nb_eval_incidence(const NbRow &r, const NbHdr &h, int m
     default:
         return 0.0;
     }
+}
+
+__device__ __forceinline__ double nb_eval_incidence(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
+                                                    int k, const nb_val_t *__restrict__ vals)
+{
+    return nb_eval_incidence_v(r, h, mpos, self, k, NbValsGlobal{vals});
 }
 
 // position of the first member word of the incidence whose header is at `pos`
@@ -455,92 +476,19 @@ __host__ __device__ inline uint32_t nb_fold_key(uint64_t seed, uint64_t epoch, u
 }
 
 // ---------------------------------------------------------------------------
-// Running statistics over the members of one incidence from which f(k = 0) and
-// f(k = 1) of every Boolean / data-programming function follow.  Used at build
-// time to tabulate the functions for the truth-table (TT) stream.
-// ---------------------------------------------------------------------------
-struct NbFastStats {
-    int any0, any1, alleq, first, cnt0, cnt1, nself, selfbody, lastself, lastval;
-    int m0, m1, m2, s0, s1, s2, extra;
-    __device__ __forceinline__ void reset()
-    {
-        any0 = any1 = 0; alleq = 1; first = -1; cnt0 = cnt1 = 0; nself = selfbody = 0; lastself = 0; lastval = 0;
-        m0 = m1 = m2 = 0; s0 = s1 = s2 = 0; extra = 0;
-    }
-    __device__ __forceinline__ void member(int j, int arity, bool isself, int x)
-    {
-        const bool last = j == arity - 1;
-        if (isself) {
-            nself++;
-            if (!last) selfbody++;
-        } else {
-            any0 |= x == 0;
-            any1 |= x == 1;
-            if (first < 0) first = x; else alleq &= x == first;
-            if (!last) { cnt0 += x == 0; cnt1 += x == 1; }
-        }
-        if (last) { lastself = isself; lastval = x; }
-        if (j == 0) { m0 = x; s0 = isself; }
-        else if (j == 1) { m1 = x; s1 = isself; }
-        else if (j == 2) { m2 = x; s2 = isself; }
-    }
-    // factor value with the variable forced to k (k in {0, 1})
-    __device__ __forceinline__ double value(int code, int k) const
-    {
-        switch (code) {
-        case C_IMPLY_NATURAL: return (!any0 && (nself == 0 || k != 0)) ? 1.0 : 0.0;
-        case C_OR: return (any1 || (nself > 0 && k == 1)) ? 1.0 : -1.0;
-        case C_AND:
-        case C_ISTRUE: return (!any0 && (nself == 0 || k != 0)) ? 1.0 : -1.0;
-        case C_EQUAL:
-            if (first < 0) return 1.0;
-            if (!alleq) return -1.0;
-            return (nself == 0 || k == first) ? 1.0 : -1.0;
-        case C_LINEAR:
-        case C_RATIO:
-        case C_LOGICAL: {
-            int head = lastself ? k : lastval;
-            int cnt = (head == 0 ? cnt0 : (head == 1 ? cnt1 : 0)) + (head == k ? selfbody : 0);
-            if (code == C_LINEAR) return (double)cnt;
-            if (code == C_RATIO) return log((double)(1 + cnt));
-            return cnt > 0 ? 1.0 : 0.0;
-        }
-        case C_DP_CLASS_PRIOR: return (s0 ? k : m0) == 1 ? 1.0 : -1.0;
-        case C_DP_LF_PRIOR: { int l = s0 ? k : m0; return l == 2 ? -1.0 : (l == 0 ? 0.0 : 1.0); }
-        case C_DP_LF_PROPENSITY: return (s0 ? k : m0) == extra ? 0.0 : 1.0;
-        case C_DP_LF_ACCURACY:
-        case C_DP_LF_CLASS_PROPENSITY: {
-            int y = s0 ? k : m0, l = s1 ? k : m1;
-            if (l == extra) return 0.0;
-            if (code == C_DP_LF_ACCURACY) return y == l ? 1.0 : -1.0;
-            return y == 1 ? 1.0 : -1.0;
-        }
-        case C_DP_DEP_FIXING:
-        case C_DP_DEP_REINFORCING: {
-            int y = s0 ? k : m0, l1 = s1 ? k : m1, l2 = s2 ? k : m2;
-            if (l1 == extra) return l2 != 1 ? -1.0 : 0.0;
-            if (code == C_DP_DEP_FIXING)
-                return ((l1 == 0 && l2 == 1 && y == 1) || (l1 == 1 && l2 == 0 && y == 0)) ? 1.0 : 0.0;
-            return ((l1 == 0 && l2 == 0 && y == 0) || (l1 == 1 && l2 == 1 && y == 1)) ? 1.0 : 0.0;
-        }
-        case C_DP_DEP_EXCLUSIVE: { int l1 = s0 ? k : m0, l2 = s1 ? k : m1; return (l1 == extra || l2 == extra) ? 0.0 : -1.0; }
-        case C_DP_DEP_SIMILAR: return (s0 ? k : m0) == (s1 ? k : m1) ? 1.0 : 0.0;
-        default: return 0.0;  // C_NOOP
-        }
-    }
-};
-
-
-// ---------------------------------------------------------------------------
 // Truth-table (TT) stream of the FAST row class.  A FAST row belongs to a
 // Boolean variable whose incidences all have arity <= 3 and an integer-valued
 // function; each incidence is ONE 16-byte quad
-//     { other member A (new id), other member B (new id), table, weight id }
+//     { other member A (new id), other member B (new id), table, weight (fp32 bits) }
 // where table holds, for the 3 x 3 combinations of (min(xA, 2), min(xB, 2)),
 // the 3-bit code of f(self = 1) - f(self = 0) + 2 at bit 3 * (3 * a + b); bit 27
 // = weight is fixed / padding.  Unused member slots point at the variable itself, padding
 // quads carry the all-zero-difference table, so every lane of a warp runs the
-// same trip count with no parsing at all.
+// same trip count with no parsing at all.  The weight VALUE is inlined (a random
+// gather of weight[wid] per incidence costs a full 32-sector request per warp
+// and was half of the L1/L2 traffic of the sweep on the KBC shape); the weight
+// ids live in a parallel word per quad (tt_wid) that only the learning sweep and
+// the refresh kernel (nb_sweep.cu k_tt_refresh) read.
 // ---------------------------------------------------------------------------
 #define NB_TT_NEUTRAL 0x2492492u   /* 9 x code 2 (difference 0) */
 #define NB_TT_FIXED_BIT (1u << 27) /* weight is fixed (also set on padding quads): no gradient */
@@ -558,14 +506,120 @@ __host__ __device__ inline bool nb_code_tt_ok(int c)
            (c >= C_DP_CLASS_PRIOR && c <= C_DP_DEP_SIMILAR);
 }
 
+__device__ __forceinline__ int nb_tt_index(int xa, int xb) { return min(xa, 2) * 3 + min(xb, 2); }
+__device__ __forceinline__ int nb_tt_diff(uint32_t table, int idx) { return (int)((table >> (3 * idx)) & 7u) - 2; }
+
+// Tabulate the incidence whose header sits at `pos` of the generic row `r` of variable `self`
+// (dataType 0, cardinality 2, arity <= 3) with nb_eval_incidence_v -- the one evaluator.  The
+// (at most two) members other than `self` are returned in other[] (unused slots = self).
+template <bool WIDE>
+__device__ inline NbHdr nb_tabulate(const NbRow &r, int pos, uint32_t self, uint32_t other[2], uint32_t &table,
+                                    uint32_t &base)
+{
+    const NbHdr h = nb_read_hdr<WIDE>(r, pos);
+    const int mpos = pos + nb_hdr_words<WIDE>();
+    int n_other = 0;
+    other[0] = other[1] = self;
+    for (int j = 0; j < h.arity && j < 3; j++) {
+        const uint32_t u = r.w(mpos + j);
+        if (u != self && n_other < 2) other[n_other++] = u;
+    }
+    table = 0u;
+    base = 0u;
+    for (int xa = 0; xa < 3; xa++)
+        for (int xb = 0; xb < 3; xb++) {
+            const NbValsForced vals{other[0], other[1], xa, xb};
+            const int f0 = (int)nb_eval_incidence_v(r, h, mpos, self, 0, vals);
+            const int f1 = (int)nb_eval_incidence_v(r, h, mpos, self, 1, vals);
+            table |= (uint32_t)(f1 - f0 + 2) << (3 * (3 * xa + xb));
+            base |= (uint32_t)(f0 + 1) << (2 * (3 * xa + xb));
+        }
+    return h;
+}
+
+// e1 - e0 of a FAST row from its quads (lane-strided SELL layout: quad j at qp[j * 32]).
+#define NB_TT_UNROLL_DEFAULT 4
+template <int NB_TT_UNROLL = NB_TT_UNROLL_DEFAULT>
+__device__ __forceinline__ double nb_tt_delta(const uint4 *__restrict__ qp, int n, uint32_t self,
+                                              const nb_val_t *__restrict__ vals)
+{
+    double d = 0.0;
+    for (int j = 0; j < n; j += NB_TT_UNROLL) {
+        uint4 q[NB_TT_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT_UNROLL; t++)
+            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4(self, self, NB_TT_NEUTRAL, 0u);
+        int xa[NB_TT_UNROLL], xb[NB_TT_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT_UNROLL; t++) {
+            xa[t] = (int)vals[q[t].x];
+            xb[t] = (int)vals[q[t].y];
+        }
+#pragma unroll
+        for (int t = 0; t < NB_TT_UNROLL; t++)
+            d = fma((double)__uint_as_float(q[t].w), (double)nb_tt_diff(q[t].z, nb_tt_index(xa[t], xb[t])), d);
+    }
+    return d;
+}
+
 // Pair records (NB_CLASS_PAIR): incidences with at most ONE other member take 8 bytes,
 //     { other member (new id, or the variable itself), table:9 | fixed:1 | wid:22 }
 // table = 3-bit code of f(1) - f(0) + 2 for min(x_other, 2) in {0, 1, 2}; two records per quad.
+// UNIFORM slices: when every record of the 32 rows of a slice carries the same second word
+// (every tied-weight MRF: the Ising grid has ONE (table, weight) pair), the word is hoisted into
+// tt2_common[slice] and the slice stores bare 4-byte member ids, four per quad
+// (NB_PAIR_NONE = no record).
 #define NB_PAIR_NEUTRAL 0x92u          /* 3 x code 2 */
 #define NB_PAIR_FIXED_BIT (1u << 9)
+#define NB_PAIR_NONE 0xFFFFFFFFu       /* tt2_common: slice is not uniform; member id: empty record */
+#define NB_PAIR_ANY 0xFFFFFFFEu        /* build only: a row without records fits any common word */
 __host__ __device__ inline uint32_t nb_pack_pair(uint32_t table9, int fixed, uint32_t wid)
 {
     return table9 | ((uint32_t)fixed << 9) | (wid << 10);
+}
+
+#define NB_TT2_UNROLL 2
+__device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int n, uint32_t common, uint32_t self,
+                                               const nb_val_t *__restrict__ vals, const double *__restrict__ weight)
+{
+    if (common != NB_PAIR_NONE) {
+        const double w = __ldg(weight + (common >> 10));
+        int acc = 0;
+        for (int j = 0; j < n; j++) {
+            const uint4 q = __ldg(qp + (size_t)j * 32);
+            const uint32_t o[4] = {q.x, q.y, q.z, q.w};
+            int x[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) x[t] = (int)vals[o[t] == NB_PAIR_NONE ? self : o[t]];
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                acc += o[t] == NB_PAIR_NONE ? 0 : (int)((common >> (3 * min(x[t], 2))) & 7u) - 2;
+        }
+        return w * (double)acc;
+    }
+    const uint32_t neutral = nb_pack_pair(NB_PAIR_NEUTRAL, 1, 0u);
+    double d = 0.0;
+    for (int j = 0; j < n; j += NB_TT2_UNROLL) {
+        uint4 q[NB_TT2_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT2_UNROLL; t++)
+            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4(self, neutral, self, neutral);
+        int x0[NB_TT2_UNROLL], x1[NB_TT2_UNROLL];
+        double w0[NB_TT2_UNROLL], w1[NB_TT2_UNROLL];
+#pragma unroll
+        for (int t = 0; t < NB_TT2_UNROLL; t++) {
+            x0[t] = (int)vals[q[t].x];
+            x1[t] = (int)vals[q[t].z];
+            w0[t] = __ldg(weight + (q[t].y >> 10));
+            w1[t] = __ldg(weight + (q[t].w >> 10));
+        }
+#pragma unroll
+        for (int t = 0; t < NB_TT2_UNROLL; t++) {
+            d = fma(w0[t], (double)((int)((q[t].y >> (3 * min(x0[t], 2))) & 7u) - 2), d);
+            d = fma(w1[t], (double)((int)((q[t].w >> (3 * min(x1[t], 2))) & 7u) - 2), d);
+        }
+    }
+    return d;
 }
 
 // Categorical records (NB_CLASS_CAT): one quad per incidence of an AND_CAT / EQUAL_CAT_CONST factor
@@ -577,4 +631,33 @@ __host__ __device__ inline uint32_t nb_pack_pair(uint32_t table9, int fixed, uin
 __host__ __device__ inline uint32_t nb_pack_cat(int k, int eq_a, int eq_b, int n_others, int fixed)
 {
     return (uint32_t)k | ((uint32_t)eq_a << 8) | ((uint32_t)eq_b << 16) | ((uint32_t)n_others << 24) | ((uint32_t)fixed << 26);
+}
+
+// Per-value energies of a CAT row: acc.add(k, w) for every satisfied incidence of bucket k.
+template <class Acc>
+__device__ __forceinline__ void nb_cat_energies(const uint4 *__restrict__ qp, int n, uint32_t self,
+                                                const nb_val_t *__restrict__ vals,
+                                                const double *__restrict__ weight, Acc &acc)
+{
+    for (int j = 0; j < n; j += 2) {
+        uint4 q[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4(self, self, nb_pack_cat(0, 0, 0, 3, 1), 0u);
+        int xa[2], xb[2];
+        float w[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            xa[t] = (int)vals[q[t].x];
+            xb[t] = (int)vals[q[t].y];
+            w[t] = (float)__ldg(weight + q[t].w);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const uint32_t m = q[t].z;
+            const int no = (int)((m >> 24) & 3u);
+            const bool sat = no < 3 && (no < 1 || xa[t] == (int)((m >> 8) & 0xFFu)) && (no < 2 || xb[t] == (int)((m >> 16) & 0xFFu));
+            if (sat) acc.add((int)(m & 0xFFu), w[t]);
+        }
+    }
 }

@@ -512,3 +512,91 @@ extern "C" int nb_load_factors(const uint8_t *data, int64_t n_bytes, int64_t n_f
     }
     return NB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Benchmark input generator (BASELINE config 4): the KBC-style Boolean graph
+// of numbskull_b200/synth.py kbc(), filled by host threads straight into the reference's packed
+// record arrays.  Counter-based randomness (splitmix64 of (seed, stream, index)): the graph does
+// not depend on the thread count.  Not part of the hot path: it only feeds it (the role
+// ising/ising.cpp plays for the reference).
+// ---------------------------------------------------------------------------
+static inline uint64_t sm64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline uint64_t rnd(uint64_t seed, uint64_t stream, uint64_t i) { return sm64(sm64(seed ^ (stream * 0xD1342543DE82EF95ull)) + i); }
+static inline double unit(uint64_t r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
+
+extern "C" int nb_synth_kbc(int64_t nvar, uint64_t seed, int64_t n_weights, double evidence_frac, int64_t window,
+                            double far_frac, double hub_frac, double fixed_frac, const double *mix3,
+                            nb_weight_rec *weight, nb_variable_rec *variable, nb_factor_rec *factor, int64_t n_factor,
+                            nb_ftv_rec *fmap, int64_t n_fmap)
+{
+    const int64_t n_imp = (int64_t)(nvar * mix3[0]), n_and = (int64_t)(nvar * mix3[1]), n_or = (int64_t)(nvar * mix3[2]);
+    if (n_factor != nvar + n_imp + n_and + n_or || n_fmap != nvar + 3 * n_imp + 2 * n_and + 3 * n_or)
+        NB_FAIL(NB_ERR_INVALID, "nb_synth_kbc: array sizes do not match the mix");
+    const int64_t nhub = std::max<int64_t>(1, (int64_t)(nvar * 1e-5));
+    const double p_geo = 1.0 / std::max(2.0, (double)window / 8.0), log1mp = std::log1p(-p_geo);
+    host_threads(n_weights, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            weight[i].isFixed = unit(rnd(seed, 1, (uint64_t)i)) < fixed_frac;
+            // N(0, 0.5) by Box-Muller
+            const double u1 = std::max(unit(rnd(seed, 2, (uint64_t)i)), 1e-300), u2 = unit(rnd(seed, 3, (uint64_t)i));
+            weight[i].initialValue = 0.5 * std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+        }
+    });
+    host_threads(nvar, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            nb_variable_rec &v = variable[i];
+            const bool ev = unit(rnd(seed, 4, (uint64_t)i)) < evidence_frac;
+            v.isEvidence = ev ? 1 : 0;
+            v.initialValue = ev ? (int64_t)(rnd(seed, 5, (uint64_t)i) & 1u) : 0;
+            v.dataType = 0;
+            v.cardinality = 2;
+            v.vtf_offset = 0;
+        }
+    });
+    // factor f: [0, nvar) ISTRUE(v = f); then IMPLY_NATURAL arity 3, AND arity 2, OR arity 3
+    host_threads(n_factor, [&](int64_t a, int64_t b) {
+        for (int64_t f = a; f < b; f++) {
+            int func, arity;
+            int64_t off;
+            if (f < nvar) { func = 4; arity = 1; off = f; }
+            else if (f < nvar + n_imp) { func = 0; arity = 3; off = nvar + 3 * (f - nvar); }
+            else if (f < nvar + n_imp + n_and) { func = 2; arity = 2; off = nvar + 3 * n_imp + 2 * (f - nvar - n_imp); }
+            else { func = 1; arity = 3; off = nvar + 3 * n_imp + 2 * n_and + 3 * (f - nvar - n_imp - n_and); }
+            nb_factor_rec &r = factor[f];
+            r.factorFunction = (int16_t)func;
+            r.weightId = (int64_t)((((uint64_t)f * 0x9E3779B97F4A7C15ull) >> 40) % (uint64_t)n_weights);
+            r.featureValue = 1.0;
+            r.arity = arity;
+            r.ftv_offset = off;
+            if (f < nvar) { fmap[off].vid = f; fmap[off].dense_equal_to = 0; continue; }
+            const int64_t anchor = (int64_t)(rnd(seed, 6, (uint64_t)f) % (uint64_t)nvar);
+            fmap[off].vid = anchor;
+            fmap[off].dense_equal_to = 0;
+            for (int j = 1; j < arity; j++) {
+                const uint64_t k = (uint64_t)f * 4 + (uint64_t)j;
+                int64_t m;
+                if (unit(rnd(seed, 7, k)) < hub_frac) {                 // Zipf-like hub: P(rank >= x) = x^-1/2... x^-(a-1), a = 1.5
+                    const double u = std::max(unit(rnd(seed, 8, k)), 1e-12);
+                    const int64_t rank = std::min<int64_t>(nhub - 1, (int64_t)(1.0 / (u * u)) - 1);
+                    m = (int64_t)(rnd(seed, 9, (uint64_t)rank) % (uint64_t)nvar);
+                } else if (unit(rnd(seed, 10, k)) < far_frac) {
+                    m = (int64_t)(rnd(seed, 11, k) % (uint64_t)nvar);
+                } else {
+                    const double u = std::max(unit(rnd(seed, 12, k)), 1e-300);
+                    int64_t d = std::min<int64_t>(window, 1 + (int64_t)(std::log(u) / log1mp));   // geometric, capped
+                    if (rnd(seed, 13, k) & 1u) d = -d;
+                    m = ((anchor + d) % nvar + nvar) % nvar;
+                }
+                fmap[off + j].vid = m;
+                fmap[off + j].dense_equal_to = 0;
+            }
+        }
+    });
+    return NB_OK;
+}

@@ -47,6 +47,7 @@ struct LearnArgs {
     const int64_t *tt_ptr;
     const uint4 *tt;
     const uint32_t *tt_base;
+    const uint32_t *tt_wid;   // weight id per quad (the quads themselves inline the weight VALUE for the Gibbs sweep)
     int32_t *gi_grad;     // [W] global integer table (large-W path)
 };
 
@@ -332,7 +333,6 @@ struct GradSinkI {
     }
 };
 
-__device__ __forceinline__ int nb_tt_index(int xa, int xb) { return min(xa, 2) * 3 + min(xb, 2); }
 
 template <bool SMEM>
 __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int beg, int end, uint32_t kfree,
@@ -364,22 +364,27 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
         const int n = (int)((a.tt_ptr[s + 1] - q0) >> 5);
         const uint4 *qp = a.tt + q0 + lane;
         const uint32_t *bp = a.tt_base + q0 + lane;
+        const uint32_t *wp = a.tt_wid + q0 + lane;
 
-        // ---- pass 1: e1 - e0 under both chains ----
+        // ---- pass 1: e1 - e0 under both chains (current weights: gathered by id, the inlined
+        //      values are only refreshed for the Gibbs sweep) ----
         double dF = 0.0, dE = 0.0;
         for (int j = 0; j < n; j += 2) {
             uint4 q[2];
+            uint32_t wid[2];
 #pragma unroll
-            for (int t = 0; t < 2; t++)
+            for (int t = 0; t < 2; t++) {
                 q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32)
                                    : make_uint4((uint32_t)nid, (uint32_t)nid, NB_TT_NEUTRAL | NB_TT_FIXED_BIT, 0u);
+                wid[t] = (j + t < n) ? __ldg(wp + (size_t)(j + t) * 32) : 0u;
+            }
             int xf[2][2], xe[2][2];
             double w[2];
 #pragma unroll
             for (int t = 0; t < 2; t++) {
                 xf[t][0] = vF[q[t].x]; xf[t][1] = vF[q[t].y];
                 xe[t][0] = vE[q[t].x]; xe[t][1] = vE[q[t].y];
-                w[t] = __ldg(weight + q[t].w);
+                w[t] = weight[wid[t]];
             }
 #pragma unroll
             for (int t = 0; t < 2; t++) {
@@ -409,6 +414,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
         for (int j = 0; j < n; j++) {
             const uint4 q = __ldg(qp + (size_t)j * 32);
             const uint32_t b = __ldg(bp + (size_t)j * 32);
+            const uint32_t wid = __ldg(wp + (size_t)j * 32);
             const int iF = nb_tt_index(vF[q.x], vF[q.y]), iE = nb_tt_index(vE[q.x], vE[q.y]);
             // this variable's own slots read its just-written values; the tables ignore them
             const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * ((int)((q.z >> (3 * iF)) & 7u) - 2);
@@ -417,13 +423,13 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
             const unsigned who = __ballot_sync(FULL, contrib);
             if (who == 0u) continue;
             const int leader = __ffs(who) - 1;
-            const uint32_t w0 = __shfl_sync(FULL, q.w, leader);
-            if (__all_sync(FULL, !contrib || q.w == w0)) {
+            const uint32_t w0 = __shfl_sync(FULL, wid, leader);
+            if (__all_sync(FULL, !contrib || wid == w0)) {
                 const int G = __reduce_add_sync(FULL, contrib ? fF - fE : 0);
                 const unsigned Cn = __reduce_add_sync(FULL, contrib ? cinc : 0u);
                 if (lane == leader) sink.add(w0, G, Cn);
             } else if (contrib) {
-                sink.add(q.w, fF - fE, cinc);
+                sink.add(wid, fF - fE, cinc);
             }
         }
     }
@@ -462,10 +468,11 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, 
         const int n = (int)((a.tt_ptr[s + 1] - q0) >> 5);
         const uint4 *qp = a.tt + q0 + (nid & 31);
         const uint32_t *bp = a.tt_base + q0 + (nid & 31);
+        const uint32_t *wp = a.tt_wid + q0 + (nid & 31);
         double dF = 0.0, dE = 0.0;
         for (int j = lane; j < n; j += 32) {
             const uint4 q = __ldg(qp + (size_t)j * 32);
-            const double w = __ldg(weight + q.w);
+            const double w = weight[__ldg(wp + (size_t)j * 32)];
             dF = fma(w, (double)((int)((q.z >> (3 * nb_tt_index(vF[q.x], vF[q.y]))) & 7u) - 2), dF);
             dE = fma(w, (double)((int)((q.z >> (3 * nb_tt_index(vE[q.x], vE[q.y]))) & 7u) - 2), dE);
         }
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, 
             const int iF = nb_tt_index(vF[q.x], vF[q.y]), iE = nb_tt_index(vE[q.x], vE[q.y]);
             const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * ((int)((q.z >> (3 * iF)) & 7u) - 2);
             const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * ((int)((q.z >> (3 * iE)) & 7u) - 2);
-            sink.add(q.w, fF - fE, cinc);
+            sink.add(__ldg(wp + (size_t)j * 32), fF - fE, cinc);
         }
     }
     if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt, 1.0);
@@ -584,7 +591,7 @@ static LearnArgs learn_args(nb_graph *g)
     a.rng_id = g->d_rng_id; a.vinit = g->d_vinit; a.val_free = g->d_val[0]; a.val_evid = g->d_val[1];
     a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
     a.g_grad = g->d_grad; a.g_cnt = g->d_nvis; a.p_grad = g->d_gpart; a.p_cnt = g->d_npart; a.done = g->d_done;
-    a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.gi_grad = g->d_gradi;
+    a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.tt_wid = g->d_tt_wid; a.gi_grad = g->d_gradi;
     return a;
 }
 
@@ -766,6 +773,7 @@ int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step,
     a.seed = seed; a.reg_param = reg_param; a.truncation = truncation; a.regularization = regularization;
     a.step = step; a.epoch = epoch;
     NB_TRY(learn_block_of_color(g, a, color, block, n_blocks));
+    g->weights_version++;
     NB_CUDA(cudaGetLastError());
     return NB_OK;
 }
@@ -785,6 +793,7 @@ int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, 
         const int nb = block_count(g, vmax, default_batch_visits(step, batch_visits));
         for (int b = 0; b < nb; b++)
             for (int c = 0; c < g->n_colors; c++) NB_TRY(learn_block_of_color(g, a, c, b, nb));
+        g->weights_version++;
         NB_CUDA(cudaGetLastError());
         step *= decay;   // factorgraph.py:206
     }

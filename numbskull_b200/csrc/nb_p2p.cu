@@ -300,6 +300,7 @@ extern "C" int nb_gibbs_sweeps_p2p(nb_graph *g, int64_t n_epochs, int burnin, in
         NB_FAIL(NB_ERR_NOT_IMPLEMENTED, "Error: Factor Function %d ( used in factor %lld ) is not implemented.",
                 g->unknown_func_id, (long long)g->unknown_func_factor);
     const int nowait = mode & 3;
+    NB_TRY(nb_refresh_inlined_weights(g));   // before the streams fork
     if (mode & 2) {
         if (n_colors & 1) NB_FAIL(NB_ERR_INVALID, "split mode needs an even phase count");
         NB_TRY(sweeps_split(g, p, n_epochs, burnin, sample_evidence, seed, n_colors));
@@ -325,6 +326,17 @@ extern "C" int nb_p2p_check(nb_graph *g)
     NB_CUDA(cudaMemcpyAsync(&err, p->d_error, 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
     if (err) NB_FAIL(NB_ERR_CUDA, "peer-to-peer halo exchange timed out waiting for a neighbour rank");
+    return NB_OK;
+}
+
+// Unmap the peers' memory.  Partitioned graphs are torn down in two steps -- every rank closes its
+// mappings, the ranks synchronise, then each frees its own arrays (nb_graph_destroy) -- so that no
+// rank frees memory a peer still has mapped.
+extern "C" int nb_p2p_close(nb_graph *g)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaStreamSynchronize(g->stream));
+    nb_p2p_destroy(g);
     return NB_OK;
 }
 

@@ -88,10 +88,12 @@ __global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int 
     nb_tally(a, nid, NB_META_CARD(meta), k);
 }
 
-// FAST rows: truth-table stream, one 16-byte quad per incidence, uniform trip count per warp.
-#define NB_TT_UNROLL 4
-__global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__restrict__ tt_ptr,
-                                                  const uint4 *__restrict__ tt, int beg, int end, uint32_t key)
+// FAST rows: truth-table stream, one 16-byte quad per incidence (weight value inlined), uniform
+// trip count per warp.  The energy difference comes from nb_tt_delta (nb_eval.cuh), the same
+// function the parity hook nb_potentials_records evaluates.
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_gibbs_tt(SweepArgs a, const int64_t *__restrict__ tt_ptr,
+                                                        const uint4 *__restrict__ tt, int beg, int end, uint32_t key)
 {
     nb_wait_halo(a);
     const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -101,30 +103,7 @@ __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__
     const uint32_t rid = a.rng_id[nid];
     const int64_t q0 = tt_ptr[nid >> 5], q1 = tt_ptr[(nid >> 5) + 1];
     const int n = (int)((q1 - q0) >> 5);                      // incidences of the longest row of this slice
-    const uint4 *qp = tt + q0 + (nid & 31);
-    const nb_val_t *__restrict__ vals = a.val;
-    const double *__restrict__ weight = a.weight;
-    double d = 0.0;                                           // e1 - e0
-    for (int j = 0; j < n; j += NB_TT_UNROLL) {
-        uint4 q[NB_TT_UNROLL];
-#pragma unroll
-        for (int t = 0; t < NB_TT_UNROLL; t++)
-            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4((uint32_t)nid, (uint32_t)nid, NB_TT_NEUTRAL, 0u);
-        int xa[NB_TT_UNROLL], xb[NB_TT_UNROLL];
-        double w[NB_TT_UNROLL];
-#pragma unroll
-        for (int t = 0; t < NB_TT_UNROLL; t++) {
-            xa[t] = (int)vals[q[t].x];
-            xb[t] = (int)vals[q[t].y];
-            w[t] = __ldg(weight + q[t].w);
-        }
-#pragma unroll
-        for (int t = 0; t < NB_TT_UNROLL; t++) {
-            const int idx = min(xa[t], 2) * 3 + min(xb[t], 2);
-            const int df = (int)((q[t].z >> (3 * idx)) & 7u) - 2;
-            d = fma(w[t], (double)df, d);
-        }
-    }
+    const double d = nb_tt_delta<UNROLL>(tt + q0 + (nid & 31), n, (uint32_t)nid, a.val);   // e1 - e0
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
     if (!(evid == 0 || a.sample_evidence)) return;          // :24
@@ -136,9 +115,9 @@ __global__ void __launch_bounds__(256) k_gibbs_tt(SweepArgs a, const int64_t *__
     if (!a.burnin) a.count_b[nid] += k;                      // inference.py:30-31
 }
 
-// PAIR rows: 8-byte records, two per quad.
-#define NB_TT2_UNROLL 2
+// PAIR rows: 8-byte records, two per quad -- or, in uniform slices, bare member ids, four per quad.
 __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *__restrict__ tt2_ptr,
+                                                   const uint32_t *__restrict__ tt2_common,
                                                    const uint4 *__restrict__ tt2, int beg, int end, uint32_t key)
 {
     nb_wait_halo(a);
@@ -147,32 +126,9 @@ __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *_
     const uint32_t meta = a.vmeta[nid];
     const uint32_t rid = a.rng_id[nid];
     const int64_t q0 = tt2_ptr[nid >> 5], q1 = tt2_ptr[(nid >> 5) + 1];
+    const uint32_t common = tt2_common[nid >> 5];
     const int n = (int)((q1 - q0) >> 5);                      // quads of the longest row of this slice
-    const uint4 *qp = tt2 + q0 + (nid & 31);
-    const nb_val_t *__restrict__ vals = a.val;
-    const double *__restrict__ weight = a.weight;
-    const uint32_t neutral = nb_pack_pair(NB_PAIR_NEUTRAL, 1, 0u);
-    double d = 0.0;                                           // e1 - e0
-    for (int j = 0; j < n; j += NB_TT2_UNROLL) {
-        uint4 q[NB_TT2_UNROLL];
-#pragma unroll
-        for (int t = 0; t < NB_TT2_UNROLL; t++)
-            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4((uint32_t)nid, neutral, (uint32_t)nid, neutral);
-        int x0[NB_TT2_UNROLL], x1[NB_TT2_UNROLL];
-        double w0[NB_TT2_UNROLL], w1[NB_TT2_UNROLL];
-#pragma unroll
-        for (int t = 0; t < NB_TT2_UNROLL; t++) {
-            x0[t] = (int)vals[q[t].x];
-            x1[t] = (int)vals[q[t].z];
-            w0[t] = __ldg(weight + (q[t].y >> 10));
-            w1[t] = __ldg(weight + (q[t].w >> 10));
-        }
-#pragma unroll
-        for (int t = 0; t < NB_TT2_UNROLL; t++) {
-            d = fma(w0[t], (double)((int)((q[t].y >> (3 * min(x0[t], 2))) & 7u) - 2), d);
-            d = fma(w1[t], (double)((int)((q[t].w >> (3 * min(x1[t], 2))) & 7u) - 2), d);
-        }
-    }
+    const double d = nb_tt2_delta(tt2 + q0 + (nid & 31), n, common, (uint32_t)nid, a.val, a.weight);   // e1 - e0
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
     if (!(evid == 0 || a.sample_evidence)) return;          // :24
@@ -186,6 +142,12 @@ __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *_
 // CAT rows: categorical variable (cardinality <= 32) with AND_CAT / EQUAL_CAT_CONST factors.  One
 // quad per incidence, uniform trip count per warp; the per-value energies live in a column of
 // shared memory private to the thread (no parsing, no divergence), then one inverse-CDF draw.
+struct NbCatSmemAcc {
+    float (*e)[256];
+    int tid;
+    __device__ __forceinline__ void add(int k, float w) { e[k][tid] += w; }
+};
+
 __global__ void __launch_bounds__(256) k_gibbs_cat(SweepArgs a, const int64_t *__restrict__ cat_ptr,
                                                    const uint4 *__restrict__ cat, int64_t first_id, int beg, int end)
 {
@@ -200,33 +162,11 @@ __global__ void __launch_bounds__(256) k_gibbs_cat(SweepArgs a, const int64_t *_
     const int64_t s = (nid - first_id) >> 5;
     const int64_t q0 = cat_ptr[s], q1 = cat_ptr[s + 1];
     const int n = (int)((q1 - q0) >> 5);
-    const uint4 *qp = cat + q0 + (nid & 31);
-    const nb_val_t *__restrict__ vals = a.val;
-    const double *__restrict__ weight = a.weight;
     const int tid = threadIdx.x;
 #pragma unroll 4
     for (int k = 0; k < card; k++) s_e[k][tid] = 0.0f;
-    for (int j = 0; j < n; j += 2) {
-        uint4 q[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++)
-            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4((uint32_t)nid, (uint32_t)nid, nb_pack_cat(0, 0, 0, 3, 1), 0u);
-        int xa[2], xb[2];
-        float w[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            xa[t] = (int)vals[q[t].x];
-            xb[t] = (int)vals[q[t].y];
-            w[t] = (float)__ldg(weight + q[t].w);
-        }
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            const uint32_t m = q[t].z;
-            const int no = (int)((m >> 24) & 3u);
-            const bool sat = no < 3 && (no < 1 || xa[t] == (int)((m >> 8) & 0xFFu)) && (no < 2 || xb[t] == (int)((m >> 16) & 0xFFu));
-            if (sat) s_e[m & 0xFFu][tid] += w[t];
-        }
-    }
+    NbCatSmemAcc acc{s_e, tid};
+    nb_cat_energies(cat + q0 + (nid & 31), n, (uint32_t)nid, a.val, a.weight, acc);
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
     if (!(evid == 0 || a.sample_evidence)) return;          // :24
@@ -236,11 +176,11 @@ __global__ void __launch_bounds__(256) k_gibbs_cat(SweepArgs a, const int64_t *_
     float tot = 0.0f;
     for (int k = 0; k < card; k++) { float z = __expf(s_e[k][tid] - mx); s_e[k][tid] = z; tot += z; }
     const float t = (float)nb_philox2x32_u53(rid, (uint32_t)a.epoch, nb_fold_key(a.seed, a.epoch, NB_TAG_FREE)) * tot;
-    float acc = 0.0f;
+    float acc_z = 0.0f;
     int pick = card - 1;
     for (int k = 0; k < card; k++) {
-        acc += s_e[k][tid];
-        if (acc >= t) { pick = k; break; }
+        acc_z += s_e[k][tid];
+        if (acc_z >= t) { pick = k; break; }
     }
     a.val[nid] = (nb_val_t)pick;
     if (!a.burnin) {
@@ -382,17 +322,26 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     if (color < 0) NB_FAIL(NB_ERR_INVALID, "negative colour %d", color);
     if (color >= g->n_colors) return NB_OK;   // partitioned graphs: a colour this rank does not own
     const NbColorRange &c = g->colors[(size_t)color];
+    if (!burnin && epoch != g->last_tally_epoch) { g->tally_bound++; g->last_tally_epoch = epoch; }
     SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
+    if (c.f_end > c.f_beg) NB_TRY(nb_refresh_inlined_weights(g));
     if (c.p_end > c.p_beg) {
         unsigned grid = (unsigned)((c.p_end - c.p_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        k_gibbs_tt2<<<grid, 256, 0, g->stream>>>(a, g->d_tt2_ptr, g->d_tt2, c.p_beg, c.p_end, key);
+        k_gibbs_tt2<<<grid, 256, 0, g->stream>>>(a, g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, c.p_beg, c.p_end, key);
         g->launches++;
     }
     if (c.f_end > c.f_beg) {
         unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        k_gibbs_tt<<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
+        static const int variant = [] { const char *e = getenv("NUMBSKULL_B200_TT_VARIANT"); return e ? atoi(e) : 0; }();
+        switch (variant) {   // experiment knob: unroll depth / registers-for-occupancy trade-off
+        case 1: k_gibbs_tt<2, 8><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
+        case 2: k_gibbs_tt<4, 8><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
+        case 3: k_gibbs_tt<8, 4><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
+        case 4: k_gibbs_tt<8, 6><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
+        default: k_gibbs_tt<4, 1><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
+        }
         g->launches++;
     }
     if (c.c_end > c.c_beg) {
@@ -480,6 +429,91 @@ int nb_run_potentials(nb_graph *g, int chain, const int64_t *var_ids, int64_t n,
     cudaMemcpyAsync(out, d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost, g->stream);
     cudaError_t e = cudaStreamSynchronize(g->stream);
     cudaFree(d_ids); cudaFree(d_off); cudaFree(d_out);
+    NB_CUDA(e);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Parity hook for the RECORD streams: the same device functions the sweep kernels call
+// (nb_tt2_delta / nb_tt_delta / nb_cat_energies) evaluated for the listed variables, so that the
+// energies the hot kernels sample from can be compared with the reference's potential()
+// (inference.py:55-71) deterministically.  PAIR / FAST rows write {0, e1 - e0}; CAT rows write the
+// fp32 per-value energies; rows of the generic classes write nothing (row_class tells).
+// ---------------------------------------------------------------------------
+struct NbCatLocalAcc {
+    float *e;
+    __device__ __forceinline__ void add(int k, float w) { e[k] += w; }
+};
+
+struct RecordStreams {
+    const int64_t *tt2_ptr; const uint32_t *tt2_common; const uint4 *tt2;
+    const int64_t *tt_ptr; const uint4 *tt;
+    const int64_t *cat_ptr; const uint4 *cat;
+    int64_t n_prows, n_frows, n_crows;
+};
+
+__global__ void k_potentials_records(SweepArgs a, RecordStreams R, const int32_t *old2new, const int64_t *var_ids, int64_t n,
+                                     const int64_t *out_offsets, double *out, int32_t *row_class)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t nid = old2new[var_ids[i]];
+    const uint32_t meta = a.vmeta[nid];
+    double *o = out + out_offsets[i];
+    const int64_t s = nid >> 5;
+    if (nid < R.n_prows) {
+        const int64_t q0 = R.tt2_ptr[s];
+        o[0] = 0.0;
+        o[1] = nb_tt2_delta(R.tt2 + q0 + (nid & 31), (int)((R.tt2_ptr[s + 1] - q0) >> 5), R.tt2_common[s], (uint32_t)nid, a.val, a.weight);
+        row_class[i] = NB_CLASS_PAIR;
+    } else if (nid < R.n_frows) {
+        const int64_t q0 = R.tt_ptr[s];
+        o[0] = 0.0;
+        o[1] = nb_tt_delta(R.tt + q0 + (nid & 31), (int)((R.tt_ptr[s + 1] - q0) >> 5), (uint32_t)nid, a.val);
+        row_class[i] = NB_CLASS_FAST;
+    } else if (nid < R.n_crows) {
+        const int64_t sc = (nid - R.n_frows) >> 5;
+        const int64_t q0 = R.cat_ptr[sc];
+        float e[NB_CAT_MAX_CARD];
+        for (int k = 0; k < NB_CAT_MAX_CARD; k++) e[k] = 0.0f;
+        NbCatLocalAcc acc{e};
+        nb_cat_energies(R.cat + q0 + (nid & 31), (int)((R.cat_ptr[sc + 1] - q0) >> 5), (uint32_t)nid, a.val, a.weight, acc);
+        const int card = NB_META_CARD(meta);
+        for (int k = 0; k < card; k++) o[k] = (double)e[k];
+        row_class[i] = NB_CLASS_CAT;
+    } else {
+        row_class[i] = nid < a.n_trows ? NB_CLASS_GEN : NB_CLASS_WARP;
+    }
+}
+
+int nb_run_potentials_records(nb_graph *g, int chain, const int64_t *var_ids, int64_t n, const int64_t *out_offsets,
+                              double *out, int64_t n_out, int32_t *row_class)
+{
+    if (chain < 0 || chain > 1) NB_FAIL(NB_ERR_INVALID, "chain must be 0 or 1");
+    if (n == 0) return NB_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (var_ids[i] < 0 || var_ids[i] >= g->V) NB_FAIL(NB_ERR_INVALID, "variable id %lld out of range", (long long)var_ids[i]);
+    NB_TRY(nb_refresh_inlined_weights(g));
+    int64_t *d_ids, *d_off;
+    double *d_out;
+    int32_t *d_cls;
+    NB_CUDA(cudaMalloc(&d_ids, (size_t)n * 8));
+    NB_CUDA(cudaMalloc(&d_off, (size_t)n * 8));
+    NB_CUDA(cudaMalloc(&d_cls, (size_t)n * 4));
+    NB_CUDA(cudaMalloc(&d_out, (size_t)std::max<int64_t>(n_out, 1) * 8));
+    cudaMemcpyAsync(d_ids, var_ids, (size_t)n * 8, cudaMemcpyHostToDevice, g->stream);
+    cudaMemcpyAsync(d_off, out_offsets, (size_t)n * 8, cudaMemcpyHostToDevice, g->stream);
+    cudaMemsetAsync(d_out, 0, (size_t)n_out * 8, g->stream);
+    SweepArgs a = sweep_args(g, chain, 1, 1, 0, 0);
+    a.w_n = 0;
+    RecordStreams R{g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, g->d_tt_ptr, g->d_tt, g->d_cat_ptr, g->d_cat,
+                    g->n_prows, g->n_frows, g->n_crows};
+    k_potentials_records<<<(unsigned)((n + 127) / 128), 128, 0, g->stream>>>(a, R, g->d_old2new, d_ids, n, d_off, d_out, d_cls);
+    cudaMemcpyAsync(out, d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost, g->stream);
+    cudaMemcpyAsync(row_class, d_cls, (size_t)n * 4, cudaMemcpyDeviceToHost, g->stream);
+    cudaError_t e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_ids); cudaFree(d_off); cudaFree(d_out); cudaFree(d_cls);
     NB_CUDA(e);
     NB_CUDA(cudaGetLastError());
     return NB_OK;

@@ -244,7 +244,10 @@ class PartitionedGibbs(object):
         _, rounds, self.n_colors = run_jp(0, 0)
         self.jp_mode = 0
         cap = int(L.nb_color_natural_round_cap())
-        if self.n_colors > 2 and cap > 0:
+        t = torch.tensor([int(fg.device_info()["max_arity"])], device=self.dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        if self.n_colors > 2 and cap > 0 and int(t.item()) <= 2:
             done, r1, nc = run_jp(1, cap)
             rounds += r1
             if done and nc < self.n_colors:
@@ -393,15 +396,25 @@ class PartitionedGibbs(object):
     def inference(self, burnin_epochs, epochs, sample_evidence=True):
         """FactorGraph.inference for the owned block; returns the owned marginals."""
         fg, L = self.fg, self.lib.lib()
-        fg._upload(0, 0, evid=False)
+        fg._sync_device(0, 0, evid=False, counts=True)
         self.sweeps(burnin_epochs, True, sample_evidence)
-        self.lib.check(L.nb_reset_counts(fg._g))
         self.sweeps(epochs, False, sample_evidence)
         self.torch.cuda.synchronize()
         if self.p2p:
             self.lib.check(L.nb_p2p_check(fg._g))
-        fg._download(0, 0, counts=True, epochs=epochs)
+        fg._marg_epochs = epochs
+        fg._mark_device_newer("var_value", "count", "marginals")
         return fg.marginals[:fg.cstart[self.n_owned]]
+
+    def close(self):
+        """Tear the rank's graph down: unmap the peers' arrays, synchronise, then free."""
+        if self.fg._g is not None:
+            self.torch.cuda.synchronize()
+            if self.p2p:
+                self.lib.check(self.lib.lib().nb_p2p_close(self.fg._g))
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+            self.fg.clear()
 
     def inference_e2e(self, epochs):
         return self.inference(0, epochs, True)
@@ -412,9 +425,9 @@ class PartitionedGibbs(object):
         exchanged; per epoch the weight deltas are summed (numbskull_master.py:223-224)."""
         fg, L, lib, torch = self.fg, self.lib.lib(), self.lib, self.torch
         g = fg._device_graph()
-        fg._upload(0, 0)
+        fg._sync_device(0, 0)
         self.sweeps(burnin_epochs, True, True)
-        w_prev = torch.from_numpy(fg.weight_value[0].copy()).to(self.dev)
+        w_prev = torch.from_numpy(fg._host("weight_value", expose=False)[0].copy()).to(self.dev)
         w_now = torch.empty_like(w_prev)
         for _ in range(epochs):
             ep = C.c_int64(0)
@@ -450,7 +463,9 @@ class PartitionedGibbs(object):
                 lib.check(L.nb_set_weights(g, lib.ptr(host)))
             stepsize *= decay
         torch.cuda.synchronize()
-        fg._download(0, 0, evid=True, weights=True)
+        fg._mark_device_newer("var_value", "var_value_evid")
+        fg._stale.add("weight_value")
+        fg._fetch("weight_value")
         return stepsize
 
 

@@ -203,6 +203,24 @@ def kbc(nvar, rng=None, n_weights=1 << 20, evidence_frac=0.1, window=1024, far_f
     return _pack(weight, variable, factor, fmap)
 
 
+def kbc_fast(nvar, seed=1004, n_weights=1 << 20, evidence_frac=0.1, window=1024, far_frac=0.2,
+             hub_frac=0.001, fixed_frac=0.1, mix=(0.5, 0.5, 0.5)):
+    """Same shape as :func:`kbc`, generated by host threads in the library (``nb_synth_kbc``):
+    counter-based randomness, so the graph depends on ``seed`` only.  The numpy generator needs
+    minutes and tens of GB of temporaries at the BASELINE size (200 M variables / 1 B edges)."""
+    from . import _lib
+    n_imp, n_and, n_or = (int(nvar * x) for x in mix)
+    weight = np.zeros(n_weights, Weight)
+    variable = np.zeros(nvar, Variable)
+    factor = np.zeros(nvar + n_imp + n_and + n_or, Factor)
+    fmap = np.zeros(nvar + 3 * n_imp + 2 * n_and + 3 * n_or, FactorToVar)
+    m3 = np.asarray(mix, np.float64)
+    _lib.check(_lib.lib().nb_synth_kbc(nvar, seed, n_weights, evidence_frac, window, far_frac, hub_frac, fixed_frac,
+                                       _lib.ptr(m3), _lib.ptr(weight), _lib.ptr(variable), _lib.ptr(factor),
+                                       len(factor), _lib.ptr(fmap), len(fmap)))
+    return _pack(weight, variable, factor, fmap)
+
+
 def categorical(nvar, card=16, factors_per_var=3, rng=None, n_weights=1 << 20,
                 evidence_frac=0.2, window=1024, far_frac=0.2):
     """Categorical graph (BASELINE config 5): dataType 1 variables of

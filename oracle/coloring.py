@@ -78,7 +78,8 @@ def policy_coloring(variable, factor, fmap, seed, global_vid=None, cap=NATURAL_R
     adj = neighbours(variable, factor, fmap)
     gid = np.arange(nvar) if global_vid is None else np.asarray(global_vid)
     hashed = _greedy(variable, adj, gid, [jp_priority(int(gid[v]), seed) for v in range(nvar)])
-    if nvar and hashed.max() + 1 > 2 and cap > 0 and natural_rounds(variable, adj, gid) <= cap:
+    pairwise = len(factor) == 0 or int(factor["arity"].max()) <= 2     # nb_build.cu color_graph: max arity <= 2
+    if nvar and hashed.max() + 1 > 2 and cap > 0 and pairwise and natural_rounds(variable, adj, gid) <= cap:
         natural = _greedy(variable, adj, gid, [-int(gid[v]) for v in range(nvar)])
         if natural.max() < hashed.max():
             return relabel_by_min_id(natural, gid), 1
