@@ -365,6 +365,7 @@ def block_c4(args, local_rank):
     med = float(np.median(ms)) / steps
     bad = C.c_int64(-1)
     _lib.check(L.nb_graph_check_coloring(dev.g, C.byref(bad)))
+    _lib.check(L.nb_reset_counts(dev.g))
     t4 = time.perf_counter()
     fg.inference(0, 1, sample_evidence=True)
     m = fg.marginals
@@ -549,6 +550,7 @@ def run_ours(args):
             return fg.marginals
         return runner.inference_e2e(1)
 
+    _lib.check(L.nb_reset_counts(g))            # the timed sweeps tallied too; start the calls from zero
     e2e_step(0)
     e2e_step(1)
     dev.barrier()
@@ -581,7 +583,7 @@ def run_ours(args):
         e2e_extra["state_roundtrip_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / e2e_steps
     V, Wn = len(fg.variable), len(fg.weight)
     h2d = Wn * 8                                  # the float64 weights (changed every step)
-    d2h = len(fg._count) * 1                      # tallies of a 1-epoch call travel as 1 byte each
+    d2h = len(fg._count) * 1                      # cumulative tallies <= 255: 1 byte each (2 up to 65535 sweeps)
 
     c4 = learn = None
     if world == 1 and rank == 0:

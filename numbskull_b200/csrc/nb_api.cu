@@ -799,5 +799,6 @@ extern "C" int nb_set_stream(nb_graph *g, void *cuda_stream)
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     g->stream = (cudaStream_t)cuda_stream;
     g->own_stream = false;
+    if (g->finalized) nb_set_l2_policy(g, g->stream);
     return NB_OK;
 }

@@ -512,10 +512,11 @@ __global__ void k_tt_refresh(int64_t n, uint4 *tt, const uint32_t *tt_wid, const
 int nb_refresh_inlined_weights(nb_graph *g)
 {
     if (g->tt_weights_version == g->weights_version) return NB_OK;
-    if (g->n_tt_quads) {
+    if (g->n_tt_quads)
         k_tt_refresh<<<(unsigned)((g->n_tt_quads + 255) / 256), 256, 0, g->stream>>>(g->n_tt_quads, g->d_tt, g->d_tt_wid, g->d_weight);
-        NB_CUDA(cudaGetLastError());
-    }
+    if (g->n_cat_quads)
+        k_tt_refresh<<<(unsigned)((g->n_cat_quads + 255) / 256), 256, 0, g->stream>>>(g->n_cat_quads, g->d_cat, g->d_cat_wid, g->d_weight);
+    NB_CUDA(cudaGetLastError());
     g->tt_weights_version = g->weights_version;
     return NB_OK;
 }
@@ -623,20 +624,21 @@ __global__ void k_cat_slice_width(int64_t n_slices, int64_t first_id, const int3
     quads[s] = (int64_t)w * 32;
 }
 
-__global__ void k_cat_pad(uint4 *cat, int64_t n)
+__global__ void k_cat_pad(uint4 *cat, uint32_t *wid, int64_t n)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) cat[i] = make_uint4(0u, 0u, nb_pack_cat(0, 0, 0, 3, 1), 0u);
+    if (i < n) { cat[i] = make_uint4(0u, 0u, nb_pack_cat(0, 0, 0, 3, 1), 0u); wid[i] = 0u; }
 }
 
 __global__ void k_fill_cat(RawGraph G, const int32_t *old2new, int64_t first_id, int64_t end_id, const int64_t *cat_ptr,
-                           uint4 *cat, const uint8_t *wfixed)
+                           uint4 *cat, uint32_t *cat_wid, const uint8_t *wfixed, const double *weight)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= G.V || G.v_evid[v] == 4) return;
     const int64_t nid = old2new[v];
     if (nid < first_id || nid >= end_id) return;
     uint4 *row = cat + cat_ptr[(nid - first_id) >> 5] + (nid & 31);
+    uint32_t *wrow = cat_wid + cat_ptr[(nid - first_id) >> 5] + (nid & 31);
     int e_out = 0;
     const int card = G.v_card[v];
     for (int k = 0; k < card; k++) {
@@ -656,8 +658,9 @@ __global__ void k_fill_cat(RawGraph G, const int32_t *old2new, int64_t first_id,
                 n_other++;
             }
             const uint32_t wid = (uint32_t)G.f_wid[f];
-            row[(size_t)e_out * 32] = make_uint4(other[0], other[1],
-                                                 nb_pack_cat(k, eq[0], eq[1], never ? 3 : n_other, wfixed[wid]), wid);
+            row[(size_t)e_out * 32] = make_uint4(other[0], other[1], nb_pack_cat(k, eq[0], eq[1], never ? 3 : n_other, wfixed[wid]),
+                                                 __float_as_uint((float)weight[wid]));
+            wrow[(size_t)e_out * 32] = wid;
             e_out++;
         }
     }
@@ -1150,8 +1153,10 @@ int nb_build_finalize(nb_graph *g)
     NB_TRY(nb_alloc(g, &d_rowlen_new, (size_t)Vn));
     NB_TRY(nb_alloc(g, &g->d_vinit, (size_t)Vn));
     NB_TRY(nb_alloc(g, &g->d_rng_id, (size_t)Vn));
-    NB_TRY(nb_alloc(g, &g->d_val[0], (size_t)Vn));
-    NB_TRY(nb_alloc(g, &g->d_val[1], (size_t)Vn));
+    // both chains in one allocation: one L2 access-policy window covers them (nb_set_l2_policy)
+    g->val_stride = ((size_t)Vn + 255) & ~(size_t)255;
+    NB_TRY(nb_alloc(g, &g->d_val[0], 2 * g->val_stride));
+    g->d_val[1] = g->d_val[0] + g->val_stride;
     k_assign_ids<<<grid_for(V), 256, 0, g->stream>>>(V, d_keys_sorted, d_ids_sorted, nc, d_gstart, d_gbase, G,
                                                      g->d_v_init, d_rowlen, d_fast, g->d_old2new, g->d_new2old, g->d_vmeta,
                                                      d_rowlen_new, g->d_vinit, g->d_rng_id, g->d_val[0], g->d_val[1]);
@@ -1173,6 +1178,9 @@ int nb_build_finalize(nb_graph *g)
             ws[g->n_win] = (int32_t)(gbase[(size_t)gi] + (int64_t)gcount[(size_t)gi]);
             for (int64_t w = g->n_win - 1; w >= 0; w--) if (ws[w] < 0) ws[w] = ws[w + 1];
         }
+        // the filled-in table goes back to the device for the persistent learning kernel
+        NB_CUDA(cudaMemcpyAsync(d_ws, g->win_start.data(), total * 4, cudaMemcpyHostToDevice, g->stream));
+        g->d_win_start = d_ws;
     }
 
     // ---- count layouts ----
@@ -1328,17 +1336,44 @@ int nb_build_finalize(nb_graph *g)
         NB_CUDA(cudaMemcpyAsync(&g->n_cat_quads, g->d_cat_ptr + ncs, 8, cudaMemcpyDeviceToHost, g->stream));
         NB_CUDA(cudaStreamSynchronize(g->stream));
         NB_TRY(nb_alloc(g, &g->d_cat, (size_t)g->n_cat_quads + 1, false));
+        NB_TRY(nb_alloc(g, &g->d_cat_wid, (size_t)g->n_cat_quads + 1, false));
         if (g->n_cat_quads) {
-            k_cat_pad<<<grid_for(g->n_cat_quads), 256, 0, g->stream>>>(g->d_cat, g->n_cat_quads);
+            k_cat_pad<<<grid_for(g->n_cat_quads), 256, 0, g->stream>>>(g->d_cat, g->d_cat_wid, g->n_cat_quads);
             k_fill_cat<<<grid_for(V), 256, 0, g->stream>>>(G, g->d_old2new, g->n_frows, g->n_crows, g->d_cat_ptr, g->d_cat,
-                                                           g->d_wfixed);
+                                                           g->d_cat_wid, g->d_wfixed, g->d_weight);
         }
     }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaStreamSynchronize(g->stream));
     nb_release_color_scratch(g);
     g->finalized = true;
+    nb_set_l2_policy(g, g->stream);
     return NB_OK;
+}
+
+// The gathered value arrays are the only data with re-use: pin as much of them as the device allows
+// in the persisting part of L2 (the rest of the window is treated as streaming).  Best effort --
+// devices / drivers without the feature simply ignore it.  NUMBSKULL_B200_L2_PERSIST=0 disables.
+void nb_set_l2_policy(nb_graph *g, cudaStream_t stream)
+{
+    const char *env = getenv("NUMBSKULL_B200_L2_PERSIST");
+    if ((env && atoi(env) == 0) || !g->d_val[0] || !stream) return;
+    int max_persist = 0, max_window = 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g->device) != cudaSuccess ||
+        max_persist <= 0 || max_window <= 0) { cudaGetLastError(); return; }
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    const size_t bytes = std::min<size_t>(2 * g->val_stride, (size_t)max_window);
+    attr.accessPolicyWindow.base_ptr = g->d_val[0];
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)max_persist / (double)std::max<size_t>(bytes, 1));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+    g->l2_persist_bytes = (int64_t)std::min<size_t>(bytes, (size_t)max_persist);
 }
 
 extern "C" int nb_graph_check_coloring(nb_graph *g, int64_t *conflicts)

@@ -269,7 +269,8 @@ struct nb_graph {
     int64_t n_frows = 0;             // PAIR + FAST rows occupy new ids [0, n_frows)
     int64_t n_crows = 0;             // CAT rows occupy new ids [n_frows, n_crows)
     int64_t *d_cat_ptr = nullptr;    // [(n_crows - n_frows)/32 + 1] quad offsets into d_cat
-    uint4 *d_cat = nullptr;          // categorical records {other A, other B, k:8 eqA:8 eqB:8 nOthers:2 fixed:1, wid}
+    uint4 *d_cat = nullptr;          // categorical records {other A, other B, k:8 eqA:8 eqB:8 nOthers:2 fixed:1, weight fp32}
+    uint32_t *d_cat_wid = nullptr;   // weight id of every categorical record (weight refresh)
     int64_t n_cat_quads = 0;
     int64_t *d_tt_ptr = nullptr;     // [n_frows/32 + 1] quad offsets into d_tt
     uint4 *d_tt = nullptr;           // truth-table stream of the FAST rows (SELL-32, one quad per incidence)
@@ -293,21 +294,18 @@ struct nb_graph {
     int wpart_stride = 4;
 
     // ---- state ----
-    nb_val_t *d_val[2] = {nullptr, nullptr};  // [Vn] chain 0 = free, 1 = evidence
+    nb_val_t *d_val[2] = {nullptr, nullptr};  // [Vn] chain 0 = free, 1 = evidence (one allocation, val_stride apart)
+    size_t val_stride = 0;
+    int64_t l2_persist_bytes = 0;    // bytes of the value arrays pinned in the persisting part of L2
     int32_t *d_count = nullptr;      // [count_entries] new-order layout
     double *d_weight = nullptr;      // [W]
     uint8_t *d_wfixed = nullptr;     // [W]
 
     // ---- learning scratch ----
-    long long *d_grad = nullptr;     // [W] fixed-point gradient sums (generic rows, large weight tables)
-    uint32_t *d_nvis = nullptr;      // [W] visits
-    uint32_t *d_ntrunc = nullptr;    // [W] truncating visits (L1)
-    int32_t *d_gradi = nullptr;      // [W] integer gradient sums (truth-table rows)
-    long long *d_gpart = nullptr;    // block partials (64-bit fixed point; int32 view for truth-table rows)
-    uint32_t *d_npart = nullptr;
-    uint32_t *d_tpart = nullptr;
-    int64_t part_blocks = 0;
-    uint32_t *d_done = nullptr;
+    long long *d_grad = nullptr;     // [3][W] rotating fixed-point gradient sums by weight id (nb_learn.cu)
+    uint32_t *d_nvis = nullptr;      // [3][W] visits (L2) / truncating visits (L1)
+    int32_t *d_win_start = nullptr;  // device copy of win_start: the persistent learning kernel finds its cells' rows in it
+    uint8_t *d_long_rows = nullptr;  // [n_colors] truth-table rows of the colour are long: one warp per row
 
     // scratch for host transfers
     void *d_xfer = nullptr;
@@ -349,6 +347,7 @@ int nb_build_color_restart(nb_graph *g, int mode);
 int nb_natural_round_cap(void);
 void nb_release_color_scratch(nb_graph *g);
 int nb_build_finalize(nb_graph *g);
+void nb_set_l2_policy(nb_graph *g, cudaStream_t stream);
 int nb_refresh_inlined_weights(nb_graph *g);   // d_tt quads carry fp32 weight values: re-inline after a weight change
 int nb_build_color_min_ids(nb_graph *g, int n_colors, int64_t *min_ids);
 int nb_build_relabel_colors(nb_graph *g, const int32_t *map, int n);

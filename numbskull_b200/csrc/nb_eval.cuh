@@ -150,6 +150,24 @@ struct NbValsGlobal {
     const nb_val_t *__restrict__ v;
     __device__ __forceinline__ int operator()(uint32_t vid) const { return (int)v[vid]; }
 };
+// same, bypassing L1: a persistent kernel reads values other CTAs wrote earlier in the same launch
+struct NbValsCG {
+    const nb_val_t *v;
+    __device__ __forceinline__ int operator()(uint32_t vid) const { return (int)__ldcg(v + vid); }
+};
+// weight accessors: global (read-only for the launch), global through L2, or a shared-memory copy
+struct NbWtsGlobal {
+    const double *__restrict__ w;
+    __device__ __forceinline__ double operator()(uint32_t i) const { return __ldg(w + i); }
+};
+struct NbWtsCG {
+    const double *w;
+    __device__ __forceinline__ double operator()(uint32_t i) const { return __ldcg(w + i); }
+};
+struct NbWtsShared {
+    const double *w;
+    __device__ __forceinline__ double operator()(uint32_t i) const { return w[i]; }
+};
 struct NbValsForced {
     uint32_t ida, idb;
     int xa, xb;
@@ -328,37 +346,43 @@ struct NbReservoir {
 // energies of a dataType-0 row for k < card <= 4, all candidate values in one
 // pass over the row (sum order = bucket order = the reference's)
 // ---------------------------------------------------------------------------
-template <bool WIDE>
-__device__ __forceinline__ void nb_row_energies4(const NbRow &r, int len, uint32_t self, int card,
-                                                 const nb_val_t *__restrict__ vals,
-                                                 const double *__restrict__ weight, double e[4])
+template <bool WIDE, class Vals, class Wts>
+__device__ __forceinline__ void nb_row_energies4_v(const NbRow &r, int len, uint32_t self, int card,
+                                                   const Vals &vals, const Wts &weight, double e[4])
 {
     int pos = 0;
     while (pos < len) {
         NbHdr h = nb_read_hdr<WIDE>(r, pos);
         int mpos = nb_member_pos<WIDE>(h, pos);
-        double w = __ldg(weight + h.wid);
+        double w = weight(h.wid);
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (k < card) e[k] = nb_acc(e[k], w, nb_eval_incidence(r, h, mpos, self, k, vals));
+            if (k < card) e[k] = nb_acc(e[k], w, nb_eval_incidence_v(r, h, mpos, self, k, vals));
         pos += nb_inc_words<WIDE>(h);
     }
 }
 
 // energy of value k of a dataType-0 row (any cardinality)
-template <bool WIDE>
-__device__ __forceinline__ double nb_row_energy_k(const NbRow &r, int len, uint32_t self, int k,
-                                                  const nb_val_t *__restrict__ vals,
-                                                  const double *__restrict__ weight)
+template <bool WIDE, class Vals, class Wts>
+__device__ __forceinline__ double nb_row_energy_k_v(const NbRow &r, int len, uint32_t self, int k,
+                                                    const Vals &vals, const Wts &weight)
 {
     double e = 0.0;
     int pos = 0;
     while (pos < len) {
         NbHdr h = nb_read_hdr<WIDE>(r, pos);
-        e = nb_acc(e, __ldg(weight + h.wid), nb_eval_incidence(r, h, nb_member_pos<WIDE>(h, pos), self, k, vals));
+        e = nb_acc(e, weight(h.wid), nb_eval_incidence_v(r, h, nb_member_pos<WIDE>(h, pos), self, k, vals));
         pos += nb_inc_words<WIDE>(h);
     }
     return e;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ double nb_row_energy_k(const NbRow &r, int len, uint32_t self, int k,
+                                                  const nb_val_t *__restrict__ vals,
+                                                  const double *__restrict__ weight)
+{
+    return nb_row_energy_k_v<WIDE>(r, len, self, k, NbValsGlobal{vals}, NbWtsGlobal{weight});
 }
 
 // j-th value (ascending) of a categorical row that has no bucket marker
@@ -401,21 +425,20 @@ __device__ __forceinline__ int nb_draw_small(const double e[4], int card, double
 }
 
 // Sample one variable whose row is `r` (thread path, or any row walked by one thread).
-template <bool WIDE>
-__device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint32_t meta,
-                                    const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
-                                    NbUniforms &rng)
+template <bool WIDE, class Vals, class Wts>
+__device__ inline int nb_sample_row_v(const NbRow &r, int len, uint32_t self, uint32_t meta,
+                                      const Vals &vals, const Wts &weight, NbUniforms &rng)
 {
     const int card = NB_META_CARD(meta);
     if (NB_META_DTYPE(meta) == 0) {
         if (card <= 4) {
             double e[4] = {0.0, 0.0, 0.0, 0.0};
-            nb_row_energies4<WIDE>(r, len, self, card, vals, weight, e);
+            nb_row_energies4_v<WIDE>(r, len, self, card, vals, weight, e);
             return nb_draw_small(e, card, rng.next());
         }
         NbReservoir res;
         for (int k = 0; k < card; k++)
-            if (res.add(nb_row_energy_k<WIDE>(r, len, self, k, vals, weight), 1.0, rng.next32())) res.pick = k;
+            if (res.add(nb_row_energy_k_v<WIDE>(r, len, self, k, vals, weight), 1.0, rng.next32())) res.pick = k;
         return res.pick;
     }
     // categorical: buckets in ascending value order, each introduced by a MARK
@@ -430,7 +453,7 @@ __device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint
             e = 0.0;
             nonempty++;
         } else {
-            e = nb_acc(e, __ldg(weight + h.wid), nb_eval_incidence(r, h, nb_member_pos<WIDE>(h, pos), self, cur, vals));
+            e = nb_acc(e, weight(h.wid), nb_eval_incidence_v(r, h, nb_member_pos<WIDE>(h, pos), self, cur, vals));
         }
         pos += nb_inc_words<WIDE>(h);
     }
@@ -441,6 +464,14 @@ __device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint
         res.pick = nb_nth_empty_value<WIDE>(r, len, j);
     }
     return res.pick;
+}
+
+template <bool WIDE>
+__device__ inline int nb_sample_row(const NbRow &r, int len, uint32_t self, uint32_t meta,
+                                    const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
+                                    NbUniforms &rng)
+{
+    return nb_sample_row_v<WIDE>(r, len, self, meta, NbValsGlobal{vals}, NbWtsGlobal{weight}, rng);
 }
 
 
@@ -490,6 +521,13 @@ __host__ __device__ inline uint32_t nb_fold_key(uint64_t seed, uint64_t epoch, u
 // ids live in a parallel word per quad (tt_wid) that only the learning sweep and
 // the refresh kernel (nb_sweep.cu k_tt_refresh) read.
 // ---------------------------------------------------------------------------
+// Streaming loads.  The record streams, slice pointers and per-variable words are read once per
+// sweep; the value array is gathered at random and re-used.  ncu on the KBC shape showed the
+// streams washing the values out of L2 (28 % L2 hit rate, 2.2x the necessary DRAM bytes), so
+// everything that streams is loaded evict-first (ld.global.cs) and the values keep the cache.
+template <class T>
+__device__ __forceinline__ T nb_lds(const T *p) { return __ldcs(p); }
+
 #define NB_TT_NEUTRAL 0x2492492u   /* 9 x code 2 (difference 0) */
 #define NB_TT_FIXED_BIT (1u << 27) /* weight is fixed (also set on padding quads): no gradient */
 // A parallel word per quad (used by the learning sweep only) holds f(self = 0) + 1 in 2 bits per
@@ -548,7 +586,7 @@ __device__ __forceinline__ double nb_tt_delta(const uint4 *__restrict__ qp, int 
         uint4 q[NB_TT_UNROLL];
 #pragma unroll
         for (int t = 0; t < NB_TT_UNROLL; t++)
-            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4(self, self, NB_TT_NEUTRAL, 0u);
+            q[t] = (j + t < n) ? nb_lds(qp + (size_t)(j + t) * 32) : make_uint4(self, self, NB_TT_NEUTRAL, 0u);
         int xa[NB_TT_UNROLL], xb[NB_TT_UNROLL];
 #pragma unroll
         for (int t = 0; t < NB_TT_UNROLL; t++) {
@@ -586,7 +624,7 @@ __device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int
         const double w = __ldg(weight + (common >> 10));
         int acc = 0;
         for (int j = 0; j < n; j++) {
-            const uint4 q = __ldg(qp + (size_t)j * 32);
+            const uint4 q = nb_lds(qp + (size_t)j * 32);
             const uint32_t o[4] = {q.x, q.y, q.z, q.w};
             int x[4];
 #pragma unroll
@@ -603,7 +641,7 @@ __device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int
         uint4 q[NB_TT2_UNROLL];
 #pragma unroll
         for (int t = 0; t < NB_TT2_UNROLL; t++)
-            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4(self, neutral, self, neutral);
+            q[t] = (j + t < n) ? nb_lds(qp + (size_t)(j + t) * 32) : make_uint4(self, neutral, self, neutral);
         int x0[NB_TT2_UNROLL], x1[NB_TT2_UNROLL];
         double w0[NB_TT2_UNROLL], w1[NB_TT2_UNROLL];
 #pragma unroll
@@ -624,7 +662,8 @@ __device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int
 
 // Categorical records (NB_CLASS_CAT): one quad per incidence of an AND_CAT / EQUAL_CAT_CONST factor
 // (inference.py:251-258) seen from a categorical variable in its bucket k:
-//     { other A, other B, k:8 | eqA:8 | eqB:8 | n_others:2 | fixed:1, weight id }
+//     { other A, other B, k:8 | eqA:8 | eqB:8 | n_others:2 | fixed:1, weight (fp32 bits) }
+// (like the FAST quads the record inlines the weight VALUE; the ids live in cat_wid for the refresh)
 // The factor is 1 iff every other member equals its dense_equal_to (the variable itself matches by
 // construction of the bucket); n_others == 3 marks "never satisfied" (padding, or the variable
 // occurring twice with different values).
@@ -636,21 +675,20 @@ __host__ __device__ inline uint32_t nb_pack_cat(int k, int eq_a, int eq_b, int n
 // Per-value energies of a CAT row: acc.add(k, w) for every satisfied incidence of bucket k.
 template <class Acc>
 __device__ __forceinline__ void nb_cat_energies(const uint4 *__restrict__ qp, int n, uint32_t self,
-                                                const nb_val_t *__restrict__ vals,
-                                                const double *__restrict__ weight, Acc &acc)
+                                                const nb_val_t *__restrict__ vals, Acc &acc)
 {
     for (int j = 0; j < n; j += 2) {
         uint4 q[2];
 #pragma unroll
         for (int t = 0; t < 2; t++)
-            q[t] = (j + t < n) ? __ldg(qp + (size_t)(j + t) * 32) : make_uint4(self, self, nb_pack_cat(0, 0, 0, 3, 1), 0u);
+            q[t] = (j + t < n) ? nb_lds(qp + (size_t)(j + t) * 32) : make_uint4(self, self, nb_pack_cat(0, 0, 0, 3, 1), 0u);
         int xa[2], xb[2];
         float w[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             xa[t] = (int)vals[q[t].x];
             xb[t] = (int)vals[q[t].y];
-            w[t] = (float)__ldg(weight + q[t].w);
+            w[t] = __uint_as_float(q[t].w);
         }
 #pragma unroll
         for (int t = 0; t < 2; t++) {

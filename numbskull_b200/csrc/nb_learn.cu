@@ -1,22 +1,39 @@
 // Weight learning sweep (learning.py:12-125 learnthread / sample_and_sgd).
 //
-// Per colour (split into mini-batches, see DESIGN.md "learning"): every owned
-// variable samples the evidence chain and the free chain in the same pass over
-// its row, then walks the row again for the per-factor gradient
-// (f(proposal | free) - f(evidence | evid)) * featureValue.  Gradients and visit
-// counts are REDUCED BY WEIGHT ID -- block-private shared-memory tables, flushed
-// to per-block partials that the last block sums in block order -- and the
-// SGD / L2-shrink / L1-truncated-gradient update is applied once per mini-batch.
-// Graphs whose weight table does not fit in shared memory accumulate into a
-// global table instead and apply with a separate kernel.
+// An epoch walks the graph in mini-batch CELLS: blocks of consecutive variable ids (outer) and,
+// inside a block, the colours (inner) -- see DESIGN.md "learning".  In a cell every owned variable
+// samples the evidence chain and the free chain in the same pass over its row, then walks the row
+// again for the per-factor gradient (f(proposal | free) - f(evidence | evid)) * featureValue.
+// Gradients and visit counts are REDUCED BY WEIGHT ID in integers (order-independent, hence
+// deterministic), and the SGD / L2-shrink / L1-truncated-gradient update is applied once per cell.
+//
+// The whole epoch is ONE persistent cooperative kernel (k_learn_cells): the CTAs stay resident,
+// walk the cells together and meet at a grid barrier after each one -- a cell of the
+// labelling-function model holds ~1000 rows, far too little for a launch of its own (round 1:
+// 3216 launches and 113 ms per epoch on 1 M x 100).  Weight tables of up to NB_LEARN_SMEM_W entries
+// are staged in shared memory: every CTA keeps its own copy of the weights, reduces its gradients in
+// shared-memory tables, adds them to a global integer table (one atomic per touched weight and
+// CTA), and after the barrier applies the closed-form update to its own copy -- identical inputs,
+// identical result in every CTA, one barrier per cell.  Larger tables accumulate straight into the
+// global integer table and are applied by the grid (two barriers per cell).
 #include <algorithm>
 #include <cmath>
+#include <cooperative_groups.h>
 
 #include "nb_eval.cuh"
 
+namespace cg = cooperative_groups;
+
 #define NB_LEARN_SMEM_W 2048
-#define NB_LEARN_MAX_BLOCKS (148 * 2)
 #define NB_LEARN_THREADS 256
+#define NB_LWARPS (NB_LEARN_THREADS / 32)
+
+// Gradients accumulate in 64-bit fixed point (2^-20 units; truth-table rows contribute integers):
+// integer addition is associative, so per-weight sums do not depend on the order in which threads,
+// CTAs or atomics land.
+#define NB_GRAD_UNIT 1048576.0
+#define NB_GRAD_SHIFT 20
+typedef long long nb_fix_t;
 
 struct LearnArgs {
     const uint32_t *vmeta;
@@ -37,19 +54,46 @@ struct LearnArgs {
     uint64_t seed, epoch;
     double step, reg_param, truncation;
     int regularization, learn_non_evidence;
-    // reduction targets
-    long long *g_grad;    // [W] global fixed-point table (large-W path)
-    uint32_t *g_cnt;      // [W]
-    long long *p_grad;    // [blocks][W] per-block partials (shared-memory path; read as int32 by the truth-table kernels)
-    uint32_t *p_cnt;
-    uint32_t *done;       // completion counter
     // truth-table rows
     const int64_t *tt_ptr;
     const uint4 *tt;
     const uint32_t *tt_base;
     const uint32_t *tt_wid;   // weight id per quad (the quads themselves inline the weight VALUE for the Gibbs sweep)
-    int32_t *gi_grad;     // [W] global integer table (large-W path)
+    // reduction by weight id: three rotating global tables [3][W] (cell c uses c % 3)
+    nb_fix_t *g_grad;
+    uint32_t *g_cnt;
 };
+
+// Where the cells' rows are: block b of n_blocks covers the units [T b / nb, T (b + 1) / nb) of
+// T = n_win * k_sub units; unit u is sub-range (u % k_sub) of k_sub of id window u / k_sub.  Inside a
+// (row class, colour) group the rows are sorted by window, so a block is one contiguous id range per
+// group; windows are cut further (k_sub > 1) when even one window holds more visits of a weight than
+// the mini-batch bound allows (tied weights on large graphs).
+struct CellPlan {
+    const int32_t *win_start;   // [NB_N_CLASSES * (n_colors + 1)][n_win + 1] first new id of each window per group
+    const uint8_t *long_rows;   // [n_colors] truth-table rows of the colour average >= 16 incidences: one warp per row
+    int64_t n_win;
+    int n_colors;               // colours of THIS graph
+    int n_blocks, k_sub;
+    int64_t n_trows;
+};
+
+__device__ __forceinline__ int nb_plan_pos(const CellPlan &p, int group, int64_t unit)
+{
+    const int32_t *ws = p.win_start + (size_t)group * (size_t)(p.n_win + 1);
+    const int64_t w = unit / p.k_sub, j = unit % p.k_sub;
+    if (w >= p.n_win) return ws[p.n_win];
+    const int64_t s = ws[w], e = ws[w + 1];
+    return (int)(s + (e - s) * j / p.k_sub);
+}
+
+__device__ __forceinline__ void nb_plan_range(const CellPlan &p, int cls, int color, int block, int &beg, int &end)
+{
+    const int64_t T = p.n_win * (int64_t)p.k_sub;
+    const int group = cls * (p.n_colors + 1) + color;
+    beg = nb_plan_pos(p, group, T * block / p.n_blocks);
+    end = nb_plan_pos(p, group, T * (block + 1) / p.n_blocks);
+}
 
 // ---------------------------------------------------------------------------
 // closed-form application of n per-visit updates (learning.py:110-125):
@@ -76,29 +120,51 @@ __device__ __forceinline__ double nb_apply_update(double w, double G, uint32_t c
     return w;
 }
 
-// Generic rows accumulate gradients in 64-bit fixed point (2^-20 units): integer addition is
-// associative, so per-weight sums do not depend on the order in which threads, blocks or atomics
-// land -- the reduction by weight id is deterministic without sorting the incidences.
-#define NB_GRAD_UNIT 1048576.0
-typedef long long nb_fix_t;
+// Per-CTA view of the reduction targets and the weights during one cell.
 template <bool SMEM>
-struct GradSink {
-    nb_fix_t *grad;
-    uint32_t *cnt;
-    __device__ __forceinline__ void add(uint32_t wid, double g, uint32_t c)
+struct LearnCtx {
+    const double *w;        // weights: this CTA's shared copy (SMEM) or the global table
+    int32_t *gi;            // SMEM: shared integer gradient table (truth-table rows)
+    nb_fix_t *gf;           // shared (SMEM) or global fixed-point gradient table
+    uint32_t *cnt;          // shared or global visit counts
+    __device__ __forceinline__ double weight(uint32_t i) const { return SMEM ? w[i] : __ldcg(w + i); }
+    __device__ __forceinline__ void add_int(uint32_t wid, int g, uint32_t c) const
     {
-        if (g != 0.0) atomicAdd((unsigned long long *)(grad + wid), (unsigned long long)__double2ll_rn(g * NB_GRAD_UNIT));
+        if (SMEM) { if (g) atomicAdd(gi + wid, g); }
+        else if (g) atomicAdd((unsigned long long *)(gf + wid), (unsigned long long)((long long)g << NB_GRAD_SHIFT));
+        if (c) atomicAdd(cnt + wid, c);
+    }
+    __device__ __forceinline__ void add_real(uint32_t wid, double g, uint32_t c) const
+    {
+        if (g != 0.0) atomicAdd((unsigned long long *)(gf + wid), (unsigned long long)__double2ll_rn(g * NB_GRAD_UNIT));
         if (c) atomicAdd(cnt + wid, c);
     }
 };
 
+template <bool SMEM>
+struct CtxWts {
+    LearnCtx<SMEM> c;
+    __device__ __forceinline__ double operator()(uint32_t i) const { return c.weight(i); }
+};
+
+// visit counter increment of one variable (learning.py:90: one truncation draw per variable)
+__device__ __forceinline__ uint32_t nb_cnt_inc(const LearnArgs &a, uint32_t id)
+{
+    if (a.regularization == 1) {
+        NbUniforms tr(id, a.epoch, NB_TAG_TRUNC, a.seed);
+        return tr.next() < 1.0 / a.truncation ? 1u : 0u;
+    }
+    return a.regularization == 2 ? 1u : 0u;
+}
+
 // second pass over a row: gradient of every visited incidence with a learnable weight
 template <bool WIDE, bool SMEM>
 __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, uint32_t meta, int ev, int prop,
-                                       const LearnArgs &a, uint32_t cnt_inc, GradSink<SMEM> &sink,
+                                       const LearnArgs &a, uint32_t cnt_inc, const LearnCtx<SMEM> &ctx,
                                        int first_inc, int inc_stride, const uint2 *inc_list, int n_inc)
 {
     const bool cat = NB_META_DTYPE(meta) == 1;
+    const NbValsCG vF{a.val_free}, vE{a.val_evid};
     if (inc_list == nullptr) {
         int pos = 0, cur = -1;
         while (pos < len) {
@@ -106,10 +172,10 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
             if (h.code == C_MARK) cur = (int)h.wid;
             else if (!h.fixed && (!cat || cur == ev || cur == prop)) {
                 int mpos = nb_member_pos<WIDE>(h, pos);
-                double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
-                double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
+                double f1 = nb_eval_incidence_v(r, h, mpos, self, prop, vF);
+                double f0 = nb_eval_incidence_v(r, h, mpos, self, ev, vE);
                 double feat = h.feat ? nb_read_feature<WIDE>(r, h, pos) : 1.0;
-                sink.add(h.wid, (f1 - f0) * feat, cnt_inc);
+                ctx.add_real(h.wid, (f1 - f0) * feat, cnt_inc);
             }
             pos += nb_inc_words<WIDE>(h);
         }
@@ -120,66 +186,22 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
             NbHdr h = nb_read_hdr<WIDE>(r, pos);
             if (h.fixed || (cat && cur != ev && cur != prop)) continue;
             int mpos = nb_member_pos<WIDE>(h, pos);
-            double f1 = nb_eval_incidence(r, h, mpos, self, prop, a.val_free);
-            double f0 = nb_eval_incidence(r, h, mpos, self, ev, a.val_evid);
+            double f1 = nb_eval_incidence_v(r, h, mpos, self, prop, vF);
+            double f0 = nb_eval_incidence_v(r, h, mpos, self, ev, vE);
             double feat = h.feat ? nb_read_feature<WIDE>(r, h, pos) : 1.0;
-            sink.add(h.wid, (f1 - f0) * feat, cnt_inc);
+            ctx.add_real(h.wid, (f1 - f0) * feat, cnt_inc);
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// block epilogue of the shared-memory path: flush the block's table, and let
-// the last block to finish sum the partials in block order and apply the update
-// ---------------------------------------------------------------------------
-template <class T>
-__device__ inline void nb_flush_and_apply(const LearnArgs &a, T *s_grad, uint32_t *s_cnt, double unit)
-{
-    __shared__ bool s_last;
-    __syncthreads();
-    T *part = reinterpret_cast<T *>(a.p_grad);
-    T *pg = part + (size_t)blockIdx.x * a.W;
-    uint32_t *pc = a.p_cnt + (size_t)blockIdx.x * a.W;
-    for (int w = threadIdx.x; w < a.W; w += blockDim.x) { pg[w] = s_grad[w]; pc[w] = s_cnt[w]; }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int w = threadIdx.x; w < a.W; w += blockDim.x) {
-        if (a.wfixed[w]) continue;
-        double G = 0.0;
-        uint32_t n = 0;
-        T Gi = 0;
-        for (unsigned b = 0; b < gridDim.x; b++) {      // integer sums: exact, order-independent
-            Gi += __ldcg(part + (size_t)b * a.W + w);
-            n += __ldcg(a.p_cnt + (size_t)b * a.W + w);
-        }
-        G = (double)Gi * unit;
-        if (Gi != 0 || n != 0)
-            a.weight[w] = nb_apply_update(a.weight[w], G, n, a.regularization, a.step, a.reg_param, a.truncation);
-    }
-    if (threadIdx.x == 0) *a.done = 0;
-}
-
-// ---------------------------------------------------------------------------
-// thread path
+// thread path: generic rows (GEN class) and categorical record rows (CAT class), one row per thread
 // ---------------------------------------------------------------------------
 template <bool WIDE, bool SMEM>
-__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, int beg0, int end0, int beg1, int end1)
+__device__ inline void learn_thread_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg0, int end0, int beg1, int end1)
 {
-    extern __shared__ unsigned char s_raw[];
-    nb_fix_t *s_grad = (nb_fix_t *)s_raw;
-    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(nb_fix_t) * (size_t)(SMEM ? a.W : 0));
-    if (SMEM) {
-        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
-        __syncthreads();
-    }
-    GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
-
-    // two id ranges per launch: the colour's FAST-class rows and its GEN-class rows
     const int64_t n0 = end0 - beg0, ntot = n0 + (end1 - beg1);
+    const CtxWts<SMEM> wts{ctx};
     for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < ntot; it += (int64_t)gridDim.x * blockDim.x) {
         const int64_t nid = it < n0 ? beg0 + it : beg1 + (it - n0);
         const uint32_t meta = a.vmeta[nid];
@@ -191,36 +213,30 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_thread(LearnArgs a, 
         int ev;
         if (evid != 1) {                                                    // :53-57
             NbUniforms rng(id, a.epoch, NB_TAG_EVID, a.seed);
-            ev = nb_sample_row<WIDE>(r, len, self, meta, a.val_evid, a.weight, rng);
+            ev = nb_sample_row_v<WIDE>(r, len, self, meta, NbValsCG{a.val_evid}, wts, rng);
         } else {
             ev = (int)a.vinit[nid];                                         // :60-61
         }
         a.val_evid[nid] = (nb_val_t)ev;                                     // :63
         NbUniforms rng(id, a.epoch, NB_TAG_FREE, a.seed);
-        int prop = nb_sample_row<WIDE>(r, len, self, meta, a.val_free, a.weight, rng);   // :65-67
+        int prop = nb_sample_row_v<WIDE>(r, len, self, meta, NbValsCG{a.val_free}, wts, rng);   // :65-67
         a.val_free[nid] = (nb_val_t)prop;                                   // :69
         if (!a.learn_non_evidence && evid != 1) continue;                   // :70-71
-        uint32_t cnt_inc = 1;
-        if (a.regularization == 1) {                                        // :90
-            NbUniforms tr(id, a.epoch, NB_TAG_TRUNC, a.seed);
-            cnt_inc = tr.next() < 1.0 / a.truncation ? 1u : 0u;
-        } else if (a.regularization != 2) cnt_inc = 0;
-        nb_row_gradient<WIDE, SMEM>(r, len, self, meta, ev, prop, a, cnt_inc, sink, 0, 1, nullptr, 0);
+        nb_row_gradient<WIDE, SMEM>(r, len, self, meta, ev, prop, a, nb_cnt_inc(a, id), ctx, 0, 1, nullptr, 0);
     }
-    if (SMEM) nb_flush_and_apply<nb_fix_t>(a, s_grad, s_cnt, 1.0 / NB_GRAD_UNIT);
 }
 
 // ---------------------------------------------------------------------------
 // warp path: one long row per warp
 // ---------------------------------------------------------------------------
 // per-value energies of a warp row into e[4] (dataType 0, card <= 4) or the shared array se
-template <bool WIDE>
+template <bool WIDE, bool SMEM>
 __device__ inline void nb_warp_energies_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
-                                          const nb_val_t *__restrict__ vals, const double *__restrict__ weight,
-                                          double e[4], double *se)
+                                          const nb_val_t *vals, const LearnCtx<SMEM> &ctx, double e[4], double *se)
 {
     const int lane = threadIdx.x & 31, card = NB_META_CARD(meta);
     const bool small = NB_META_DTYPE(meta) == 0 && card <= 4;
+    const NbValsCG v{vals};
     if (!small) {
         for (int k = lane; k < card; k += 32) se[k] = 0.0;
         __syncwarp();
@@ -230,15 +246,15 @@ __device__ inline void nb_warp_energies_l(const NbRow &r, const uint2 *inc, int 
         int pos = (int)ent.x;
         NbHdr h = nb_read_hdr<WIDE>(r, pos);
         int mpos = nb_member_pos<WIDE>(h, pos);
-        double w = weight[h.wid];
+        double w = ctx.weight(h.wid);
         if (small) {
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (k < card) e[k] += w * nb_eval_incidence(r, h, mpos, self, k, vals);
+                if (k < card) e[k] += w * nb_eval_incidence_v(r, h, mpos, self, k, v);
         } else if (NB_META_DTYPE(meta) == 0) {
-            for (int k = 0; k < card; k++) atomicAdd(&se[k], w * nb_eval_incidence(r, h, mpos, self, k, vals));
+            for (int k = 0; k < card; k++) atomicAdd(&se[k], w * nb_eval_incidence_v(r, h, mpos, self, k, v));
         } else {
-            atomicAdd(&se[(int)ent.y], w * nb_eval_incidence(r, h, mpos, self, (int)ent.y, vals));
+            atomicAdd(&se[(int)ent.y], w * nb_eval_incidence_v(r, h, mpos, self, (int)ent.y, v));
         }
     }
     if (small) {
@@ -249,14 +265,13 @@ __device__ inline void nb_warp_energies_l(const NbRow &r, const uint2 *inc, int 
     }
 }
 
-template <bool WIDE>
+template <bool WIDE, bool SMEM>
 __device__ inline int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
-                                       const nb_val_t *__restrict__ vals, const double *__restrict__ weight, double *se,
-                                       NbUniforms &rng)
+                                       const nb_val_t *vals, const LearnCtx<SMEM> &ctx, double *se, NbUniforms &rng)
 {
     const int card = NB_META_CARD(meta);
     double e[4] = {0.0, 0.0, 0.0, 0.0};
-    nb_warp_energies_l<WIDE>(r, inc, n_inc, self, meta, vals, weight, e, se);
+    nb_warp_energies_l<WIDE, SMEM>(r, inc, n_inc, self, meta, vals, ctx, e, se);
     int k;
     if (NB_META_DTYPE(meta) == 0 && card <= 4) k = nb_draw_small(e, card, rng.next());
     else {
@@ -269,22 +284,10 @@ __device__ inline int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_i
     return k;
 }
 
-#define NB_LWARPS (NB_LEARN_THREADS / 32)
-
 template <bool WIDE, bool SMEM>
-__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, int wbeg, int wend)
+__device__ inline void learn_warp_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, double *s_e, int wbeg, int wend)
 {
-    extern __shared__ unsigned char s_raw[];
-    __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
-    nb_fix_t *s_grad = (nb_fix_t *)s_raw;
-    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(nb_fix_t) * (size_t)(SMEM ? a.W : 0));
-    if (SMEM) {
-        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
-        __syncthreads();
-    }
-    GradSink<SMEM> sink{SMEM ? s_grad : a.g_grad, SMEM ? s_cnt : a.g_cnt};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
     for (int64_t wr = (int64_t)wbeg + blockIdx.x * (int64_t)NB_LWARPS + warp; wr < wend;
          wr += (int64_t)gridDim.x * NB_LWARPS) {
         const int64_t nid = a.n_trows + wr;
@@ -298,61 +301,34 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_warp(LearnArgs a, in
         int ev;
         if (evid != 1) {
             NbUniforms rng(id, a.epoch, NB_TAG_EVID, a.seed);
-            ev = nb_warp_sample_l<WIDE>(r, inc, n_inc, self, meta, a.val_evid, a.weight, s_e[warp], rng);
+            ev = nb_warp_sample_l<WIDE, SMEM>(r, inc, n_inc, self, meta, a.val_evid, ctx, s_e, rng);
         } else {
             ev = (int)a.vinit[nid];
         }
         NbUniforms rng(id, a.epoch, NB_TAG_FREE, a.seed);
-        int prop = nb_warp_sample_l<WIDE>(r, inc, n_inc, self, meta, a.val_free, a.weight, s_e[warp], rng);
+        int prop = nb_warp_sample_l<WIDE, SMEM>(r, inc, n_inc, self, meta, a.val_free, ctx, s_e, rng);
         if (lane == 0) { a.val_evid[nid] = (nb_val_t)ev; a.val_free[nid] = (nb_val_t)prop; }
         if (!a.learn_non_evidence && evid != 1) continue;
-        uint32_t cnt_inc = 1;
-        if (a.regularization == 1) {
-            NbUniforms tr(id, a.epoch, NB_TAG_TRUNC, a.seed);
-            cnt_inc = tr.next() < 1.0 / a.truncation ? 1u : 0u;
-        } else if (a.regularization != 2) cnt_inc = 0;
-        nb_row_gradient<WIDE, SMEM>(r, 0, self, meta, ev, prop, a, cnt_inc, sink, lane, 32, inc, n_inc);
+        nb_row_gradient<WIDE, SMEM>(r, 0, self, meta, ev, prop, a, nb_cnt_inc(a, id), ctx, lane, 32, inc, n_inc);
     }
-    if (SMEM) nb_flush_and_apply<nb_fix_t>(a, s_grad, s_cnt, 1.0 / NB_GRAD_UNIT);
 }
 
 // ---------------------------------------------------------------------------
 // truth-table rows (Boolean variable, arity <= 3, unit featureValue): one warp per
 // SELL slice with a uniform trip count.  f(k) = f(0) + k (f(1) - f(0)) comes from
-// the two tables, so the gradient is an INTEGER; the per-weight sums are exact and
-// independent of the order of accumulation (warp REDUX -> shared int table ->
-// per-block partials summed in block order, or an integer global table).
+// the two tables, so the gradient is an INTEGER.
 // ---------------------------------------------------------------------------
-struct GradSinkI {
-    int32_t *grad;
-    uint32_t *cnt;
-    __device__ __forceinline__ void add(uint32_t wid, int g, uint32_t c)
-    {
-        if (g) atomicAdd(grad + wid, g);
-        if (c) atomicAdd(cnt + wid, c);
-    }
-};
-
+__device__ __forceinline__ int nb_ldv(const nb_val_t *v, uint32_t i) { return (int)__ldcg(v + i); }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int beg, int end, uint32_t kfree,
-                                                               uint32_t kevid, uint32_t ktrunc)
+__device__ inline void learn_tt_slices(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg, int end, uint32_t kfree,
+                                       uint32_t kevid, uint32_t ktrunc)
 {
-    extern __shared__ unsigned char s_raw[];
-    int32_t *s_grad = (int32_t *)s_raw;
-    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(int32_t) * (size_t)(SMEM ? a.W : 0));
-    if (SMEM) {
-        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
-        __syncthreads();
-    }
-    GradSinkI sink{SMEM ? s_grad : a.gi_grad, SMEM ? s_cnt : a.g_cnt};
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = blockIdx.x * (int64_t)NB_LWARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
-    const nb_val_t *__restrict__ vF = a.val_free;
-    const nb_val_t *__restrict__ vE = a.val_evid;
-    const double *__restrict__ weight = a.weight;
+    const nb_val_t *vF = a.val_free, *vE = a.val_evid;
 
     for (int64_t s = (beg >> 5) + warp_global; s < (((int64_t)end + 31) >> 5); s += n_warps) {
         const int64_t nid = (s << 5) + lane;
@@ -366,8 +342,8 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
         const uint32_t *bp = a.tt_base + q0 + lane;
         const uint32_t *wp = a.tt_wid + q0 + lane;
 
-        // ---- pass 1: e1 - e0 under both chains (current weights: gathered by id, the inlined
-        //      values are only refreshed for the Gibbs sweep) ----
+        // ---- pass 1: e1 - e0 under both chains (current weights by id: the values inlined in the
+        //      quads are only refreshed for the Gibbs sweep) ----
         double dF = 0.0, dE = 0.0;
         for (int j = 0; j < n; j += 2) {
             uint4 q[2];
@@ -382,14 +358,14 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
             double w[2];
 #pragma unroll
             for (int t = 0; t < 2; t++) {
-                xf[t][0] = vF[q[t].x]; xf[t][1] = vF[q[t].y];
-                xe[t][0] = vE[q[t].x]; xe[t][1] = vE[q[t].y];
-                w[t] = weight[wid[t]];
+                xf[t][0] = nb_ldv(vF, q[t].x); xf[t][1] = nb_ldv(vF, q[t].y);
+                xe[t][0] = nb_ldv(vE, q[t].x); xe[t][1] = nb_ldv(vE, q[t].y);
+                w[t] = ctx.weight(wid[t]);
             }
 #pragma unroll
             for (int t = 0; t < 2; t++) {
-                dF = fma(w[t], (double)((int)((q[t].z >> (3 * nb_tt_index(xf[t][0], xf[t][1]))) & 7u) - 2), dF);
-                dE = fma(w[t], (double)((int)((q[t].z >> (3 * nb_tt_index(xe[t][0], xe[t][1]))) & 7u) - 2), dE);
+                dF = fma(w[t], (double)nb_tt_diff(q[t].z, nb_tt_index(xf[t][0], xf[t][1])), dF);
+                dE = fma(w[t], (double)nb_tt_diff(q[t].z, nb_tt_index(xe[t][0], xe[t][1])), dE);
             }
         }
         // ---- both samples (learning.py:53-69) ----
@@ -415,10 +391,10 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
             const uint4 q = __ldg(qp + (size_t)j * 32);
             const uint32_t b = __ldg(bp + (size_t)j * 32);
             const uint32_t wid = __ldg(wp + (size_t)j * 32);
-            const int iF = nb_tt_index(vF[q.x], vF[q.y]), iE = nb_tt_index(vE[q.x], vE[q.y]);
-            // this variable's own slots read its just-written values; the tables ignore them
-            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * ((int)((q.z >> (3 * iF)) & 7u) - 2);
-            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * ((int)((q.z >> (3 * iE)) & 7u) - 2);
+            // this variable's own slots are ignored by the tables (they may read its fresh values)
+            const int iF = nb_tt_index(nb_ldv(vF, q.x), nb_ldv(vF, q.y)), iE = nb_tt_index(nb_ldv(vE, q.x), nb_ldv(vE, q.y));
+            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * nb_tt_diff(q.z, iF);
+            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * nb_tt_diff(q.z, iE);
             const bool contrib = active && !(q.z & NB_TT_FIXED_BIT);
             const unsigned who = __ballot_sync(FULL, contrib);
             if (who == 0u) continue;
@@ -427,36 +403,24 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt(LearnArgs a, int 
             if (__all_sync(FULL, !contrib || wid == w0)) {
                 const int G = __reduce_add_sync(FULL, contrib ? fF - fE : 0);
                 const unsigned Cn = __reduce_add_sync(FULL, contrib ? cinc : 0u);
-                if (lane == leader) sink.add(w0, G, Cn);
+                if (lane == leader) ctx.add_int(w0, G, Cn);
             } else if (contrib) {
-                sink.add(wid, fF - fE, cinc);
+                ctx.add_int(wid, fF - fE, cinc);
             }
         }
     }
-    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt, 1.0);
 }
 
 // Same algorithm, one WARP per row with the lanes striding over the row's quads: used when the
-// rows are long (data-programming models: a label variable with ~100 labelling functions), where
-// the mini-batches are too small to fill the GPU with one thread per row.
+// rows are long (data-programming models: a label variable with ~100 labelling functions).
 template <bool SMEM>
-__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, int beg, int end, uint32_t kfree,
-                                                                   uint32_t kevid, uint32_t ktrunc)
+__device__ inline void learn_tt_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg, int end, uint32_t kfree,
+                                     uint32_t kevid, uint32_t ktrunc)
 {
-    extern __shared__ unsigned char s_raw[];
-    int32_t *s_grad = (int32_t *)s_raw;
-    uint32_t *s_cnt = (uint32_t *)(s_raw + sizeof(int32_t) * (size_t)(SMEM ? a.W : 0));
-    if (SMEM) {
-        for (int w = threadIdx.x; w < a.W; w += blockDim.x) { s_grad[w] = 0; s_cnt[w] = 0u; }
-        __syncthreads();
-    }
-    GradSinkI sink{SMEM ? s_grad : a.gi_grad, SMEM ? s_cnt : a.g_cnt};
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = blockIdx.x * (int64_t)NB_LWARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
-    const nb_val_t *__restrict__ vF = a.val_free;
-    const nb_val_t *__restrict__ vE = a.val_evid;
-    const double *__restrict__ weight = a.weight;
+    const nb_val_t *vF = a.val_free, *vE = a.val_evid;
 
     for (int64_t nid = (int64_t)beg + warp_global; nid < end; nid += n_warps) {
         const uint32_t meta = a.vmeta[nid];
@@ -472,9 +436,9 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, 
         double dF = 0.0, dE = 0.0;
         for (int j = lane; j < n; j += 32) {
             const uint4 q = __ldg(qp + (size_t)j * 32);
-            const double w = weight[__ldg(wp + (size_t)j * 32)];
-            dF = fma(w, (double)((int)((q.z >> (3 * nb_tt_index(vF[q.x], vF[q.y]))) & 7u) - 2), dF);
-            dE = fma(w, (double)((int)((q.z >> (3 * nb_tt_index(vE[q.x], vE[q.y]))) & 7u) - 2), dE);
+            const double w = ctx.weight(__ldg(wp + (size_t)j * 32));
+            dF = fma(w, (double)nb_tt_diff(q.z, nb_tt_index(nb_ldv(vF, q.x), nb_ldv(vF, q.y))), dF);
+            dE = fma(w, (double)nb_tt_diff(q.z, nb_tt_index(nb_ldv(vE, q.x), nb_ldv(vE, q.y))), dE);
         }
         dF = nb_warp_sum(dF);
         dE = nb_warp_sum(dE);
@@ -499,41 +463,122 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_tt_row(LearnArgs a, 
             if (q.z & NB_TT_FIXED_BIT) continue;
             const uint32_t b = __ldg(bp + (size_t)j * 32);
             // slots that point at the variable itself are ignored by the tables
-            const int iF = nb_tt_index(vF[q.x], vF[q.y]), iE = nb_tt_index(vE[q.x], vE[q.y]);
-            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * ((int)((q.z >> (3 * iF)) & 7u) - 2);
-            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * ((int)((q.z >> (3 * iE)) & 7u) - 2);
-            sink.add(__ldg(wp + (size_t)j * 32), fF - fE, cinc);
+            const int iF = nb_tt_index(nb_ldv(vF, q.x), nb_ldv(vF, q.y)), iE = nb_tt_index(nb_ldv(vE, q.x), nb_ldv(vE, q.y));
+            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * nb_tt_diff(q.z, iF);
+            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * nb_tt_diff(q.z, iE);
+            ctx.add_int(__ldg(wp + (size_t)j * 32), fF - fE, cinc);
         }
     }
-    if (SMEM) nb_flush_and_apply<int32_t>(a, s_grad, s_cnt, 1.0);
 }
 
-__global__ void k_apply_global_int(LearnArgs a)
+// ---------------------------------------------------------------------------
+// the persistent epoch kernel
+// ---------------------------------------------------------------------------
+template <bool WIDE, bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, CellPlan plan, int cell_beg, int cell_end,
+                                                                  int only_color)
 {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.W) return;
-    int G = a.gi_grad[w];
-    uint32_t n = a.g_cnt[w];
-    if (G == 0 && n == 0u) return;
-    a.gi_grad[w] = 0;
-    a.g_cnt[w] = 0u;
-    if (a.wfixed[w]) return;
-    a.weight[w] = nb_apply_update(a.weight[w], (double)G, n, a.regularization, a.step, a.reg_param, a.truncation);
-}
+    extern __shared__ unsigned char s_raw[];
+    __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
+    cg::grid_group grid = cg::this_grid();
+    const int W = a.W;
+    // shared layout (SMEM): weights f64 [W] | fixed-point sums i64 [W] | integer sums i32 [W] | counts u32 [W]
+    double *s_w = (double *)s_raw;
+    nb_fix_t *s_gf = (nb_fix_t *)(s_raw + (size_t)8 * (SMEM ? W : 0));
+    int32_t *s_gi = (int32_t *)(s_raw + (size_t)16 * (SMEM ? W : 0));
+    uint32_t *s_cnt = (uint32_t *)(s_raw + (size_t)20 * (SMEM ? W : 0));
+    if (SMEM) {
+        for (int w = threadIdx.x; w < W; w += blockDim.x) { s_w[w] = __ldcg(a.weight + w); s_gf[w] = 0; s_gi[w] = 0; s_cnt[w] = 0u; }
+        __syncthreads();
+    }
+    const uint32_t kf = nb_fold_key(a.seed, a.epoch, NB_TAG_FREE), ke = nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
+                   kt = nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC);
 
-// large-W path: apply the global table and clear it
-__global__ void k_apply_global(LearnArgs a)
-{
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.W) return;
-    long long G = a.g_grad[w];
-    uint32_t n = a.g_cnt[w];
-    if (G == 0 && n == 0u) return;
-    a.g_grad[w] = 0;
-    a.g_cnt[w] = 0u;
-    if (a.wfixed[w]) return;
-    a.weight[w] = nb_apply_update(a.weight[w], (double)G * (1.0 / NB_GRAD_UNIT), n, a.regularization, a.step, a.reg_param,
-                                  a.truncation);
+    int k = 0;   // cells processed so far in this launch (uniform across the grid): picks the rotating table
+    for (int cell = cell_beg; cell < cell_end; cell++) {
+        // cells enumerate (block, colour) with the colour running fastest; only_color >= 0: the
+        // caller drives the colours itself (partitioned graphs) and `cell` is the block
+        const int block = only_color >= 0 ? cell : cell / plan.n_colors;
+        const int color = only_color >= 0 ? only_color : cell % plan.n_colors;
+        int pb, pe, fb, fe, cb, ce, tb, te, wb, we;
+        nb_plan_range(plan, NB_CLASS_PAIR, color, block, pb, pe);
+        nb_plan_range(plan, NB_CLASS_FAST, color, block, fb, fe);
+        nb_plan_range(plan, NB_CLASS_CAT, color, block, cb, ce);
+        nb_plan_range(plan, NB_CLASS_GEN, color, block, tb, te);
+        nb_plan_range(plan, NB_CLASS_WARP, color, block, wb, we);
+        wb -= (int)plan.n_trows;          // warp rows are addressed by their index
+        we -= (int)plan.n_trows;
+        if (pe <= pb && fe <= fb && ce <= cb && te <= tb && we <= wb) continue;   // uniform across the grid
+        const int slot = k % 3;
+        nb_fix_t *g_gf = a.g_grad + (size_t)slot * W;
+        uint32_t *g_cn = a.g_cnt + (size_t)slot * W;
+        LearnCtx<SMEM> ctx;
+        ctx.w = SMEM ? s_w : a.weight;
+        ctx.gi = s_gi;
+        ctx.gf = SMEM ? s_gf : g_gf;
+        ctx.cnt = SMEM ? s_cnt : g_cn;
+
+        // the table of the NEXT cell is cleared now: its last readers (cell k - 2) passed the previous
+        // barrier, its next writers (cell k + 1) start after this cell's barrier.  Table 0 is cleared
+        // by the host before the launch.
+        {
+            nb_fix_t *z_gf = a.g_grad + (size_t)((k + 1) % 3) * W;
+            uint32_t *z_cn = a.g_cnt + (size_t)((k + 1) % 3) * W;
+            for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
+                z_gf[w] = 0;
+                z_cn[w] = 0u;
+            }
+        }
+        const bool long_rows = plan.long_rows[color] != 0;
+        if (long_rows) {
+            if (pe > pb) learn_tt_rows<SMEM>(a, ctx, pb, pe, kf, ke, kt);
+            if (fe > fb) learn_tt_rows<SMEM>(a, ctx, fb, fe, kf, ke, kt);
+        } else {
+            if (pe > pb) learn_tt_slices<SMEM>(a, ctx, pb, pe, kf, ke, kt);
+            if (fe > fb) learn_tt_slices<SMEM>(a, ctx, fb, fe, kf, ke, kt);
+        }
+        if (te > tb || ce > cb) learn_thread_rows<WIDE, SMEM>(a, ctx, cb, ce, tb, te);
+        if (we > wb) learn_warp_rows<WIDE, SMEM>(a, ctx, s_e[threadIdx.x >> 5], wb, we);
+
+        if (SMEM) {
+            // flush this CTA's tables: one integer atomic per touched weight
+            __syncthreads();
+            for (int w = threadIdx.x; w < W; w += blockDim.x) {
+                const nb_fix_t gsum = s_gf[w] + ((nb_fix_t)s_gi[w] << NB_GRAD_SHIFT);
+                const uint32_t c = s_cnt[w];
+                if (gsum) atomicAdd((unsigned long long *)(g_gf + w), (unsigned long long)gsum);
+                if (c) atomicAdd(g_cn + w, c);
+                s_gf[w] = 0; s_gi[w] = 0; s_cnt[w] = 0u;
+            }
+        }
+        __threadfence();
+        grid.sync();
+        if (SMEM) {
+            // every CTA applies the same sums to its own copy of the weights; CTA 0 publishes them
+            for (int w = threadIdx.x; w < W; w += blockDim.x) {
+                const nb_fix_t Gi = __ldcg(g_gf + w);
+                const uint32_t n = __ldcg(g_cn + w);
+                if ((Gi != 0 || n != 0u) && !a.wfixed[w]) {
+                    const double nw = nb_apply_update(s_w[w], (double)Gi * (1.0 / NB_GRAD_UNIT), n, a.regularization, a.step,
+                                                      a.reg_param, a.truncation);
+                    s_w[w] = nw;
+                    if (blockIdx.x == 0) a.weight[w] = nw;
+                }
+            }
+            __syncthreads();
+        } else {
+            for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
+                const nb_fix_t Gi = __ldcg(g_gf + w);
+                const uint32_t n = __ldcg(g_cn + w);
+                if ((Gi != 0 || n != 0u) && !a.wfixed[w])
+                    __stcg(a.weight + w, nb_apply_update(__ldcg(a.weight + w), (double)Gi * (1.0 / NB_GRAD_UNIT), n,
+                                                        a.regularization, a.step, a.reg_param, a.truncation));
+            }
+            __threadfence();
+            grid.sync();
+        }
+        k++;
+    }
 }
 
 // visits per weight of one colour (upper bound: every incidence of a learnable row)
@@ -590,22 +635,16 @@ static LearnArgs learn_args(nb_graph *g)
     a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
     a.rng_id = g->d_rng_id; a.vinit = g->d_vinit; a.val_free = g->d_val[0]; a.val_evid = g->d_val[1];
     a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
-    a.g_grad = g->d_grad; a.g_cnt = g->d_nvis; a.p_grad = g->d_gpart; a.p_cnt = g->d_npart; a.done = g->d_done;
-    a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.tt_wid = g->d_tt_wid; a.gi_grad = g->d_gradi;
+    a.g_grad = g->d_grad; a.g_cnt = g->d_nvis;
+    a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.tt_wid = g->d_tt_wid;
     return a;
 }
 
-static int ensure_learn_buffers(nb_graph *g, bool smem)
+static int ensure_learn_buffers(nb_graph *g)
 {
-    if (!g->d_done) NB_TRY(nb_alloc(g, &g->d_done, 4));
     if (!g->d_grad) {
-        NB_TRY(nb_alloc(g, &g->d_grad, (size_t)g->W));
-        NB_TRY(nb_alloc(g, &g->d_gradi, (size_t)g->W));
-        NB_TRY(nb_alloc(g, &g->d_nvis, (size_t)g->W));
-    }
-    if (smem && !g->d_gpart) {
-        NB_TRY(nb_alloc(g, &g->d_gpart, (size_t)NB_LEARN_MAX_BLOCKS * (size_t)g->W));
-        NB_TRY(nb_alloc(g, &g->d_npart, (size_t)NB_LEARN_MAX_BLOCKS * (size_t)g->W));
+        NB_TRY(nb_alloc(g, &g->d_grad, 3 * (size_t)std::max<int64_t>(g->W, 1)));     // three rotating tables, zeroed
+        NB_TRY(nb_alloc(g, &g->d_nvis, 3 * (size_t)std::max<int64_t>(g->W, 1)));
     }
     return NB_OK;
 }
@@ -614,9 +653,11 @@ static int ensure_learn_buffers(nb_graph *g, bool smem)
 static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &out)
 {
     out.assign((size_t)g->n_colors, 0);
-    uint32_t *d_max;
+    uint32_t *d_max, *d_hist;
     NB_TRY(nb_alloc(g, &d_max, 1));
-    for (int c = 0; c < g->n_colors; c++) {
+    NB_CUDA(cudaMalloc(&d_hist, (size_t)std::max<int64_t>(g->W, 1) * 4));
+    int rc = NB_OK;
+    for (int c = 0; c < g->n_colors && rc == NB_OK; c++) {
         const NbColorRange &cr = g->colors[(size_t)c];
         RowRanges rr;
         rr.beg[0] = cr.p_beg; rr.end[0] = cr.p_end; rr.beg[1] = cr.f_beg; rr.end[1] = cr.f_end;
@@ -625,68 +666,26 @@ static int color_visit_bounds(nb_graph *g, LearnArgs a, std::vector<int64_t> &ou
         int64_t n = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.c_end - cr.c_beg) + (cr.t_end - cr.t_beg) +
                     (cr.w_end - cr.w_beg);
         if (n == 0) continue;
-        NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
-        NB_CUDA(cudaMemsetAsync(d_max, 0, 4, g->stream));
+        cudaMemsetAsync(d_hist, 0, (size_t)g->W * 4, g->stream);
+        cudaMemsetAsync(d_max, 0, 4, g->stream);
         unsigned grid = (unsigned)((n + 255) / 256);
-        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, rr, g->d_nvis);
-        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, rr, g->d_nvis);
-        k_max_u32<<<64, 256, 0, g->stream>>>(g->d_nvis, (int)g->W, d_max);
+        if (g->wide) k_visit_histogram<true><<<grid, 256, 0, g->stream>>>(a, rr, d_hist);
+        else k_visit_histogram<false><<<grid, 256, 0, g->stream>>>(a, rr, d_hist);
+        k_max_u32<<<64, 256, 0, g->stream>>>(d_hist, (int)g->W, d_max);
         uint32_t m = 0;
-        NB_CUDA(cudaMemcpyAsync(&m, d_max, 4, cudaMemcpyDeviceToHost, g->stream));
-        NB_CUDA(cudaStreamSynchronize(g->stream));
+        cudaMemcpyAsync(&m, d_max, 4, cudaMemcpyDeviceToHost, g->stream);
+        if (cudaStreamSynchronize(g->stream) != cudaSuccess) rc = NB_ERR_CUDA;
         out[(size_t)c] = m;
     }
-    NB_CUDA(cudaMemsetAsync(g->d_nvis, 0, (size_t)g->W * 4, g->stream));
+    cudaFree(d_hist);
+    if (rc != NB_OK) NB_FAIL(NB_ERR_CUDA, "visit histogram failed: %s", cudaGetErrorString(cudaGetLastError()));
     return NB_OK;
 }
 
-template <bool WIDE, bool SMEM>
-static int launch_learn_range(nb_graph *g, const LearnArgs &a, int pb, int pe, int fb, int fe, int cb, int ce, int tb, int te,
-                              int wb, int we, bool long_rows)
-{
-    const size_t smem_tt = SMEM ? (size_t)g->W * 8 : 0;     // int32 sums + counts
-    const size_t smem = SMEM ? (size_t)g->W * 12 : 0;       // 64-bit fixed-point sums + counts
-    const unsigned apply_grid = (unsigned)((g->W + 255) / 256);
-    const int tt_range[2][2] = {{pb, pe}, {fb, fe}};                // PAIR rows, then FAST rows: both have TT quads
-    for (int pass = 0; pass < 2; pass++) {
-        const int rb = tt_range[pass][0], re = tt_range[pass][1];
-        if (re <= rb) continue;
-        const uint32_t kf = nb_fold_key(a.seed, a.epoch, NB_TAG_FREE), ke = nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
-                       kt = nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC);
-        if (long_rows) {     // one warp per row
-            int64_t need = ((int64_t)(re - rb) + NB_LWARPS - 1) / NB_LWARPS;
-            unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
-            k_learn_tt_row<SMEM><<<grid, NB_LEARN_THREADS, smem_tt, g->stream>>>(a, rb, re, kf, ke, kt);
-        } else {             // one thread per row, one warp per SELL slice
-            int64_t need = ((((int64_t)re + 31) >> 5) - (rb >> 5) + NB_LWARPS - 1) / NB_LWARPS;
-            unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : 148 * 16);
-            k_learn_tt<SMEM><<<grid, NB_LEARN_THREADS, smem_tt, g->stream>>>(a, rb, re, kf, ke, kt);
-        }
-        g->launches++;
-        if (!SMEM) { k_apply_global_int<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
-    }
-    if (te > tb || ce > cb) {
-        int64_t need = ((int64_t)(te - tb) + (ce - cb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
-        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
-        k_learn_thread<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, cb, ce, tb, te);
-        g->launches++;
-        if (!SMEM) { k_apply_global<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
-    }
-    if (we > wb) {
-        int64_t need = ((int64_t)(we - wb) + NB_LWARPS - 1) / NB_LWARPS;
-        unsigned grid = (unsigned)std::min<int64_t>(need, SMEM ? NB_LEARN_MAX_BLOCKS : (1 << 30));
-        k_learn_warp<WIDE, SMEM><<<grid, NB_LEARN_THREADS, smem, g->stream>>>(a, wb, we);
-        g->launches++;
-        if (!SMEM) { k_apply_global<<<apply_grid, 256, 0, g->stream>>>(a); g->launches++; }
-    }
-    return NB_OK;
-}
-
-// per-graph cache of the visit bounds (depends on learn_non_evidence)
+// per-graph cache of the visit bounds (depends on learn_non_evidence) and the device-side plan data
 static int learn_prepare(nb_graph *g, LearnArgs &a, std::vector<int64_t> &vmax, int learn_non_evidence)
 {
-    const bool smem = g->W <= NB_LEARN_SMEM_W;
-    NB_TRY(ensure_learn_buffers(g, smem));
+    NB_TRY(ensure_learn_buffers(g));
     a = learn_args(g);
     a.learn_non_evidence = learn_non_evidence;
     if (g->learn_vmax_flag != learn_non_evidence || (int)g->learn_vmax.size() != g->n_colors) {
@@ -694,43 +693,20 @@ static int learn_prepare(nb_graph *g, LearnArgs &a, std::vector<int64_t> &vmax, 
         g->learn_vmax_flag = learn_non_evidence;
     }
     vmax = g->learn_vmax;
-    return NB_OK;
-}
-
-// Rows of colour c whose original id falls into block `b` of `nb` (blocks = runs of id windows).
-// The learning epoch walks the blocks in increasing id order and, inside a block, the colours:
-// weights and chains advance together through the graph like in the reference's ascending-id
-// scan (learning.py:20-31), instead of one whole colour (all of a variable type) at a time.
-static int learn_block_of_color(nb_graph *g, const LearnArgs &a, int c, int b, int nb)
-{
-    const bool smem = g->W <= NB_LEARN_SMEM_W;
-    const NbColorRange &cr = g->colors[(size_t)c];
-    const int64_t w_lo = g->n_win * (int64_t)b / nb, w_hi = g->n_win * (int64_t)(b + 1) / nb;
-    const size_t row = (size_t)g->n_win + 1;
-    auto range = [&](int cls, int &beg, int &end) {
-        const int32_t *ws = g->win_start.data() + (size_t)(cls * (g->n_colors + 1) + c) * row;
-        beg = ws[w_lo];
-        end = ws[w_hi];
-    };
-    int pb, pe, fb, fe, cb, ce, tb, te, wb, we;
-    range(NB_CLASS_PAIR, pb, pe);
-    range(NB_CLASS_FAST, fb, fe);
-    range(NB_CLASS_CAT, cb, ce);      // categorical rows: learned by the generic thread kernel
-    range(NB_CLASS_GEN, tb, te);
-    range(NB_CLASS_WARP, wb, we);
-    wb -= (int)g->n_trows;          // warp rows are addressed by their index
-    we -= (int)g->n_trows;
-    if (pe <= pb && fe <= fb && ce <= cb && te <= tb && we <= wb) return NB_OK;
-    const int64_t rows = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.c_end - cr.c_beg) + (cr.t_end - cr.t_beg) +
-                         (cr.w_end - cr.w_beg);
-    // truth-table rows of this colour average >= 16 incidences: spread each row over a warp
-    const bool long_rows = ((cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg)) > 0 && cr.edges >= 16 * rows;
-    if (g->wide) {
-        if (smem) return launch_learn_range<true, true>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
-        return launch_learn_range<true, false>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
+    if (!g->d_long_rows) {
+        std::vector<uint8_t> lr((size_t)std::max(g->n_colors, 1), 0);
+        for (int c = 0; c < g->n_colors; c++) {
+            const NbColorRange &cr = g->colors[(size_t)c];
+            const int64_t rows = (cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg) + (cr.c_end - cr.c_beg) + (cr.t_end - cr.t_beg) +
+                                 (cr.w_end - cr.w_beg);
+            // truth-table rows of this colour average >= 16 incidences: spread each row over a warp
+            lr[(size_t)c] = ((cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg)) > 0 && cr.edges >= 16 * rows;
+        }
+        NB_TRY(nb_alloc(g, &g->d_long_rows, lr.size(), false));
+        NB_CUDA(cudaMemcpyAsync(g->d_long_rows, lr.data(), lr.size(), cudaMemcpyHostToDevice, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
     }
-    if (smem) return launch_learn_range<false, true>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
-    return launch_learn_range<false, false>(g, a, pb, pe, fb, fe, cb, ce, tb, te, wb, we, long_rows);
+    return NB_OK;
 }
 
 // Mini-batch size: at most this many visits of any one weight between two applications.  The
@@ -744,13 +720,29 @@ static int64_t default_batch_visits(double step, int64_t batch_visits)
     return batch_visits > 0 ? batch_visits : (int64_t)std::max(1.0, std::floor(0.25 / std::max(std::fabs(step), 1e-12)));
 }
 
-// number of id blocks per epoch: enough that no weight collects more than the batch bound in a block
+// Number of id blocks per epoch: enough that no weight collects more than the batch bound in a block.
+// NOT capped at the number of id windows: when one window already exceeds the bound (a weight tied
+// across a large graph) the plan cuts the windows further (CellPlan::k_sub).
 static int block_count(const nb_graph *g, const std::vector<int64_t> &vmax, int64_t bv)
 {
     int64_t total = 0;
     for (int64_t v : vmax) total += v;       // a weight can be visited from every colour inside a block
     int64_t nb = std::max<int64_t>(1, (total + bv - 1) / bv);
-    return (int)std::min<int64_t>(nb, std::max<int64_t>(1, g->n_win));
+    const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(g->V, 1ll << 30));   // one variable per cell at the very least
+    return (int)std::min<int64_t>(nb, cap);
+}
+
+static CellPlan make_plan(const nb_graph *g, int n_blocks)
+{
+    CellPlan p;
+    p.win_start = g->d_win_start;
+    p.long_rows = g->d_long_rows;
+    p.n_win = g->n_win;
+    p.n_colors = g->n_colors;
+    p.n_blocks = std::max(1, n_blocks);
+    p.k_sub = (int)std::max<int64_t>(1, ((int64_t)p.n_blocks + g->n_win - 1) / std::max<int64_t>(g->n_win, 1));
+    p.n_trows = g->n_trows;
+    return p;
 }
 
 int nb_learn_block_count(nb_graph *g, double step, int learn_non_evidence, int64_t batch_visits, int *n_blocks)
@@ -762,6 +754,36 @@ int nb_learn_block_count(nb_graph *g, double step, int learn_non_evidence, int64
     return NB_OK;
 }
 
+template <bool WIDE, bool SMEM>
+static int launch_cells_t(nb_graph *g, LearnArgs a, CellPlan plan, int cell_beg, int cell_end, int only_color)
+{
+    const size_t smem = SMEM ? (size_t)g->W * 24 : 0;
+    auto kern = k_learn_cells<WIDE, SMEM>;
+    if (smem > 32 * 1024) NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 0;
+    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NB_LEARN_THREADS, smem));
+    NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
+    if (per_sm < 1) NB_FAIL(NB_ERR_CUDA, "the learning kernel does not fit on an SM");
+    // all CTAs must be co-resident (grid barrier); two per SM hide each other's latencies
+    const int grid = sms * std::min(per_sm, 2);
+    NB_CUDA(cudaMemsetAsync(a.g_grad, 0, (size_t)g->W * sizeof(nb_fix_t), g->stream));   // rotating table 0
+    NB_CUDA(cudaMemsetAsync(a.g_cnt, 0, (size_t)g->W * sizeof(uint32_t), g->stream));
+    void *args[] = {&a, &plan, &cell_beg, &cell_end, &only_color};
+    NB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)grid), dim3(NB_LEARN_THREADS), args, smem, g->stream));
+    g->launches++;
+    return NB_OK;
+}
+
+static int launch_cells(nb_graph *g, const LearnArgs &a, const CellPlan &plan, int cell_beg, int cell_end, int only_color)
+{
+    const bool smem = g->W <= NB_LEARN_SMEM_W;
+    if (g->wide) return smem ? launch_cells_t<true, true>(g, a, plan, cell_beg, cell_end, only_color)
+                             : launch_cells_t<true, false>(g, a, plan, cell_beg, cell_end, only_color);
+    return smem ? launch_cells_t<false, true>(g, a, plan, cell_beg, cell_end, only_color)
+                : launch_cells_t<false, false>(g, a, plan, cell_beg, cell_end, only_color);
+}
+
+// one (block, colour) cell: the partitioned runner exchanges halo values between the cells itself
 int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step, int regularization, double reg_param,
                    double truncation, int learn_non_evidence, uint64_t seed, uint64_t epoch)
 {
@@ -772,7 +794,7 @@ int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step,
     NB_TRY(learn_prepare(g, a, vmax, learn_non_evidence));
     a.seed = seed; a.reg_param = reg_param; a.truncation = truncation; a.regularization = regularization;
     a.step = step; a.epoch = epoch;
-    NB_TRY(learn_block_of_color(g, a, color, block, n_blocks));
+    NB_TRY(launch_cells(g, a, make_plan(g, n_blocks), block, block + 1, color));
     g->weights_version++;
     NB_CUDA(cudaGetLastError());
     return NB_OK;
@@ -791,8 +813,12 @@ int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, 
         a.step = step;
         a.epoch = g->epoch_counter++;
         const int nb = block_count(g, vmax, default_batch_visits(step, batch_visits));
-        for (int b = 0; b < nb; b++)
-            for (int c = 0; c < g->n_colors; c++) NB_TRY(learn_block_of_color(g, a, c, b, nb));
+        const int64_t cells = (int64_t)nb * g->n_colors;
+        // one persistent launch per epoch (cell indices are 32-bit: split absurdly long epochs)
+        for (int64_t c0 = 0; c0 < cells; c0 += (1 << 30)) {
+            const int64_t c1 = std::min<int64_t>(cells, c0 + (1 << 30));
+            NB_TRY(launch_cells(g, a, make_plan(g, nb), (int)c0, (int)c1, -1));
+        }
         g->weights_version++;
         NB_CUDA(cudaGetLastError());
         step *= decay;   // factorgraph.py:206

@@ -99,9 +99,9 @@ __global__ void __launch_bounds__(256, MINB) k_gibbs_tt(SweepArgs a, const int64
     const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (nid >= end) return;
     // independent loads first: they overlap with the stream
-    const uint32_t meta = a.vmeta[nid];
-    const uint32_t rid = a.rng_id[nid];
-    const int64_t q0 = tt_ptr[nid >> 5], q1 = tt_ptr[(nid >> 5) + 1];
+    const uint32_t meta = nb_lds(a.vmeta + nid);
+    const uint32_t rid = nb_lds(a.rng_id + nid);
+    const int64_t q0 = nb_lds(tt_ptr + (nid >> 5)), q1 = nb_lds(tt_ptr + (nid >> 5) + 1);
     const int n = (int)((q1 - q0) >> 5);                      // incidences of the longest row of this slice
     const double d = nb_tt_delta<UNROLL>(tt + q0 + (nid & 31), n, (uint32_t)nid, a.val);   // e1 - e0
     const int evid = NB_META_EVID(meta);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256, MINB) k_gibbs_tt(SweepArgs a, const int64
     const float p0 = 1.0f / (1.0f + __expf((float)d));
     const int k = u <= (double)p0 ? 0 : 1;
     a.val[nid] = (nb_val_t)k;
-    if (!a.burnin) a.count_b[nid] += k;                      // inference.py:30-31
+    if (!a.burnin && k) __stcs(a.count_b + nid, nb_lds(a.count_b + nid) + 1);   // inference.py:30-31
 }
 
 // PAIR rows: 8-byte records, two per quad -- or, in uniform slices, bare member ids, four per quad.
@@ -123,10 +123,10 @@ __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *_
     nb_wait_halo(a);
     const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (nid >= end) return;
-    const uint32_t meta = a.vmeta[nid];
-    const uint32_t rid = a.rng_id[nid];
-    const int64_t q0 = tt2_ptr[nid >> 5], q1 = tt2_ptr[(nid >> 5) + 1];
-    const uint32_t common = tt2_common[nid >> 5];
+    const uint32_t meta = nb_lds(a.vmeta + nid);
+    const uint32_t rid = nb_lds(a.rng_id + nid);
+    const int64_t q0 = nb_lds(tt2_ptr + (nid >> 5)), q1 = nb_lds(tt2_ptr + (nid >> 5) + 1);
+    const uint32_t common = nb_lds(tt2_common + (nid >> 5));
     const int n = (int)((q1 - q0) >> 5);                      // quads of the longest row of this slice
     const double d = nb_tt2_delta(tt2 + q0 + (nid & 31), n, common, (uint32_t)nid, a.val, a.weight);   // e1 - e0
     const int evid = NB_META_EVID(meta);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *_
     const float p0 = 1.0f / (1.0f + __expf((float)d));
     const int k = u <= (double)p0 ? 0 : 1;
     a.val[nid] = (nb_val_t)k;
-    if (!a.burnin) a.count_b[nid] += k;                      // inference.py:30-31
+    if (!a.burnin && k) __stcs(a.count_b + nid, nb_lds(a.count_b + nid) + 1);   // inference.py:30-31
 }
 
 // CAT rows: categorical variable (cardinality <= 32) with AND_CAT / EQUAL_CAT_CONST factors.  One
@@ -155,18 +155,18 @@ __global__ void __launch_bounds__(256) k_gibbs_cat(SweepArgs a, const int64_t *_
     nb_wait_halo(a);
     const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (nid >= end) return;
-    const uint32_t meta = a.vmeta[nid];
-    const uint32_t rid = a.rng_id[nid];
-    const uint32_t cs = a.cstart[nid];
+    const uint32_t meta = nb_lds(a.vmeta + nid);
+    const uint32_t rid = nb_lds(a.rng_id + nid);
+    const uint32_t cs = nb_lds(a.cstart + nid);
     const int card = NB_META_CARD(meta);
     const int64_t s = (nid - first_id) >> 5;
-    const int64_t q0 = cat_ptr[s], q1 = cat_ptr[s + 1];
+    const int64_t q0 = nb_lds(cat_ptr + s), q1 = nb_lds(cat_ptr + s + 1);
     const int n = (int)((q1 - q0) >> 5);
     const int tid = threadIdx.x;
 #pragma unroll 4
     for (int k = 0; k < card; k++) s_e[k][tid] = 0.0f;
     NbCatSmemAcc acc{s_e, tid};
-    nb_cat_energies(cat + q0 + (nid & 31), n, (uint32_t)nid, a.val, a.weight, acc);
+    nb_cat_energies(cat + q0 + (nid & 31), n, (uint32_t)nid, a.val, acc);
     const int evid = NB_META_EVID(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
     if (!(evid == 0 || a.sample_evidence)) return;          // :24
@@ -324,7 +324,7 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     const NbColorRange &c = g->colors[(size_t)color];
     if (!burnin && epoch != g->last_tally_epoch) { g->tally_bound++; g->last_tally_epoch = epoch; }
     SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
-    if (c.f_end > c.f_beg) NB_TRY(nb_refresh_inlined_weights(g));
+    if (c.f_end > c.f_beg || c.c_end > c.c_beg) NB_TRY(nb_refresh_inlined_weights(g));
     if (c.p_end > c.p_beg) {
         unsigned grid = (unsigned)((c.p_end - c.p_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
@@ -478,7 +478,7 @@ __global__ void k_potentials_records(SweepArgs a, RecordStreams R, const int32_t
         float e[NB_CAT_MAX_CARD];
         for (int k = 0; k < NB_CAT_MAX_CARD; k++) e[k] = 0.0f;
         NbCatLocalAcc acc{e};
-        nb_cat_energies(R.cat + q0 + (nid & 31), (int)((R.cat_ptr[sc + 1] - q0) >> 5), (uint32_t)nid, a.val, a.weight, acc);
+        nb_cat_energies(R.cat + q0 + (nid & 31), (int)((R.cat_ptr[sc + 1] - q0) >> 5), (uint32_t)nid, a.val, acc);
         const int card = NB_META_CARD(meta);
         for (int k = 0; k < card; k++) o[k] = (double)e[k];
         row_class[i] = NB_CLASS_CAT;

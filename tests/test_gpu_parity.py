@@ -571,3 +571,26 @@ def test_ising_full_size_properties():
     fg2 = _fg_from_synth(synth.ising_grid(n, n), seed=2024)
     fg2.inference(5, 20, sample_evidence=True)
     assert np.array_equal(fg2.count, c1)                       # checksum of a seeded run repeats
+
+
+def test_tied_weights_at_the_default_step_follow_the_oracle(oracle):
+    """Three weights tied over 20 000 evidence pairs at the CLI's default step 0.01: the mini-batch
+    bound (step * visits of one weight <= 0.25 between two applications) needs far more blocks than
+    there are id windows, so the windows are cut further (CellPlan::k_sub).  Without that cut one
+    stale-weight update applies step * (hundreds of gradients) and the trajectory leaves the
+    per-visit SGD of the reference (learning.py:110-125)."""
+    import ctypes as C
+    from numbskull_b200 import _lib, synth
+    g = synth.ising_pairs(20000, rng=np.random.default_rng(17))
+    args = (0, 30, 0.01, 0.95, 2, 0.001, 1)
+    fg = _fg_from_synth(g, seed=2)
+    fg.learn(*args)
+    nb = C.c_int(0)
+    _lib.check(_lib.lib().nb_learn_blocks(fg._g, 0.01, 0, 0, C.byref(nb)))
+    info = fg.device_info()
+    assert nb.value > (info["n_variable"] >> 5) + 1                # more blocks than id windows
+    og = _oracle_of(oracle, fg, seed=5)
+    og.learn(*args)
+    wg, wc = fg.weight_value[0], og.weight_value
+    assert np.abs(wg - wc).max() < 0.05, (wg, wc)
+    assert np.abs(wg - [1.0, 1.0, 0.5]).max() < 0.1, wg
