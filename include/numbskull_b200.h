@@ -126,6 +126,16 @@ int nb_synth_kbc(int64_t nvar, uint64_t seed, int64_t n_weights, double evidence
                  double far_frac, double hub_frac, double fixed_frac, const double *mix3,
                  nb_weight_rec *weight, nb_variable_rec *variable, nb_factor_rec *factor, int64_t n_factor,
                  nb_ftv_rec *fmap, int64_t n_fmap);
+/* The same graph piecewise, for partitioned runs that never hold the whole graph: the weight table,
+ * the variable records of listed global ids (NULL: 0 .. n-1), and the factors that touch the owner
+ * block [lo, hi) in increasing global factor id with GLOBAL member ids (factor == NULL: only size the
+ * arrays through *n_factor / *n_fmap). */
+int nb_synth_kbc_weights(uint64_t seed, int64_t n_weights, double fixed_frac, nb_weight_rec *weight);
+int nb_synth_kbc_variables(uint64_t seed, double evidence_frac, const int64_t *gids, int64_t n,
+                           nb_variable_rec *variable);
+int nb_synth_kbc_block(int64_t nvar, uint64_t seed, int64_t n_weights, int64_t window, double far_frac,
+                       double hub_frac, const double *mix3, int64_t lo, int64_t hi, nb_factor_rec *factor,
+                       int64_t *n_factor, nb_ftv_rec *fmap, int64_t *n_fmap);
 
 /* -------------------------- graph lifecycle -------------------------- */
 

@@ -61,6 +61,10 @@ SIGNATURES = {
     "nb_load_domains": (C.c_int, [_P, _I64, _P, _P, _I64, _P, _I64]),
     "nb_load_factors": (C.c_int, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _I64]),
     "nb_synth_kbc": (C.c_int, [_I64, _U64, _I64, _DBL, _I64, _DBL, _DBL, _DBL, _P, _P, _P, _P, _I64, _P, _I64]),
+    "nb_synth_kbc_weights": (C.c_int, [_U64, _I64, _DBL, _P]),
+    "nb_synth_kbc_variables": (C.c_int, [_U64, _DBL, _P, _I64, _P]),
+    "nb_synth_kbc_block": (C.c_int, [_I64, _U64, _I64, _I64, _DBL, _DBL, _P, _I64, _I64, _P, C.POINTER(_I64), _P,
+                                     C.POINTER(_I64)]),
     "nb_graph_create": (C.c_int, [C.POINTER(GraphDesc), C.POINTER(_P)]),
     "nb_graph_destroy": (None, [_P]),
     "nb_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),

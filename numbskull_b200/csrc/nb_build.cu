@@ -1351,13 +1351,16 @@ int nb_build_finalize(nb_graph *g)
     return NB_OK;
 }
 
-// The gathered value arrays are the only data with re-use: pin as much of them as the device allows
-// in the persisting part of L2 (the rest of the window is treated as streaming).  Best effort --
-// devices / drivers without the feature simply ignore it.  NUMBSKULL_B200_L2_PERSIST=0 disables.
+// The gathered value arrays are the only data with re-use.  Loading everything else evict-first
+// (nb_lds) is what keeps them in L2; additionally pinning them in the PERSISTING part of L2 through
+// an access-policy window was measured and is off by default: on B200 it made the sweeps slower
+// (KBC 50 M: 2.51 -> 2.86 ms, KBC 200 M: 8.97 -> 9.58 ms, Ising: 0.162 -> 0.184 ms;
+// profiles/r2c_*), presumably because the carve-out shrinks the cache left for the streams' own
+// short-lived lines.  NUMBSKULL_B200_L2_PERSIST=1 enables it.
 void nb_set_l2_policy(nb_graph *g, cudaStream_t stream)
 {
     const char *env = getenv("NUMBSKULL_B200_L2_PERSIST");
-    if ((env && atoi(env) == 0) || !g->d_val[0] || !stream) return;
+    if (!env || atoi(env) == 0 || !g->d_val[0] || !stream) return;
     int max_persist = 0, max_window = 0;
     if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g->device) != cudaSuccess ||
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g->device) != cudaSuccess ||

@@ -517,8 +517,9 @@ extern "C" int nb_load_factors(const uint8_t *data, int64_t n_bytes, int64_t n_f
 // Benchmark input generator (BASELINE config 4): the KBC-style Boolean graph
 // of numbskull_b200/synth.py kbc(), filled by host threads straight into the reference's packed
 // record arrays.  Counter-based randomness (splitmix64 of (seed, stream, index)): the graph does
-// not depend on the thread count.  Not part of the hot path: it only feeds it (the role
-// ising/ising.cpp plays for the reference).
+// not depend on the thread count, and any owner block of it can be generated on its own
+// (nb_synth_kbc_block: partitioned runs never materialise the 1 B-edge graph).  Not part of the
+// hot path: it only feeds it (the role ising/ising.cpp plays for the reference).
 // ---------------------------------------------------------------------------
 static inline uint64_t sm64(uint64_t x)
 {
@@ -530,16 +531,74 @@ static inline uint64_t sm64(uint64_t x)
 static inline uint64_t rnd(uint64_t seed, uint64_t stream, uint64_t i) { return sm64(sm64(seed ^ (stream * 0xD1342543DE82EF95ull)) + i); }
 static inline double unit(uint64_t r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
 
-extern "C" int nb_synth_kbc(int64_t nvar, uint64_t seed, int64_t n_weights, double evidence_frac, int64_t window,
-                            double far_frac, double hub_frac, double fixed_frac, const double *mix3,
-                            nb_weight_rec *weight, nb_variable_rec *variable, nb_factor_rec *factor, int64_t n_factor,
-                            nb_ftv_rec *fmap, int64_t n_fmap)
+struct KbcShape {
+    int64_t nvar, n_imp, n_and, n_or, nhub, window, n_weights;
+    uint64_t seed;
+    double far_frac, hub_frac, log1mp;
+    int64_t n_factor() const { return nvar + n_imp + n_and + n_or; }
+};
+
+static KbcShape kbc_shape(int64_t nvar, uint64_t seed, int64_t n_weights, int64_t window, double far_frac, double hub_frac,
+                          const double *mix3)
 {
-    const int64_t n_imp = (int64_t)(nvar * mix3[0]), n_and = (int64_t)(nvar * mix3[1]), n_or = (int64_t)(nvar * mix3[2]);
-    if (n_factor != nvar + n_imp + n_and + n_or || n_fmap != nvar + 3 * n_imp + 2 * n_and + 3 * n_or)
-        NB_FAIL(NB_ERR_INVALID, "nb_synth_kbc: array sizes do not match the mix");
-    const int64_t nhub = std::max<int64_t>(1, (int64_t)(nvar * 1e-5));
-    const double p_geo = 1.0 / std::max(2.0, (double)window / 8.0), log1mp = std::log1p(-p_geo);
+    KbcShape S;
+    S.nvar = nvar; S.seed = seed; S.n_weights = n_weights; S.window = window; S.far_frac = far_frac; S.hub_frac = hub_frac;
+    S.n_imp = (int64_t)(nvar * mix3[0]); S.n_and = (int64_t)(nvar * mix3[1]); S.n_or = (int64_t)(nvar * mix3[2]);
+    S.nhub = std::max<int64_t>(1, (int64_t)(nvar * 1e-5));
+    S.log1mp = std::log1p(-1.0 / std::max(2.0, (double)window / 8.0));
+    return S;
+}
+
+// factor f: [0, nvar) ISTRUE(v = f); then IMPLY_NATURAL arity 3, AND arity 2, OR arity 3.  Members: an
+// anchor plus geometric-window partners (local), uniform partners (far) or Zipf-like hubs.
+static inline int kbc_factor(const KbcShape &S, int64_t f, int &func, int64_t m[3])
+{
+    int arity;
+    if (f < S.nvar) { func = 4; m[0] = f; return 1; }
+    else if (f < S.nvar + S.n_imp) { func = 0; arity = 3; }
+    else if (f < S.nvar + S.n_imp + S.n_and) { func = 2; arity = 2; }
+    else { func = 1; arity = 3; }
+    const int64_t anchor = (int64_t)(rnd(S.seed, 6, (uint64_t)f) % (uint64_t)S.nvar);
+    m[0] = anchor;
+    for (int j = 1; j < arity; j++) {
+        const uint64_t k = (uint64_t)f * 4 + (uint64_t)j;
+        if (unit(rnd(S.seed, 7, k)) < S.hub_frac) {                 // P(rank >= x) = x^-(a-1), a = 1.5
+            const double u = std::max(unit(rnd(S.seed, 8, k)), 1e-12);
+            const int64_t rank = std::min<int64_t>(S.nhub - 1, (int64_t)(1.0 / (u * u)) - 1);
+            m[j] = (int64_t)(rnd(S.seed, 9, (uint64_t)rank) % (uint64_t)S.nvar);
+        } else if (unit(rnd(S.seed, 10, k)) < S.far_frac) {
+            m[j] = (int64_t)(rnd(S.seed, 11, k) % (uint64_t)S.nvar);
+        } else {
+            const double u = std::max(unit(rnd(S.seed, 12, k)), 1e-300);
+            int64_t d = std::min<int64_t>(S.window, 1 + (int64_t)(std::log(u) / S.log1mp));   // geometric, capped
+            if (rnd(S.seed, 13, k) & 1u) d = -d;
+            m[j] = ((anchor + d) % S.nvar + S.nvar) % S.nvar;
+        }
+    }
+    return arity;
+}
+
+static inline void kbc_factor_rec(const KbcShape &S, int64_t f, int func, int arity, int64_t off, nb_factor_rec &r)
+{
+    r.factorFunction = (int16_t)func;
+    r.weightId = (int64_t)((((uint64_t)f * 0x9E3779B97F4A7C15ull) >> 40) % (uint64_t)S.n_weights);
+    r.featureValue = 1.0;
+    r.arity = arity;
+    r.ftv_offset = off;
+}
+
+static inline void kbc_variable_rec(uint64_t seed, double evidence_frac, int64_t gid, nb_variable_rec &v)
+{
+    const bool ev = unit(rnd(seed, 4, (uint64_t)gid)) < evidence_frac;
+    v.isEvidence = ev ? 1 : 0;
+    v.initialValue = ev ? (int64_t)(rnd(seed, 5, (uint64_t)gid) & 1u) : 0;
+    v.dataType = 0;
+    v.cardinality = 2;
+    v.vtf_offset = 0;
+}
+
+extern "C" int nb_synth_kbc_weights(uint64_t seed, int64_t n_weights, double fixed_frac, nb_weight_rec *weight)
+{
     host_threads(n_weights, [&](int64_t a, int64_t b) {
         for (int64_t i = a; i < b; i++) {
             weight[i].isFixed = unit(rnd(seed, 1, (uint64_t)i)) < fixed_frac;
@@ -548,54 +607,86 @@ extern "C" int nb_synth_kbc(int64_t nvar, uint64_t seed, int64_t n_weights, doub
             weight[i].initialValue = 0.5 * std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
         }
     });
-    host_threads(nvar, [&](int64_t a, int64_t b) {
-        for (int64_t i = a; i < b; i++) {
-            nb_variable_rec &v = variable[i];
-            const bool ev = unit(rnd(seed, 4, (uint64_t)i)) < evidence_frac;
-            v.isEvidence = ev ? 1 : 0;
-            v.initialValue = ev ? (int64_t)(rnd(seed, 5, (uint64_t)i) & 1u) : 0;
-            v.dataType = 0;
-            v.cardinality = 2;
-            v.vtf_offset = 0;
-        }
+    return NB_OK;
+}
+
+// variable records of the listed global ids (gids == NULL: ids 0 .. n-1)
+extern "C" int nb_synth_kbc_variables(uint64_t seed, double evidence_frac, const int64_t *gids, int64_t n,
+                                      nb_variable_rec *variable)
+{
+    host_threads(n, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) kbc_variable_rec(seed, evidence_frac, gids ? gids[i] : i, variable[i]);
     });
-    // factor f: [0, nvar) ISTRUE(v = f); then IMPLY_NATURAL arity 3, AND arity 2, OR arity 3
+    return NB_OK;
+}
+
+extern "C" int nb_synth_kbc(int64_t nvar, uint64_t seed, int64_t n_weights, double evidence_frac, int64_t window,
+                            double far_frac, double hub_frac, double fixed_frac, const double *mix3,
+                            nb_weight_rec *weight, nb_variable_rec *variable, nb_factor_rec *factor, int64_t n_factor,
+                            nb_ftv_rec *fmap, int64_t n_fmap)
+{
+    const KbcShape S = kbc_shape(nvar, seed, n_weights, window, far_frac, hub_frac, mix3);
+    if (n_factor != S.n_factor() || n_fmap != nvar + 3 * S.n_imp + 2 * S.n_and + 3 * S.n_or)
+        NB_FAIL(NB_ERR_INVALID, "nb_synth_kbc: array sizes do not match the mix");
+    nb_synth_kbc_weights(seed, n_weights, fixed_frac, weight);
+    nb_synth_kbc_variables(seed, evidence_frac, nullptr, nvar, variable);
     host_threads(n_factor, [&](int64_t a, int64_t b) {
         for (int64_t f = a; f < b; f++) {
-            int func, arity;
-            int64_t off;
-            if (f < nvar) { func = 4; arity = 1; off = f; }
-            else if (f < nvar + n_imp) { func = 0; arity = 3; off = nvar + 3 * (f - nvar); }
-            else if (f < nvar + n_imp + n_and) { func = 2; arity = 2; off = nvar + 3 * n_imp + 2 * (f - nvar - n_imp); }
-            else { func = 1; arity = 3; off = nvar + 3 * n_imp + 2 * n_and + 3 * (f - nvar - n_imp - n_and); }
-            nb_factor_rec &r = factor[f];
-            r.factorFunction = (int16_t)func;
-            r.weightId = (int64_t)((((uint64_t)f * 0x9E3779B97F4A7C15ull) >> 40) % (uint64_t)n_weights);
-            r.featureValue = 1.0;
-            r.arity = arity;
-            r.ftv_offset = off;
-            if (f < nvar) { fmap[off].vid = f; fmap[off].dense_equal_to = 0; continue; }
-            const int64_t anchor = (int64_t)(rnd(seed, 6, (uint64_t)f) % (uint64_t)nvar);
-            fmap[off].vid = anchor;
-            fmap[off].dense_equal_to = 0;
-            for (int j = 1; j < arity; j++) {
-                const uint64_t k = (uint64_t)f * 4 + (uint64_t)j;
-                int64_t m;
-                if (unit(rnd(seed, 7, k)) < hub_frac) {                 // Zipf-like hub: P(rank >= x) = x^-1/2... x^-(a-1), a = 1.5
-                    const double u = std::max(unit(rnd(seed, 8, k)), 1e-12);
-                    const int64_t rank = std::min<int64_t>(nhub - 1, (int64_t)(1.0 / (u * u)) - 1);
-                    m = (int64_t)(rnd(seed, 9, (uint64_t)rank) % (uint64_t)nvar);
-                } else if (unit(rnd(seed, 10, k)) < far_frac) {
-                    m = (int64_t)(rnd(seed, 11, k) % (uint64_t)nvar);
-                } else {
-                    const double u = std::max(unit(rnd(seed, 12, k)), 1e-300);
-                    int64_t d = std::min<int64_t>(window, 1 + (int64_t)(std::log(u) / log1mp));   // geometric, capped
-                    if (rnd(seed, 13, k) & 1u) d = -d;
-                    m = ((anchor + d) % nvar + nvar) % nvar;
-                }
-                fmap[off + j].vid = m;
-                fmap[off + j].dense_equal_to = 0;
-            }
+            int func;
+            int64_t m[3], off;
+            const int arity = kbc_factor(S, f, func, m);
+            if (f < nvar) off = f;
+            else if (f < nvar + S.n_imp) off = nvar + 3 * (f - nvar);
+            else if (f < nvar + S.n_imp + S.n_and) off = nvar + 3 * S.n_imp + 2 * (f - nvar - S.n_imp);
+            else off = nvar + 3 * S.n_imp + 2 * S.n_and + 3 * (f - nvar - S.n_imp - S.n_and);
+            kbc_factor_rec(S, f, func, arity, off, factor[f]);
+            for (int j = 0; j < arity; j++) { fmap[off + j].vid = m[j]; fmap[off + j].dense_equal_to = 0; }
+        }
+    });
+    return NB_OK;
+}
+
+// The factors with at least one member in the owner block [lo, hi), in increasing global factor id,
+// members as GLOBAL variable ids.  Call with factor == NULL to size the arrays (*n_factor, *n_fmap
+// are outputs), then again to fill them (*n_factor, *n_fmap are the sizes returned before).
+extern "C" int nb_synth_kbc_block(int64_t nvar, uint64_t seed, int64_t n_weights, int64_t window, double far_frac,
+                                  double hub_frac, const double *mix3, int64_t lo, int64_t hi, nb_factor_rec *factor,
+                                  int64_t *n_factor, nb_ftv_rec *fmap, int64_t *n_fmap)
+{
+    const KbcShape S = kbc_shape(nvar, seed, n_weights, window, far_frac, hub_frac, mix3);
+    const int64_t F = S.n_factor();
+    const int nt = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    const int64_t chunk = (F + nt - 1) / nt;
+    std::vector<int64_t> cf((size_t)nt + 1, 0), ce((size_t)nt + 1, 0);
+    auto touches = [&](const int64_t *m, int arity) {
+        for (int j = 0; j < arity; j++) if (m[j] >= lo && m[j] < hi) return true;
+        return false;
+    };
+    run_threads(nt, [&](int t) {
+        int64_t nf = 0, ne = 0;
+        for (int64_t f = t * chunk; f < std::min(F, (t + 1) * chunk); f++) {
+            int func;
+            int64_t m[3];
+            const int arity = kbc_factor(S, f, func, m);
+            if (touches(m, arity)) { nf++; ne += arity; }
+        }
+        cf[(size_t)t + 1] = nf;
+        ce[(size_t)t + 1] = ne;
+    });
+    for (int t = 0; t < nt; t++) { cf[(size_t)t + 1] += cf[(size_t)t]; ce[(size_t)t + 1] += ce[(size_t)t]; }
+    if (!factor) { *n_factor = cf[(size_t)nt]; *n_fmap = ce[(size_t)nt]; return NB_OK; }
+    if (*n_factor != cf[(size_t)nt] || *n_fmap != ce[(size_t)nt]) NB_FAIL(NB_ERR_INVALID, "nb_synth_kbc_block: sizes changed between the calls");
+    run_threads(nt, [&](int t) {
+        int64_t nf = cf[(size_t)t], ne = ce[(size_t)t];
+        for (int64_t f = t * chunk; f < std::min(F, (t + 1) * chunk); f++) {
+            int func;
+            int64_t m[3];
+            const int arity = kbc_factor(S, f, func, m);
+            if (!touches(m, arity)) continue;
+            kbc_factor_rec(S, f, func, arity, ne, factor[nf]);
+            for (int j = 0; j < arity; j++) { fmap[ne + j].vid = m[j]; fmap[ne + j].dense_equal_to = 0; }
+            nf++;
+            ne += arity;
         }
     });
     return NB_OK;

@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
 {
     extern __shared__ unsigned char s_raw[];
     __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
+    __shared__ int s_rng[2 * NB_N_CLASSES];
     cg::grid_group grid = cg::this_grid();
     const int W = a.W;
     // shared layout (SMEM): weights f64 [W] | fixed-point sums i64 [W] | integer sums i32 [W] | counts u32 [W]
@@ -500,12 +501,14 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
         // caller drives the colours itself (partitioned graphs) and `cell` is the block
         const int block = only_color >= 0 ? cell : cell / plan.n_colors;
         const int color = only_color >= 0 ? only_color : cell % plan.n_colors;
-        int pb, pe, fb, fe, cb, ce, tb, te, wb, we;
-        nb_plan_range(plan, NB_CLASS_PAIR, color, block, pb, pe);
-        nb_plan_range(plan, NB_CLASS_FAST, color, block, fb, fe);
-        nb_plan_range(plan, NB_CLASS_CAT, color, block, cb, ce);
-        nb_plan_range(plan, NB_CLASS_GEN, color, block, tb, te);
-        nb_plan_range(plan, NB_CLASS_WARP, color, block, wb, we);
+        // five threads look the cell's id ranges up (64-bit divisions and dependent loads: not per thread)
+        __syncthreads();
+        if (threadIdx.x < NB_N_CLASSES) nb_plan_range(plan, (int)threadIdx.x, color, block, s_rng[2 * threadIdx.x], s_rng[2 * threadIdx.x + 1]);
+        __syncthreads();
+        const int pb = s_rng[2 * NB_CLASS_PAIR], pe = s_rng[2 * NB_CLASS_PAIR + 1], fb = s_rng[2 * NB_CLASS_FAST],
+                  fe = s_rng[2 * NB_CLASS_FAST + 1], cb = s_rng[2 * NB_CLASS_CAT], ce = s_rng[2 * NB_CLASS_CAT + 1],
+                  tb = s_rng[2 * NB_CLASS_GEN], te = s_rng[2 * NB_CLASS_GEN + 1];
+        int wb = s_rng[2 * NB_CLASS_WARP], we = s_rng[2 * NB_CLASS_WARP + 1];
         wb -= (int)plan.n_trows;          // warp rows are addressed by their index
         we -= (int)plan.n_trows;
         if (pe <= pb && fe <= fb && ce <= cb && te <= tb && we <= wb) continue;   // uniform across the grid

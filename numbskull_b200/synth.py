@@ -221,6 +221,38 @@ def kbc_fast(nvar, seed=1004, n_weights=1 << 20, evidence_frac=0.1, window=1024,
     return _pack(weight, variable, factor, fmap)
 
 
+def kbc_block(nvar, lo, hi, seed=1004, n_weights=1 << 20, evidence_frac=0.1, window=1024, far_frac=0.2,
+              hub_frac=0.001, fixed_frac=0.1, mix=(0.5, 0.5, 0.5)):
+    """Rank-local share of :func:`kbc_fast`'s graph for the owner block ``[lo, hi)``: every factor
+    with a member in the block, owned variables first and the remote members as ghosts
+    (``isEvidence = 4``) -- the dict :func:`numbskull_b200.partition.extract_local` returns, built
+    without ever materialising the global graph (BASELINE config 4 across 8 GPUs)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    m3 = np.asarray(mix, np.float64)
+    nf, ne = C.c_int64(0), C.c_int64(0)
+    _lib.check(L.nb_synth_kbc_block(nvar, seed, n_weights, window, far_frac, hub_frac, _lib.ptr(m3), lo, hi,
+                                    None, C.byref(nf), None, C.byref(ne)))
+    factor = np.zeros(nf.value, Factor)
+    fmap = np.zeros(ne.value, FactorToVar)
+    _lib.check(L.nb_synth_kbc_block(nvar, seed, n_weights, window, far_frac, hub_frac, _lib.ptr(m3), lo, hi,
+                                    _lib.ptr(factor), C.byref(nf), _lib.ptr(fmap), C.byref(ne)))
+    gvid = fmap["vid"]
+    owned = (gvid >= lo) & (gvid < hi)
+    ghosts = np.unique(gvid[~owned])
+    n_owned = hi - lo
+    global_vid = np.concatenate((np.arange(lo, hi, dtype=np.int64), ghosts))
+    variable = np.zeros(len(global_vid), Variable)
+    _lib.check(L.nb_synth_kbc_variables(seed, evidence_frac, _lib.ptr(global_vid), len(global_vid), _lib.ptr(variable)))
+    variable["isEvidence"][n_owned:] = 4
+    fmap["vid"] = np.where(owned, gvid - lo, n_owned + np.searchsorted(ghosts, gvid))
+    weight = np.zeros(n_weights, Weight)
+    _lib.check(L.nb_synth_kbc_weights(seed, n_weights, fixed_frac, _lib.ptr(weight)))
+    return dict(weight=weight, variable=variable, factor=factor, fmap=fmap,
+                domain_mask=np.zeros(len(variable), np.bool_), global_vid=global_vid, n_owned=int(n_owned))
+
+
 def categorical(nvar, card=16, factors_per_var=3, rng=None, n_weights=1 << 20,
                 evidence_frac=0.2, window=1024, far_frac=0.2):
     """Categorical graph (BASELINE config 5): dataType 1 variables of

@@ -131,3 +131,24 @@ def test_halo_exchange_gloo_world2(tmp_path):
     for r in res:
         assert r[0] == 1 and r[1] == 1
     assert res[0][2] == res[1][3] and res[0][3] == res[1][2] and res[0][2] > 0
+
+
+def test_kbc_block_generator_matches_extract_local():
+    """Partitioned runs of BASELINE config 4 generate each owner block on its own
+    (synth.kbc_block, host threads, counter-based randomness): identical to cutting the block out
+    of the whole graph (partition.extract_local on synth.kbc_fast)."""
+    import numpy as np
+    from numbskull_b200 import partition, synth
+    n = 60_000
+    w, v, f, fm, dm, e = synth.kbc_fast(n, seed=7)
+    for world in (1, 3):
+        for r in range(world):
+            lo, hi = n * r // world, n * (r + 1) // world
+            a = partition.extract_local(w, v, f, fm, lo, hi)
+            b = synth.kbc_block(n, lo, hi, seed=7)
+            for k in ("variable", "factor", "fmap", "global_vid", "weight"):
+                assert np.array_equal(a[k], b[k]), (world, r, k)
+            assert a["n_owned"] == b["n_owned"]
+    # the whole-graph generator does not depend on the number of host threads
+    import os
+    assert len(f) == n + 3 * (n // 2) and int(f["arity"].sum()) == len(fm) == e
