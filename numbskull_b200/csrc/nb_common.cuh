@@ -305,6 +305,7 @@ struct nb_graph {
     long long *d_grad = nullptr;     // [3][W] rotating fixed-point gradient sums by weight id (nb_learn.cu)
     uint32_t *d_nvis = nullptr;      // [3][W] visits (L2) / truncating visits (L1)
     int32_t *d_win_start = nullptr;  // device copy of win_start: the persistent learning kernel finds its cells' rows in it
+    unsigned *d_learn_bar = nullptr; // grid barrier state of the persistent learning kernel
     uint8_t *d_long_rows = nullptr;  // [n_colors] truth-table rows of the colour are long: one warp per row
 
     // scratch for host transfers

@@ -182,9 +182,13 @@ __device__ __forceinline__ int nb_member(const NbRow &r, int mpos, int step, int
     return vid == self ? k : vals(vid);
 }
 
+// NOT inlined: the 26-way switch is called from a dozen places in the generic samplers and the
+// learning kernel; inlined everywhere it blew the persistent learning kernel up to 855 KB of SASS
+// (k_gibbs_thread: 195 KB), and every mini-batch cell then ran out of a cold instruction cache
+// (ncu: 81 % i-cache hit rate, the slowest CTA 6x slower than the average one).
 template <class Vals>
-__device__ inline double nb_eval_incidence_v(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
-                                             int k, const Vals &vals)
+__device__ __noinline__ double nb_eval_incidence_v(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
+                                                   int k, const Vals &vals)
 {
     const int a = h.arity;
     const int step = nb_code_has_eq(h.code) ? 2 : 1;
@@ -426,8 +430,8 @@ __device__ __forceinline__ int nb_draw_small(const double e[4], int card, double
 
 // Sample one variable whose row is `r` (thread path, or any row walked by one thread).
 template <bool WIDE, class Vals, class Wts>
-__device__ inline int nb_sample_row_v(const NbRow &r, int len, uint32_t self, uint32_t meta,
-                                      const Vals &vals, const Wts &weight, NbUniforms &rng)
+__device__ __noinline__ int nb_sample_row_v(const NbRow &r, int len, uint32_t self, uint32_t meta,
+                                            const Vals &vals, const Wts &weight, NbUniforms &rng)
 {
     const int card = NB_META_CARD(meta);
     if (NB_META_DTYPE(meta) == 0) {

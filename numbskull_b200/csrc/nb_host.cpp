@@ -411,17 +411,22 @@ static inline double be_f64(const uint8_t *p)
     return d;
 }
 
-// dataloading.py:103-123: 17-byte records (int64 weightId, u8 isFixed, f64 initialValue)
+// dataloading.py:103-123: 17-byte records (int64 weightId, u8 isFixed, f64 initialValue).
+// Fixed-width records: parsed by host threads (every id occurs once, so the writes do not collide).
 extern "C" int nb_load_weights(const uint8_t *data, int64_t n_bytes, int64_t n_weight, nb_weight_rec *out)
 {
     if (n_bytes < 17 * n_weight) NB_FAIL(NB_ERR_INVALID, "graph.weights: %lld bytes < %lld records", (long long)n_bytes, (long long)n_weight);
-    for (int64_t i = 0; i < n_weight; i++) {
-        const uint8_t *r = data + 17 * i;
-        int64_t id = (int64_t)be64(r);
-        if (id < 0 || id >= n_weight) NB_FAIL(NB_ERR_INVALID, "graph.weights: weightId %lld out of range", (long long)id);
-        out[id].isFixed = r[8];
-        out[id].initialValue = be_f64(r + 9);
-    }
+    std::atomic<int64_t> bad(-1);
+    host_threads(n_weight, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            const uint8_t *r = data + 17 * i;
+            int64_t id = (int64_t)be64(r);
+            if (id < 0 || id >= n_weight) { bad.store(id); continue; }
+            out[id].isFixed = r[8];
+            out[id].initialValue = be_f64(r + 9);
+        }
+    });
+    if (bad.load() != -1) NB_FAIL(NB_ERR_INVALID, "graph.weights: weightId %lld out of range", (long long)bad.load());
     return NB_OK;
 }
 
@@ -430,15 +435,19 @@ extern "C" int nb_load_weights(const uint8_t *data, int64_t n_bytes, int64_t n_w
 extern "C" int nb_load_variables(const uint8_t *data, int64_t n_bytes, int64_t n_variable, nb_variable_rec *out)
 {
     if (n_bytes < 27 * n_variable) NB_FAIL(NB_ERR_INVALID, "graph.variables: %lld bytes < %lld records", (long long)n_bytes, (long long)n_variable);
-    for (int64_t i = 0; i < n_variable; i++) {
-        const uint8_t *r = data + 27 * i;
-        int64_t id = (int64_t)be64(r);
-        if (id < 0 || id >= n_variable) NB_FAIL(NB_ERR_INVALID, "graph.variables: variableId %lld out of range", (long long)id);
-        out[id].isEvidence = (int8_t)r[8];
-        out[id].initialValue = (int64_t)be64(r + 9);
-        out[id].dataType = (int16_t)be16(r + 17);
-        out[id].cardinality = (int64_t)be64(r + 19);
-    }
+    std::atomic<int64_t> bad(-1);
+    host_threads(n_variable, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            const uint8_t *r = data + 27 * i;
+            int64_t id = (int64_t)be64(r);
+            if (id < 0 || id >= n_variable) { bad.store(id); continue; }
+            out[id].isEvidence = (int8_t)r[8];
+            out[id].initialValue = (int64_t)be64(r + 9);
+            out[id].dataType = (int16_t)be16(r + 17);
+            out[id].cardinality = (int64_t)be64(r + 19);
+        }
+    });
+    if (bad.load() != -1) NB_FAIL(NB_ERR_INVALID, "graph.variables: variableId %lld out of range", (long long)bad.load());
     return NB_OK;
 }
 
@@ -468,48 +477,67 @@ extern "C" int nb_load_domains(const uint8_t *data, int64_t n_bytes, uint8_t *do
     return NB_OK;
 }
 
-// dataloading.py:190-237: sequential variable-length records
+// dataloading.py:190-237: variable-length records
 // (int16 func, int64 arity, arity x (int64 vid, int64 value), int64 weightId, f64 feature);
 // values of variables with an explicit domain are translated to dense indices by
 // binary search over vmap[].value (np.searchsorted, side='left').
+// Two passes: a sequential scan that only reads the arity of every record (record start and
+// ftv_offset are running sums: 26 + 16 arity bytes and arity entries per record), then the bodies
+// are decoded by host threads.  Same output as the reference's one-pass loop.
 extern "C" int nb_load_factors(const uint8_t *data, int64_t n_bytes, int64_t n_factor, nb_factor_rec *factor,
                                nb_ftv_rec *fmap, int64_t n_fmap, const uint8_t *domain_mask,
                                const nb_variable_rec *variable, int64_t n_variable, const nb_vtf_rec *vmap,
                                int64_t n_vmap)
 {
-    int64_t idx = 0, e = 0;
-    for (int64_t i = 0; i < n_factor; i++) {
-        if (idx + 10 > n_bytes) NB_FAIL(NB_ERR_INVALID, "graph.factors: truncated at factor %lld", (long long)i);
-        factor[i].factorFunction = (int16_t)be16(data + idx);
-        int64_t arity = (int64_t)be64(data + idx + 2);
-        idx += 10;
-        if (arity < 0 || idx + 16 * arity + 16 > n_bytes || e + arity > n_fmap)
-            NB_FAIL(NB_ERR_INVALID, "graph.factors: factor %lld has bad arity %lld", (long long)i, (long long)arity);
-        factor[i].arity = arity;
-        factor[i].ftv_offset = e;
-        for (int64_t k = 0; k < arity; k++) {
-            int64_t vid = (int64_t)be64(data + idx);
-            int64_t val = (int64_t)be64(data + idx + 8);
-            idx += 16;
-            if (vid < 0 || vid >= n_variable) NB_FAIL(NB_ERR_INVALID, "graph.factors: factor %lld references variable %lld", (long long)i, (long long)vid);
-            if (domain_mask && domain_mask[vid]) {
-                int64_t s = variable[vid].vtf_offset, n = variable[vid].cardinality;
-                if (s < 0 || s + n > n_vmap) NB_FAIL(NB_ERR_INVALID, "graph.factors: domain of variable %lld out of range", (long long)vid);
-                int64_t lo = 0, hi = n;
-                while (lo < hi) {
-                    int64_t mid = (lo + hi) / 2;
-                    if (vmap[s + mid].value < val) lo = mid + 1; else hi = mid;
-                }
-                val = lo;
-            }
-            fmap[e + k].vid = vid;
-            fmap[e + k].dense_equal_to = val;
+    std::vector<int64_t> start((size_t)n_factor + 1);
+    {
+        int64_t idx = 0, e = 0;
+        for (int64_t i = 0; i < n_factor; i++) {
+            if (idx + 10 > n_bytes) NB_FAIL(NB_ERR_INVALID, "graph.factors: truncated at factor %lld", (long long)i);
+            const int64_t arity = (int64_t)be64(data + idx + 2);
+            if (arity < 0 || arity > n_fmap || idx + 26 + 16 * arity > n_bytes || e + arity > n_fmap)
+                NB_FAIL(NB_ERR_INVALID, "graph.factors: factor %lld has bad arity %lld", (long long)i, (long long)arity);
+            start[(size_t)i] = idx;
+            factor[i].arity = arity;
+            factor[i].ftv_offset = e;
+            idx += 26 + 16 * arity;
+            e += arity;
         }
-        e += arity;
-        factor[i].weightId = (int64_t)be64(data + idx);
-        factor[i].featureValue = be_f64(data + idx + 8);
-        idx += 16;
+        start[(size_t)n_factor] = idx;
     }
+    std::atomic<int64_t> bad_factor(-1), bad_vid(0);
+    std::atomic<int> bad_kind(0);
+    host_threads(n_factor, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            const uint8_t *r = data + start[(size_t)i];
+            const int64_t arity = factor[i].arity, e = factor[i].ftv_offset;
+            factor[i].factorFunction = (int16_t)be16(r);
+            r += 10;
+            for (int64_t k = 0; k < arity; k++, r += 16) {
+                int64_t vid = (int64_t)be64(r);
+                int64_t val = (int64_t)be64(r + 8);
+                if (vid < 0 || vid >= n_variable) { bad_factor.store(i); bad_vid.store(vid); bad_kind.store(1); vid = 0; val = 0; }
+                else if (domain_mask && domain_mask[vid]) {
+                    int64_t s = variable[vid].vtf_offset, n = variable[vid].cardinality;
+                    if (s < 0 || s + n > n_vmap) { bad_factor.store(i); bad_vid.store(vid); bad_kind.store(2); n = 0; }
+                    int64_t lo = 0, hi = n;
+                    while (lo < hi) {
+                        int64_t mid = (lo + hi) / 2;
+                        if (vmap[s + mid].value < val) lo = mid + 1; else hi = mid;
+                    }
+                    val = lo;
+                }
+                fmap[e + k].vid = vid;
+                fmap[e + k].dense_equal_to = val;
+            }
+            factor[i].weightId = (int64_t)be64(r);
+            factor[i].featureValue = be_f64(r + 8);
+        }
+    });
+    if (bad_kind.load() == 1)
+        NB_FAIL(NB_ERR_INVALID, "graph.factors: factor %lld references variable %lld", (long long)bad_factor.load(), (long long)bad_vid.load());
+    if (bad_kind.load() == 2)
+        NB_FAIL(NB_ERR_INVALID, "graph.factors: domain of variable %lld out of range", (long long)bad_vid.load());
     return NB_OK;
 }
 

@@ -62,7 +62,21 @@ struct LearnArgs {
     // reduction by weight id: three rotating global tables [3][W] (cell c uses c % 3)
     nb_fix_t *g_grad;
     uint32_t *g_cnt;
+    // NUMBSKULL_B200_LEARN_TRACE=1: per-phase nanoseconds summed over CTAs and cells
+    // [0] range lookup + zeroing  [1] truth-table rows  [2] thread rows  [3] warp rows  [4] flush
+    // [5] grid barrier  [6] apply  [7] cells processed  [8] sum over cells of the slowest CTA's work time
+    unsigned *bar;            // grid barrier state {arrivals, generation}
+    unsigned long long *trace;
+    unsigned long long *trace_cell;   // [n cells] scratch: max work time of the cell over the CTAs
+    unsigned long long *trace_cta;    // [grid][3] per-CTA sums: truth-table rows, thread rows, whole work phase
 };
+
+__device__ __forceinline__ unsigned long long nb_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Where the cells' rows are: block b of n_blocks covers the units [T b / nb, T (b + 1) / nb) of
 // T = n_win * k_sub units; unit u is sub-range (u % k_sub) of k_sub of id window u / k_sub.  Inside a
@@ -159,7 +173,7 @@ __device__ __forceinline__ uint32_t nb_cnt_inc(const LearnArgs &a, uint32_t id)
 
 // second pass over a row: gradient of every visited incidence with a learnable weight
 template <bool WIDE, bool SMEM>
-__device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, uint32_t meta, int ev, int prop,
+__device__ __noinline__ void nb_row_gradient(const NbRow &r, int len, uint32_t self, uint32_t meta, int ev, int prop,
                                        const LearnArgs &a, uint32_t cnt_inc, const LearnCtx<SMEM> &ctx,
                                        int first_inc, int inc_stride, const uint2 *inc_list, int n_inc)
 {
@@ -198,7 +212,7 @@ __device__ inline void nb_row_gradient(const NbRow &r, int len, uint32_t self, u
 // thread path: generic rows (GEN class) and categorical record rows (CAT class), one row per thread
 // ---------------------------------------------------------------------------
 template <bool WIDE, bool SMEM>
-__device__ inline void learn_thread_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg0, int end0, int beg1, int end1)
+__device__ __noinline__ void learn_thread_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg0, int end0, int beg1, int end1)
 {
     const int64_t n0 = end0 - beg0, ntot = n0 + (end1 - beg1);
     const CtxWts<SMEM> wts{ctx};
@@ -266,7 +280,7 @@ __device__ inline void nb_warp_energies_l(const NbRow &r, const uint2 *inc, int 
 }
 
 template <bool WIDE, bool SMEM>
-__device__ inline int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
+__device__ __noinline__ int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
                                        const nb_val_t *vals, const LearnCtx<SMEM> &ctx, double *se, NbUniforms &rng)
 {
     const int card = NB_META_CARD(meta);
@@ -285,7 +299,7 @@ __device__ inline int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_i
 }
 
 template <bool WIDE, bool SMEM>
-__device__ inline void learn_warp_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, double *s_e, int wbeg, int wend)
+__device__ __noinline__ void learn_warp_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, double *s_e, int wbeg, int wend)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t wr = (int64_t)wbeg + blockIdx.x * (int64_t)NB_LWARPS + warp; wr < wend;
@@ -320,17 +334,26 @@ __device__ inline void learn_warp_rows(const LearnArgs &a, const LearnCtx<SMEM> 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int nb_ldv(const nb_val_t *v, uint32_t i) { return (int)__ldcg(v + i); }
 
+// (two id ranges per call: the cell's PAIR rows and its FAST rows -- one copy of the code)
 template <bool SMEM>
-__device__ inline void learn_tt_slices(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg, int end, uint32_t kfree,
-                                       uint32_t kevid, uint32_t ktrunc)
+__device__ __noinline__ void learn_tt_slices(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg0, int end0, int beg1, int end1,
+                                             uint32_t kfree, uint32_t kevid, uint32_t ktrunc, int rot)
 {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = blockIdx.x * (int64_t)NB_LWARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
     const nb_val_t *vF = a.val_free, *vE = a.val_evid;
+    const int64_t s0b = beg0 >> 5, s0e = end0 > beg0 ? (((int64_t)end0 + 31) >> 5) : s0b;
+    const int64_t s1b = beg1 >> 5, s1e = end1 > beg1 ? (((int64_t)end1 + 31) >> 5) : s1b;
+    const int64_t ns0 = s0e - s0b, ns = ns0 + (s1e - s1b);
 
-    for (int64_t s = (beg >> 5) + warp_global; s < (((int64_t)end + 31) >> 5); s += n_warps) {
+    int64_t it_first = warp_global + rot;
+    if (it_first >= n_warps) it_first -= n_warps;
+    for (int64_t it = it_first; it < ns; it += n_warps) {
+        const bool first = it < ns0;
+        const int64_t s = first ? s0b + it : s1b + (it - ns0);
+        const int beg = first ? beg0 : beg1, end = first ? end0 : end1;
         const int64_t nid = (s << 5) + lane;
         const uint32_t meta = a.vmeta[nid];
         const uint32_t rid = a.rng_id[nid];
@@ -414,15 +437,19 @@ __device__ inline void learn_tt_slices(const LearnArgs &a, const LearnCtx<SMEM> 
 // Same algorithm, one WARP per row with the lanes striding over the row's quads: used when the
 // rows are long (data-programming models: a label variable with ~100 labelling functions).
 template <bool SMEM>
-__device__ inline void learn_tt_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg, int end, uint32_t kfree,
-                                     uint32_t kevid, uint32_t ktrunc)
+__device__ __noinline__ void learn_tt_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg0, int end0, int beg1, int end1,
+                                           uint32_t kfree, uint32_t kevid, uint32_t ktrunc, int rot)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = blockIdx.x * (int64_t)NB_LWARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
     const nb_val_t *vF = a.val_free, *vE = a.val_evid;
+    const int64_t n0 = max(end0 - beg0, 0), ntot = n0 + max(end1 - beg1, 0);
 
-    for (int64_t nid = (int64_t)beg + warp_global; nid < end; nid += n_warps) {
+    int64_t it_first = warp_global + rot;
+    if (it_first >= n_warps) it_first -= n_warps;          // rot < n_warps
+    for (int64_t it = it_first; it < ntot; it += n_warps) {
+        const int64_t nid = it < n0 ? beg0 + it : beg1 + (it - n0);
         const uint32_t meta = a.vmeta[nid];
         const int evid = NB_META_EVID(meta);
         if (!NB_META_VALID(meta) || evid == 4) continue;                         // learning.py:24-26
@@ -469,11 +496,35 @@ __device__ inline void learn_tt_rows(const LearnArgs &a, const LearnCtx<SMEM> &c
             ctx.add_int(__ldg(wp + (size_t)j * 32), fF - fE, cinc);
         }
     }
+    // per-warp arrival at the end of the function, for the CTA at rotated position 0
+
 }
 
 // ---------------------------------------------------------------------------
 // the persistent epoch kernel
 // ---------------------------------------------------------------------------
+// Grid barrier (the kernel is launched cooperatively: all CTAs are resident).  CTAs that wait back
+// off with nanosleep instead of polling flat out: in a cell with fewer rows than warps most CTAs
+// arrive at once and 100+ pollers hammering one L2 line slowed the CTAs still working.
+__device__ __forceinline__ void nb_grid_sync(unsigned *bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned gen = *(volatile unsigned *)(bar + 1);      // generation BEFORE arriving
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            *(volatile unsigned *)bar = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            unsigned ns = 20;
+            while (*(volatile unsigned *)(bar + 1) == gen) { __nanosleep(ns); if (ns < 320) ns *= 2; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 template <bool WIDE, bool SMEM>
 __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, CellPlan plan, int cell_beg, int cell_end,
                                                                   int only_color)
@@ -481,7 +532,6 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
     extern __shared__ unsigned char s_raw[];
     __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
     __shared__ int s_rng[2 * NB_N_CLASSES];
-    cg::grid_group grid = cg::this_grid();
     const int W = a.W;
     // shared layout (SMEM): weights f64 [W] | fixed-point sums i64 [W] | integer sums i32 [W] | counts u32 [W]
     double *s_w = (double *)s_raw;
@@ -501,6 +551,8 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
         // caller drives the colours itself (partitioned graphs) and `cell` is the block
         const int block = only_color >= 0 ? cell : cell / plan.n_colors;
         const int color = only_color >= 0 ? only_color : cell % plan.n_colors;
+        const bool tr = a.trace != nullptr && threadIdx.x == 0;
+        unsigned long long t0 = tr ? nb_now() : 0ull, t1;
         // five threads look the cell's id ranges up (64-bit divisions and dependent loads: not per thread)
         __syncthreads();
         if (threadIdx.x < NB_N_CLASSES) nb_plan_range(plan, (int)threadIdx.x, color, block, s_rng[2 * threadIdx.x], s_rng[2 * threadIdx.x + 1]);
@@ -532,16 +584,28 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
                 z_cn[w] = 0u;
             }
         }
-        const bool long_rows = plan.long_rows[color] != 0;
-        if (long_rows) {
-            if (pe > pb) learn_tt_rows<SMEM>(a, ctx, pb, pe, kf, ke, kt);
-            if (fe > fb) learn_tt_rows<SMEM>(a, ctx, fb, fe, kf, ke, kt);
-        } else {
-            if (pe > pb) learn_tt_slices<SMEM>(a, ctx, pb, pe, kf, ke, kt);
-            if (fe > fb) learn_tt_slices<SMEM>(a, ctx, fb, fe, kf, ke, kt);
+        const unsigned long long t_begin = t0;
+#define NB_TRACE(i) if (a.trace != nullptr) { __syncthreads(); if (tr) { t1 = nb_now(); atomicAdd(a.trace + (i), t1 - t0); \
+            if ((i) == 1 || (i) == 2) a.trace_cta[3 * blockIdx.x + (i) - 1] += t1 - t0; t0 = t1; } }
+        NB_TRACE(0)
+        if (pe > pb || fe > fb) {
+            // One warp per row when the rows are long -- or when the cell holds fewer truth-table rows
+            // than the grid has warps, whatever their length: a thread walking a 100-incidence row on
+            // its own is a chain of 100 dependent loads (the 1 % of label variables that the
+            // colouring puts with the labelling functions kept one warp busy for 150 us per cell
+            // while 2367 others waited at the barrier).
+            const int64_t n_warps = (int64_t)gridDim.x * NB_LWARPS;
+            const bool by_row = plan.long_rows[color] != 0 || (int64_t)(pe - pb) + (fe - fb) <= 2 * n_warps;
+            // the first row of the cell goes to a different warp every cell: the idle CTAs rotate
+            const int rot = (int)(((int64_t)k * 37 * NB_LWARPS) % n_warps);
+            if (by_row) learn_tt_rows<SMEM>(a, ctx, pb, pe, fb, fe, kf, ke, kt, rot);
+            else learn_tt_slices<SMEM>(a, ctx, pb, pe, fb, fe, kf, ke, kt, rot);
         }
+        NB_TRACE(1)
         if (te > tb || ce > cb) learn_thread_rows<WIDE, SMEM>(a, ctx, cb, ce, tb, te);
+        NB_TRACE(2)
         if (we > wb) learn_warp_rows<WIDE, SMEM>(a, ctx, s_e[threadIdx.x >> 5], wb, we);
+        NB_TRACE(3)
 
         if (SMEM) {
             // flush this CTA's tables: one integer atomic per touched weight
@@ -554,8 +618,10 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
                 s_gf[w] = 0; s_gi[w] = 0; s_cnt[w] = 0u;
             }
         }
-        __threadfence();
-        grid.sync();
+        NB_TRACE(4)
+        if (tr) { atomicMax(a.trace_cell + (cell - cell_beg), t0 - t_begin); a.trace_cta[3 * blockIdx.x + 2] += t0 - t_begin; }
+        nb_grid_sync(a.bar);     // (fences the CTAs' writes: values, tables)
+        NB_TRACE(5)
         if (SMEM) {
             // every CTA applies the same sums to its own copy of the weights; CTA 0 publishes them
             for (int w = threadIdx.x; w < W; w += blockDim.x) {
@@ -577,9 +643,11 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
                     __stcg(a.weight + w, nb_apply_update(__ldcg(a.weight + w), (double)Gi * (1.0 / NB_GRAD_UNIT), n,
                                                         a.regularization, a.step, a.reg_param, a.truncation));
             }
-            __threadfence();
-            grid.sync();
+            nb_grid_sync(a.bar);
         }
+        NB_TRACE(6)
+        if (tr && blockIdx.x == 0) { atomicAdd(a.trace + 7, 1ull); atomicAdd(a.trace + 8, a.trace_cell[cell - cell_beg]); }
+#undef NB_TRACE
         k++;
     }
 }
@@ -638,7 +706,7 @@ static LearnArgs learn_args(nb_graph *g)
     a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
     a.rng_id = g->d_rng_id; a.vinit = g->d_vinit; a.val_free = g->d_val[0]; a.val_evid = g->d_val[1];
     a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
-    a.g_grad = g->d_grad; a.g_cnt = g->d_nvis;
+    a.g_grad = g->d_grad; a.g_cnt = g->d_nvis; a.bar = g->d_learn_bar;
     a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.tt_wid = g->d_tt_wid;
     return a;
 }
@@ -648,6 +716,7 @@ static int ensure_learn_buffers(nb_graph *g)
     if (!g->d_grad) {
         NB_TRY(nb_alloc(g, &g->d_grad, 3 * (size_t)std::max<int64_t>(g->W, 1)));     // three rotating tables, zeroed
         NB_TRY(nb_alloc(g, &g->d_nvis, 3 * (size_t)std::max<int64_t>(g->W, 1)));
+        NB_TRY(nb_alloc(g, &g->d_learn_bar, 64));
     }
     return NB_OK;
 }
@@ -769,11 +838,54 @@ static int launch_cells_t(nb_graph *g, LearnArgs a, CellPlan plan, int cell_beg,
     if (per_sm < 1) NB_FAIL(NB_ERR_CUDA, "the learning kernel does not fit on an SM");
     // all CTAs must be co-resident (grid barrier); two per SM hide each other's latencies
     const int grid = sms * std::min(per_sm, 2);
+    static const bool trace_on = [] { const char *e = getenv("NUMBSKULL_B200_LEARN_TRACE"); return e && atoi(e) != 0; }();
+    unsigned long long *d_trace = nullptr;
+    if (trace_on) {
+        const size_t n = 64 + 3 * 4096 + (size_t)(cell_end - cell_beg);
+        NB_CUDA(cudaMalloc(&d_trace, n * 8));
+        NB_CUDA(cudaMemsetAsync(d_trace, 0, n * 8, g->stream));
+        a.trace = d_trace;
+        a.trace_cta = d_trace + 64;
+        a.trace_cell = d_trace + 64 + 3 * 4096;
+    }
     NB_CUDA(cudaMemsetAsync(a.g_grad, 0, (size_t)g->W * sizeof(nb_fix_t), g->stream));   // rotating table 0
     NB_CUDA(cudaMemsetAsync(a.g_cnt, 0, (size_t)g->W * sizeof(uint32_t), g->stream));
     void *args[] = {&a, &plan, &cell_beg, &cell_end, &only_color};
     NB_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)grid), dim3(NB_LEARN_THREADS), args, smem, g->stream));
     g->launches++;
+    if (d_trace) {
+        std::vector<unsigned long long> hv(64 + 3 * 4096 + (size_t)std::min(cell_end - cell_beg, 4096));
+        if (false) {}
+        unsigned long long *h = hv.data();
+        NB_CUDA(cudaMemcpyAsync(h, d_trace, hv.size() * 8, cudaMemcpyDeviceToHost, g->stream));
+        NB_CUDA(cudaStreamSynchronize(g->stream));
+        cudaFree(d_trace);
+        {
+            std::vector<std::pair<unsigned long long, int>> tot;
+            for (int b = 0; b < grid && b < 4096; b++) tot.push_back({h[64 + 3 * b + 2], b});
+            std::sort(tot.begin(), tot.end());
+            fprintf(stderr, "[learn trace] per-CTA work (ms): min %.3f (cta %d) median %.3f max %.3f (cta %d); slowest CTAs:",
+                    1e-6 * tot.front().first, tot.front().second, 1e-6 * tot[tot.size() / 2].first, 1e-6 * tot.back().first,
+                    tot.back().second);
+            for (size_t i = tot.size() > 6 ? tot.size() - 6 : 0; i < tot.size(); i++)
+                fprintf(stderr, " %d: tt %.3f thr %.3f all %.3f;", tot[i].second, 1e-6 * h[64 + 3 * tot[i].second],
+                        1e-6 * h[64 + 3 * tot[i].second + 1], 1e-6 * tot[i].first);
+            fprintf(stderr, "\n");
+            {
+                const int nc = std::min(cell_end - cell_beg, 4096), ncol = std::max(plan.n_colors, 1);
+                std::vector<double> sum((size_t)ncol, 0.0), cnt((size_t)ncol, 0.0);
+                for (int c = 0; c < nc; c++) { sum[(size_t)(c % ncol)] += 1e-3 * h[64 + 3 * 4096 + c]; cnt[(size_t)(c % ncol)] += 1; }
+                fprintf(stderr, "[learn trace] slowest CTA's work per cell by colour (us):");
+                for (int c = 0; c < ncol && c < 12; c++) fprintf(stderr, " %.1f", sum[(size_t)c] / std::max(cnt[(size_t)c], 1.0));
+                fprintf(stderr, "\n");
+            }
+        }
+        const double cells = (double)std::max<unsigned long long>(h[7], 1), per = 1e-3 / (cells * grid);
+        fprintf(stderr, "[learn trace] %d CTAs, %.0f cells; us per cell and CTA: lookup %.2f, tt rows %.2f, thread rows %.2f, "
+                        "warp rows %.2f, flush %.2f, barrier wait %.2f, apply %.2f; slowest CTA's work per cell %.2f us\n",
+                grid, cells, h[0] * per, h[1] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per,
+                1e-3 * (double)h[8] / cells);
+    }
     return NB_OK;
 }
 
