@@ -433,6 +433,54 @@ def block_learn(args, local_rank):
     return out
 
 
+def block_c4_strong(args, rank, world, local_rank):
+    """BASELINE config 4 (the 200 M-variable / 1 B-edge KBC graph) partitioned over the ranks: STRONG
+    scaling -- the same graph whatever N.  Every rank generates its owner block on its own
+    (synth.kbc_block: the global graph is never materialised), ghosts are refreshed after every
+    colour.  Returns the block on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from numbskull_b200 import _lib, partition, synth
+    t0 = time.perf_counter()
+    bounds = partition.block_bounds(C4_VARS, world)
+    local = synth.kbc_block(C4_VARS, int(bounds[rank]), int(bounds[rank + 1]), seed=1004)
+    n_ghost = len(local["variable"]) - local["n_owned"]
+    t1 = time.perf_counter()
+    run = partition.PartitionedGibbs(local, C4_VARS, rank, world, local_rank, seed=SEED)
+    del local
+    t2 = time.perf_counter()
+    fg = run.fg
+    dev = Dev(fg, world)
+    fg._sync_device(0, 0, evid=False)
+    run.sweeps(2, True, True)
+    steps = max(3, min(args.steps, 10))
+    ms = dev.timed_blocks(lambda n: run.sweeps(n, False, True), steps, 3)
+    if run.p2p:
+        _lib.check(dev.L.nb_p2p_check(dev.g))
+    med = float(np.median(ms)) / steps
+    tot = torch.tensor([float(fg.color_edges().sum()), float(run.n_owned), float(n_ghost), float(run.halo_bytes_per_sweep),
+                        t1 - t0, t2 - t1], device="cuda", dtype=torch.float64)
+    mx = tot.clone()
+    dist.all_reduce(tot)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        edges = tot[0].item()
+        out = {"workload": "kbc_%d_vars_%d_edges_block_partitioned_over_%d_gpus (BASELINE config 4, strong scaling)"
+                           % (C4_VARS, int(edges), world),
+               "metric": METRIC, "value": edges / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "scaling": "strong",
+               "steps": steps, "timed_blocks_ms": ms, "colors": run.n_colors, "phases_per_sweep": run.n_phases,
+               "ghost_copies_total": int(tot[2].item()), "ghost_copies_per_owned_variable": tot[2].item() / max(tot[1].item(), 1),
+               "halo_values_per_sweep_total": int(tot[3].item()), "halo_values_per_sweep_max_rank": int(mx[3].item()),
+               "transport": "NVLink peer stores + in-kernel flag barrier" if run.p2p else "NCCL point-to-point",
+               "boundary_interior_split": bool(run.split), "jp_rounds": run.jp_rounds,
+               "build_s": {"generate_block_max": round(mx[4].item(), 1), "partitioned_build_max": round(mx[5].item(), 1)},
+               "limiting_phase": "per colour: boundary kernel + halo push (%d values per rank and sweep at most) + interior "
+                                 "kernel; %d phases of launch + flag latency per sweep" % (int(mx[3].item()), run.n_phases)}
+    run.close()
+    return out
+
+
 def p2p_identity_check(rank, world, local_rank):
     """Before timing: a (256*world) x 256 strip problem sampled partitioned (this launch, the same
     transport the timed sweeps use) and unpartitioned (every rank, its own GPU) must give the same
@@ -600,6 +648,16 @@ def run_ours(args):
             except Exception as exc:  # noqa: BLE001
                 learn = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
+    c4s = None
+    if world > 1 and "c4" in workloads:
+        runner.close()
+        try:
+            c4s = block_c4_strong(args, rank, world, local_rank)
+        except Exception as exc:  # noqa: BLE001
+            c4s = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+            import traceback
+            traceback.print_exc()
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -639,6 +697,8 @@ def run_ours(args):
     if identical is not None:
         line["p2p_bit_identical"] = identical[0]
         line["p2p_transport"] = {"peer_stores": identical[1], "boundary_interior_split": identical[2]}
+    if c4s is not None:
+        line["c4_strong"] = c4s
     if c4 is not None:
         line["c4"] = c4
     if learn is not None:

@@ -165,6 +165,10 @@ int nb_set_var_values(nb_graph *g, int chain, const int64_t *values);
 int nb_get_var_values(nb_graph *g, int chain, int64_t *values);
 int nb_set_weights(nb_graph *g, const double *weights);
 int nb_get_weights(nb_graph *g, double *weights);
+/* device-to-device copies of the weight table on the graph's stream (multi-GPU learning: the
+ * per-epoch weight-delta all-reduce, numbskull_master.py:223-224, never touches the host) */
+int nb_get_weights_dev(nb_graph *g, double *dev_weights);
+int nb_set_weights_dev(nb_graph *g, const double *dev_weights);
 int nb_reset_counts(nb_graph *g);
 /* accumulate != 0: counts[i] += device tally (the reference's count is cumulative,
  * factorgraph.py:172-173); else counts[i] = device tally. */

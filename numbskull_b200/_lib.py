@@ -75,6 +75,8 @@ SIGNATURES = {
     "nb_get_var_values": (C.c_int, [_P, C.c_int, _P]),
     "nb_set_weights": (C.c_int, [_P, _P]),
     "nb_get_weights": (C.c_int, [_P, _P]),
+    "nb_get_weights_dev": (C.c_int, [_P, _P]),
+    "nb_set_weights_dev": (C.c_int, [_P, _P]),
     "nb_reset_counts": (C.c_int, [_P]),
     "nb_get_counts": (C.c_int, [_P, _P, C.c_int]),
     "nb_get_counts_marginals": (C.c_int, [_P, _P, C.c_int, _P, _DBL]),

@@ -234,13 +234,16 @@ static int download_chunks(nb_graph *g, const void *d_src, int64_t n, int elem)
     return NB_OK;
 }
 
+// An out-of-range value is an error for an evidence variable; for a variable that is sampled
+// anyway (or a ghost, refreshed by its owner) the reference simply overwrites it at the first
+// sample (load_domains leaves a raw initialValue that is not in the explicit domain): mapped to 0.
 __global__ void k_scatter_values_u8(int64_t V, const uint8_t *in, const int32_t *old2new, const int32_t *v_card,
-                                    nb_val_t *val, int *bad)
+                                    const int8_t *v_evid, nb_val_t *val, int *bad)
 {
     int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (v >= V) return;
     int x = in[v];
-    if (x >= v_card[v]) { *bad = 1; x = 0; }
+    if (x >= v_card[v]) { if (v_evid[v] == 1) *bad = 1; x = 0; }
     val[old2new[v]] = (nb_val_t)x;
 }
 
@@ -265,10 +268,9 @@ extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
         int bad = 0;
         for (int64_t i = a; i < b; i++) {
             int64_t x = values[i];
-            bad |= (x < 0) | (x > NB_MAX_CARD);
-            stage[i] = (uint8_t)x;
+            stage[i] = (x < 0 || x > NB_MAX_CARD) ? (uint8_t)NB_MAX_CARD : (uint8_t)x;   // 255 >= every cardinality: judged on the device
         }
-        if (bad) out_of_range.store(1);
+        (void)bad;
         return cudaMemcpyAsync((uint8_t *)g->d_xfer + a, stage + a, (size_t)(b - a), cudaMemcpyHostToDevice, g->stream);
     });
     if (rc != NB_OK || out_of_range.load()) {
@@ -279,11 +281,11 @@ extern "C" int nb_set_var_values(nb_graph *g, int chain, const int64_t *values)
     int *d_bad = (int *)((char *)g->d_xfer + (((size_t)V + 15) & ~(size_t)15));
     NB_CUDA(cudaMemsetAsync(d_bad, 0, 4, g->stream));
     k_scatter_values_u8<<<grid_for(V), 256, 0, g->stream>>>(V, (const uint8_t *)g->d_xfer, g->d_old2new, g->d_v_card,
-                                                            g->d_val[chain], d_bad);
+                                                            g->d_v_evid, g->d_val[chain], d_bad);
     int bad = 0;
     NB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
-    if (bad) NB_FAIL(NB_ERR_INVALID, "var_value holds entries outside [0, cardinality)");
+    if (bad) NB_FAIL(NB_ERR_INVALID, "var_value of an evidence variable lies outside [0, cardinality)");
     return NB_OK;
 }
 
@@ -327,6 +329,21 @@ extern "C" int nb_get_weights(nb_graph *g, double *weights)
     NB_CUDA(cudaSetDevice(g->device));
     NB_CUDA(cudaMemcpyAsync(weights, g->d_weight, (size_t)g->W * 8, cudaMemcpyDeviceToHost, g->stream));
     NB_CUDA(cudaStreamSynchronize(g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_get_weights_dev(nb_graph *g, double *dev_weights)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaMemcpyAsync(dev_weights, g->d_weight, (size_t)g->W * 8, cudaMemcpyDeviceToDevice, g->stream));
+    return NB_OK;
+}
+
+extern "C" int nb_set_weights_dev(nb_graph *g, const double *dev_weights)
+{
+    NB_CUDA(cudaSetDevice(g->device));
+    NB_CUDA(cudaMemcpyAsync(g->d_weight, dev_weights, (size_t)g->W * 8, cudaMemcpyDeviceToDevice, g->stream));
+    g->weights_version++;
     return NB_OK;
 }
 

@@ -723,11 +723,14 @@ static int extract_and_upload(nb_graph *g, const nb_graph_desc *d)
                 const nb_variable_rec &r = d->variable[i];
                 if (r.dataType != 0 && r.dataType != 1) { fail("variable dataType must be 0 or 1", i); continue; }
                 if (r.cardinality < 1 || r.cardinality > NB_MAX_CARD) { fail("variable cardinality outside [1, 255]", i); continue; }
-                if (r.initialValue < 0 || r.initialValue >= r.cardinality) { fail("variable initialValue outside [0, cardinality)", i); continue; }
+                // the reference accepts such graphs: a sampled variable's value is overwritten at its first
+                // sample (load_domains can leave a raw initialValue that is not in the domain)
+                const bool init_ok = r.initialValue >= 0 && r.initialValue < r.cardinality;
+                if (!init_ok && r.isEvidence == 1) { fail("evidence variable with initialValue outside [0, cardinality)", i); continue; }
                 int64_t nb = r.dataType == 0 ? 1 : r.cardinality;
                 if (r.vtf_offset < 0 || r.vtf_offset + nb > NV) { fail("variable vtf_offset out of range", i); continue; }
                 v_evid[i] = r.isEvidence; v_dtype[i] = (int8_t)r.dataType;
-                v_card[i] = (int32_t)r.cardinality; v_init[i] = (int32_t)r.initialValue; v_vtf[i] = r.vtf_offset;
+                v_card[i] = (int32_t)r.cardinality; v_init[i] = init_ok ? (int32_t)r.initialValue : 0; v_vtf[i] = r.vtf_offset;
                 mc = std::max(mc, (int)r.cardinality);
                 cat |= r.dataType == 1;
             }

@@ -45,9 +45,9 @@ __device__ __forceinline__ void nb_wait_halo(const SweepArgs &a)
             if (clock64() - t0 > 20000000000ll) { *a.w_error = 1; break; }
         }
     }
-    // the peer fenced its stores before the flag store, both land in this GPU's L2; this kernel has
-    // not touched the ghost slots yet (L1 is clean at launch), so ordering the loads after the
-    // flag read is all that is needed
+    // the peer fenced its stores before the flag store; the acquire side is a system-scope fence in
+    // the waiting threads before anybody reads a ghost slot
+    __threadfence_system();
     __syncthreads();
 }
 

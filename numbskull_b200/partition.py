@@ -78,6 +78,98 @@ def extract_local(weight, variable, factor, fmap, lo, hi):
                 n_owned=int(n_owned))
 
 
+def extract_local_by_owner(weight, variable, factor, fmap, owner, rank):
+    """:func:`extract_local` for an arbitrary placement: ``owner[v]`` is the rank that owns global
+    variable ``v`` (an imported partition, e.g. :func:`owners_from_salt_keys`, or a locality-aware
+    one, :func:`locality_owners`).  Owned variables keep their relative order; ghosts follow in
+    increasing global id with ``isEvidence = 4``."""
+    owner = np.asarray(owner)
+    assert len(owner) == len(variable)
+    arity = factor["arity"].astype(np.int64)
+    fid_of_entry = np.repeat(np.arange(len(factor), dtype=np.int64), arity)
+    entry = np.repeat(factor["ftv_offset"].astype(np.int64), arity) + \
+        (np.arange(len(fid_of_entry), dtype=np.int64) - np.repeat(np.cumsum(arity) - arity, arity))
+    vids = fmap["vid"][entry].astype(np.int64)
+    owned_entry = owner[vids] == rank
+    keep_factor = np.zeros(len(factor), bool)
+    keep_factor[fid_of_entry[owned_entry]] = True
+    keep_entry = keep_factor[fid_of_entry]
+
+    loc_factor = factor[keep_factor].copy()
+    loc_arity = loc_factor["arity"].astype(np.int64)
+    off = np.zeros(len(loc_factor), np.int64)
+    if len(loc_factor) > 1:
+        np.cumsum(loc_arity[:-1], out=off[1:])
+    loc_factor["ftv_offset"] = off
+    loc_entries = entry[keep_entry]
+    loc_vids = vids[keep_entry]
+
+    owned = np.nonzero(owner == rank)[0].astype(np.int64)
+    ghosts = np.unique(loc_vids[owner[loc_vids] != rank])
+    n_owned = len(owned)
+    global_vid = np.concatenate((owned, ghosts))
+    loc_variable = variable[global_vid].copy()
+    loc_variable["isEvidence"][n_owned:] = 4
+    loc_variable["vtf_offset"] = 0
+
+    loc_fmap = np.zeros(len(loc_entries), FactorToVar)
+    mine = owner[loc_vids] == rank
+    loc_fmap["vid"] = np.where(mine, np.searchsorted(owned, loc_vids), n_owned + np.searchsorted(ghosts, loc_vids))
+    loc_fmap["dense_equal_to"] = fmap["dense_equal_to"][loc_entries]
+    return dict(weight=weight.copy(), variable=loc_variable, factor=loc_factor, fmap=loc_fmap,
+                domain_mask=np.zeros(len(loc_variable), np.bool_), global_vid=global_vid,
+                n_owned=int(n_owned), owner=owner)
+
+
+def owners_from_salt_keys(keys, world):
+    """Placement from the reference's semantic-partition keys (salt/src/messages.py:175-179,229-236:
+    the first character of ``partition_key`` is the partition type, the master's SQL filter
+    ``numbskull_master.py:329-332`` keeps 'A', 'B', 'D', 'F' rows; minion ``i`` gets the rows whose
+    key carries its id).  'A' / 'B' variables belong to the master = rank 0; 'C<i>' / 'D<i>' (and any
+    other keyed type) to minion ``i`` = rank ``1 + i mod (world - 1)``; the variable still appears as
+    a ghost wherever one of its factors lives, which is what the visible-to-both types 'B' / 'D'
+    ask for.  ``keys``: sequence of str / bytes, e.g. ``["A", "B", "C0", "D1"]``."""
+    out = np.zeros(len(keys), np.int32)
+    for i, k in enumerate(keys):
+        k = k.decode() if isinstance(k, bytes) else str(k)
+        t, rest = k[:1].upper(), k[1:].lstrip("uU")
+        if t in ("A", "B") or world == 1:
+            out[i] = 0
+        else:
+            idx = int(rest) if rest.isdigit() else 0
+            out[i] = 1 + idx % (world - 1)
+    return out
+
+
+def locality_owners(variable, factor, fmap, world):
+    """Locality-aware placement for graphs whose variable ids carry no locality: a reverse
+    Cuthill-McKee ordering of the variable graph (variables adjacent iff they share a factor; every
+    factor contributes a path over its members) cut into ``world`` contiguous pieces of equal
+    size.  The role METIS plays in the reference (salt/src/messages.py:591-640 find_metis_parts);
+    host-side scipy, meant for graphs up to a few 10^7 edges."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    n = len(variable)
+    arity = factor["arity"].astype(np.int64)
+    off = factor["ftv_offset"].astype(np.int64)
+    fid = np.repeat(np.arange(len(factor), dtype=np.int64), arity)
+    entry = np.repeat(off, arity) + (np.arange(len(fid), dtype=np.int64) - np.repeat(np.cumsum(arity) - arity, arity))
+    vids = fmap["vid"][entry].astype(np.int64)
+    same = fid[1:] == fid[:-1]
+    a, b = vids[:-1][same], vids[1:][same]
+    g = sp.coo_matrix((np.ones(len(a), np.int8), (a, b)), shape=(n, n)).tocsr()
+    g = g + g.T
+    order = np.asarray(reverse_cuthill_mckee(g.tocsr(), symmetric_mode=True), np.int64)
+    owner = np.empty(n, np.int32)
+    owner[order] = (np.arange(n, dtype=np.int64) * world // max(n, 1)).astype(np.int32)
+    return owner
+
+
+def ghost_fraction(local):
+    """Ghost copies per owned variable of one rank's share (what the halo exchange moves)."""
+    return (len(local["variable"]) - local["n_owned"]) / max(1, local["n_owned"])
+
+
 def ising_strip(rows, cols, rank, world, coupling=0.1):
     """Rank ``rank``'s share of a (rows*world) x cols Ising grid (BASELINE config 2
     shape, weak scaling): it owns ``rows`` grid rows and sees the row above and
@@ -95,30 +187,61 @@ def ising_strip(rows, cols, rank, world, coupling=0.1):
     return local, (rows * world) * cols
 
 
+# --------------------------------------------------------------------------- plumbing
+def exchange_arrays(send, rank, world, device, group=None):
+    """All-to-all of variable-length int64 arrays: ``send[p]`` goes to rank p; returns the list of
+    arrays received from every rank.  Counts travel in one all_gather, payloads point-to-point
+    (tensors, not pickled Python lists: at the 1 B-edge scale a rank has 10^7 ghosts)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [np.asarray(send[0], np.int64)]
+    stage = dist.get_backend(group) == "gloo"
+    dev = torch.device("cpu") if stage else device
+    counts = torch.tensor([len(x) for x in send], dtype=torch.int64, device=dev)
+    allc = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(allc, counts, group=group)
+    recv_counts = [int(allc[p][rank].item()) for p in range(world)]
+    sbufs = [torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(dev) for x in send]
+    rbufs = [torch.empty(n, dtype=torch.int64, device=dev) for n in recv_counts]
+    ops = []
+    for p in range(world):
+        if p == rank:
+            continue
+        if len(send[p]):
+            ops.append(dist.P2POp(dist.isend, sbufs[p], p, group=group))
+        if recv_counts[p]:
+            ops.append(dist.P2POp(dist.irecv, rbufs[p], p, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if not stage:
+        torch.cuda.synchronize()
+    out = [b.cpu().numpy() for b in rbufs]
+    out[rank] = np.asarray(send[rank], np.int64)
+    return out
+
+
 # --------------------------------------------------------------------------- halo plan
 class HaloPlan(object):
     """Who needs whose values.  ``send_ids[p]`` are local ids of owned variables
     that rank p holds as ghosts, ``recv_ids[p]`` the local ids of this rank's
     ghosts owned by p, in matching order."""
 
-    def __init__(self, global_vid, n_owned, bounds, rank, world, group=None):
-        import torch.distributed as dist
+    def __init__(self, global_vid, n_owned, owner_of, rank, world, group=None, device="cpu"):
         self.rank, self.world = rank, world
         ghosts = np.asarray(global_vid[n_owned:], np.int64)
-        owner = np.searchsorted(bounds, ghosts, side="right") - 1
+        owned = np.asarray(global_vid[:n_owned], np.int64)          # ascending global ids
+        owner = np.asarray(owner_of(ghosts), np.int64)
         requests = [ghosts[owner == p] for p in range(world)]
         self.recv_ids = [np.nonzero(owner == p)[0].astype(np.int64) + n_owned for p in range(world)]
-        if world > 1:
-            gathered = [None] * world
-            dist.all_gather_object(gathered, [r.tolist() for r in requests], group=group)
-        else:
-            gathered = [[r.tolist() for r in requests]]
-        lo = int(bounds[rank])
+        asked_by = exchange_arrays(requests, rank, world, device, group)    # what every rank wants from me
         self.send_ids = []
         for p in range(world):
-            asked = np.asarray(gathered[p][rank], np.int64)
-            assert ((asked >= lo) & (asked < bounds[rank + 1])).all()
-            self.send_ids.append(asked - lo)
+            asked = np.asarray(asked_by[p], np.int64)
+            loc = np.searchsorted(owned, asked)
+            assert len(asked) == 0 or (loc < n_owned).all() and np.array_equal(owned[loc], asked)
+            self.send_ids.append(loc.astype(np.int64))
         assert len(self.send_ids[rank]) == 0 and len(self.recv_ids[rank]) == 0
 
     def restrict(self, keep_local):
@@ -207,9 +330,14 @@ class PartitionedGibbs(object):
         # everything (library kernels and NCCL transport) is ordered on torch's current stream
         _lib.check(L.nb_set_stream(g, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
-        bounds = block_bounds(n_global, world)
-        assert bounds[rank + 1] - bounds[rank] == self.n_owned and self.global_vid[0] == bounds[rank]
-        self.plan = HaloPlan(self.global_vid, self.n_owned, bounds, rank, world, group)
+        if local.get("owner") is not None:                     # imported / locality-aware placement
+            owner_arr = np.asarray(local["owner"])
+            owner_of = lambda gids: owner_arr[gids]               # noqa: E731
+        else:                                                   # contiguous owner blocks
+            bounds = block_bounds(n_global, world)
+            assert bounds[rank + 1] - bounds[rank] == self.n_owned and (self.n_owned == 0 or self.global_vid[0] == bounds[rank])
+            owner_of = lambda gids: np.searchsorted(bounds, gids, side="right") - 1   # noqa: E731
+        self.plan = HaloPlan(self.global_vid, self.n_owned, owner_of, rank, world, group, self.dev)
 
         # ---- distributed Jones-Plassmann ----
         full = Exchange(self.plan.send_ids, self.plan.recv_ids, rank, world, torch.int32, self.dev, group)
@@ -307,9 +435,9 @@ class PartitionedGibbs(object):
         Returns False (after taking part in every collective) if this rank cannot set it up."""
         L, lib, dist, g = self.lib.lib(), self.lib, self.dist, self.fg._g
         world, rank = self.world, self.rank
-        payload = None
+        handles = np.zeros(3 * 64, np.uint8)
+        my_slots, ok = [np.zeros(0, np.int64)] * world, 1
         try:
-            handles = np.zeros(3 * 64, np.uint8)
             lib.check(L.nb_p2p_export(g, world, rank, lib.ptr(handles)))
             # slots (new ids) of my ghosts, per owner, in the order the owner sends them
             my_slots = []
@@ -318,37 +446,35 @@ class PartitionedGibbs(object):
                 out = np.zeros(len(ids), np.int32)
                 if len(ids):
                     lib.check(L.nb_p2p_local_slots(g, lib.ptr(ids), len(ids), lib.ptr(out)))
-                my_slots.append(out.tolist())
-            payload = (handles.tobytes(), my_slots)
+                my_slots.append(out.astype(np.int64))
         except Exception as exc:  # noqa: BLE001
             self.p2p_error = str(exc)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, payload, group=self.group)
-        if any(x is None for x in gathered):
+            ok = 0
+        th = self.torch.from_numpy(np.concatenate((handles, np.array([ok], np.uint8)))).to(self.dev)
+        allh = [self.torch.zeros_like(th) for _ in range(world)]
+        dist.all_gather(allh, th, group=self.group)
+        allh = np.stack([t.cpu().numpy() for t in allh])
+        # p's slots for what I send it, in my send order (tensors: a rank can have 10^7 ghosts)
+        remote_slots = exchange_arrays(my_slots, rank, world, self.dev, self.group)
+        if not allh[:, -1].all():
             return False
         try:
             neigh = [p for p in range(world)
                      if p != rank and (len(self.plan.send_ids[p]) or len(self.plan.recv_ids[p]))]
-            allh = np.zeros((world, 3 * 64), np.uint8)
-            for p in range(world):
-                allh[p] = np.frombuffer(gathered[p][0], np.uint8)
+            hs = np.ascontiguousarray(allh[:, :3 * 64])
             nb_arr = np.asarray(neigh, np.int32)
-            lib.check(L.nb_p2p_open(g, lib.ptr(allh), lib.ptr(nb_arr) if len(neigh) else None, len(neigh)))
-            src, peer, dst, ptr = [], [], [], [0]
-            for c in range(self.n_phases):
-                for p in range(world):
-                    ids = self.plan.send_ids[p]
-                    if not len(ids):
-                        continue
-                    sel = colors[ids] == c
-                    remote = np.asarray(gathered[p][1][rank], np.int32)     # p's slots for what I send it
-                    src.append(ids[sel].astype(np.int32))
-                    dst.append(remote[sel])
-                    peer.append(np.full(int(sel.sum()), p, np.int32))
-                ptr.append(sum(len(x) for x in src))
-            cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.int32), dtype=np.int32)  # noqa: E731
+            lib.check(L.nb_p2p_open(g, lib.ptr(hs), lib.ptr(nb_arr) if len(neigh) else None, len(neigh)))
+            # plan entries grouped by phase: (owned local variable, peer rank, slot in the peer's value array)
+            src = np.concatenate([self.plan.send_ids[p] for p in range(world)] + [np.zeros(0, np.int64)]).astype(np.int64)
+            peer = np.concatenate([np.full(len(self.plan.send_ids[p]), p, np.int64) for p in range(world)] + [np.zeros(0, np.int64)])
+            dst = np.concatenate([np.asarray(remote_slots[p], np.int64) for p in range(world)] + [np.zeros(0, np.int64)])
+            assert len(src) == len(dst)
+            phase = colors[src] if len(src) else np.zeros(0, np.int64)
+            order = np.argsort(phase, kind="stable")
+            ptr = np.zeros(self.n_phases + 1, np.int64)
+            np.cumsum(np.bincount(phase, minlength=self.n_phases)[:self.n_phases], out=ptr[1:])
+            cat = lambda x: np.ascontiguousarray(x[order], dtype=np.int32)  # noqa: E731
             src, peer, dst = cat(src), cat(peer), cat(dst)
-            ptr = np.asarray(ptr, np.int64)
             lib.check(L.nb_p2p_set_plan(g, self.n_phases, lib.ptr(ptr), lib.ptr(src), lib.ptr(peer), lib.ptr(dst)))
         except Exception as exc:  # noqa: BLE001  (CUDA IPC unavailable, peer access denied, ...)
             self.p2p_error = str(exc)
@@ -428,7 +554,7 @@ class PartitionedGibbs(object):
         fg._sync_device(0, 0)
         self.sweeps(burnin_epochs, True, True)
         w_prev = torch.from_numpy(fg._host("weight_value", expose=False)[0].copy()).to(self.dev)
-        w_now = torch.empty_like(w_prev)
+        w_now = torch.empty_like(w_prev)      # the deltas never leave the devices (nb_get/set_weights_dev + NCCL)
         for _ in range(epochs):
             ep = C.c_int64(0)
             lib.check(L.nb_begin_epoch(g, C.byref(ep)))
@@ -452,15 +578,16 @@ class PartitionedGibbs(object):
                             self._exchange(c, 0)
                             self._exchange(c, 1)
             if self.world > 1:
-                torch.cuda.synchronize()
-                host = np.empty(len(fg.weight), np.float64)
-                lib.check(L.nb_get_weights(g, lib.ptr(host)))
-                w_now.copy_(torch.from_numpy(host))
+                lib.check(L.nb_get_weights_dev(g, C.c_void_p(w_now.data_ptr())))
                 delta = w_now - w_prev
-                self.dist.all_reduce(delta, group=self.group)
+                if delta.is_cuda and self.dist.get_backend(self.group) == "gloo":   # 1-GPU tests: gloo moves host memory
+                    d = delta.cpu()
+                    self.dist.all_reduce(d, group=self.group)
+                    delta = d.to(self.dev)
+                else:
+                    self.dist.all_reduce(delta, group=self.group)
                 w_prev = w_prev + delta
-                host[:] = w_prev.cpu().numpy()
-                lib.check(L.nb_set_weights(g, lib.ptr(host)))
+                lib.check(L.nb_set_weights_dev(g, C.c_void_p(w_prev.data_ptr())))
             stepsize *= decay
         torch.cuda.synchronize()
         fg._mark_device_newer("var_value", "var_value_evid")
@@ -469,10 +596,17 @@ class PartitionedGibbs(object):
         return stepsize
 
 
-def partition_graph(weight, variable, factor, fmap, rank, world, device, seed, group=None, color_seed=0x5EED):
-    """Block-partition a global graph (every rank passes the same arrays)."""
-    bounds = block_bounds(len(variable), world)
-    local = extract_local(weight, variable, factor, fmap, int(bounds[rank]), int(bounds[rank + 1]))
+def partition_graph(weight, variable, factor, fmap, rank, world, device, seed, group=None, color_seed=0x5EED,
+                    owner=None):
+    """Partition a global graph (every rank passes the same arrays): contiguous owner blocks, or
+    the placement ``owner[v]`` -- e.g. :func:`owners_from_salt_keys` (the reference's partition
+    keys) or :func:`locality_owners`.  Samples do not depend on the placement: colours and Philox
+    streams are functions of the global ids."""
+    if owner is None:
+        bounds = block_bounds(len(variable), world)
+        local = extract_local(weight, variable, factor, fmap, int(bounds[rank]), int(bounds[rank + 1]))
+    else:
+        local = extract_local_by_owner(weight, variable, factor, fmap, owner, rank)
     return PartitionedGibbs(local, len(variable), rank, world, device, seed, color_seed, group)
 
 

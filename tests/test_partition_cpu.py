@@ -95,7 +95,7 @@ def _worker(rank, world, port, out_dir):
     b = partition.block_bounds(len(v), world)
     loc = partition.extract_local(w, v, f, fm, int(b[rank]), int(b[rank + 1]))
     gv, n_owned = loc["global_vid"], loc["n_owned"]
-    plan = partition.HaloPlan(gv, n_owned, b, rank, world)
+    plan = partition.HaloPlan(gv, n_owned, lambda gids: np.searchsorted(b, gids, side="right") - 1, rank, world)
     # state: owners know f(global id); ghosts start at -1 and must be filled by the exchange
     x = torch.full((len(gv),), -1, dtype=torch.int32)
     x[:n_owned] = torch.from_numpy((gv[:n_owned] * 7 + 3).astype(np.int32))
@@ -152,3 +152,63 @@ def test_kbc_block_generator_matches_extract_local():
     # the whole-graph generator does not depend on the number of host threads
     import os
     assert len(f) == n + 3 * (n // 2) and int(f["arity"].sum()) == len(fm) == e
+
+
+def test_owner_array_placement_matches_block_partition():
+    """extract_local_by_owner with the block owners is extract_local; with a scrambled placement the
+    ranks' shares still tile the graph (every variable owned once, every factor kept wherever it has
+    an owned member, ghosts flagged isEvidence = 4)."""
+    import numpy as np
+    from numbskull_b200 import partition, synth
+    w, v, f, fm, dm, e = synth.random_graph(500, 1200, np.random.default_rng(3), max_arity=3)
+    world = 3
+    bounds = partition.block_bounds(len(v), world)
+    owner = (np.searchsorted(bounds, np.arange(len(v)), side="right") - 1).astype(np.int32)
+    for r in range(world):
+        a = partition.extract_local(w, v, f, fm, int(bounds[r]), int(bounds[r + 1]))
+        b = partition.extract_local_by_owner(w, v, f, fm, owner, r)
+        for k in ("variable", "factor", "fmap", "global_vid"):
+            assert np.array_equal(a[k], b[k]), (r, k)
+    owner = np.random.default_rng(4).integers(0, world, len(v)).astype(np.int32)
+    seen = np.zeros(len(v), int)
+    for r in range(world):
+        loc = partition.extract_local_by_owner(w, v, f, fm, owner, r)
+        n = loc["n_owned"]
+        gv = loc["global_vid"]
+        seen[gv[:n]] += 1
+        assert (owner[gv[:n]] == r).all() and (owner[gv[n:]] != r).all()
+        assert (loc["variable"]["isEvidence"][n:] == 4).all()
+        assert (np.diff(gv[:n]) > 0).all() and (np.diff(gv[n:]) > 0).all()
+        # every kept factor has an owned member, members translate back to the global ids
+        ar = loc["factor"]["arity"].astype(int)
+        first = loc["factor"]["ftv_offset"].astype(int)
+        for i in range(0, len(ar), 37):
+            m = loc["fmap"]["vid"][first[i]:first[i] + ar[i]]
+            assert (m < n).any()
+    assert (seen == 1).all()
+
+
+def test_salt_partition_keys_and_locality_owners():
+    """Reference partition keys (salt/src/messages.py:175-179; master keeps 'A' / 'B', minion i the
+    keys that carry its id) and the locality-aware placement: on a windowed graph whose ids were
+    shuffled, the RCM placement needs far fewer ghosts than blocks of the shuffled ids."""
+    import numpy as np
+    from numbskull_b200 import partition, synth
+    own = partition.owners_from_salt_keys(["A", "B", "C0", "D0", "C1", "Du1", b"C2", "Au"], world=3)
+    assert own.tolist() == [0, 0, 1, 1, 2, 2, 1, 0]
+    assert partition.owners_from_salt_keys(["C5", "A"], world=1).tolist() == [0, 0]
+    n = 20000
+    w, v, f, fm, dm, e = synth.kbc_fast(n, seed=3, far_frac=0.0, hub_frac=0.0)
+    perm = np.random.default_rng(1).permutation(n)
+    fm2 = fm.copy()
+    fm2["vid"] = perm[fm["vid"]]                    # same graph, ids carry no locality any more
+    v2 = np.empty_like(v)
+    v2[perm] = v
+    world = 4
+    bounds = partition.block_bounds(n, world)
+    blocks = (np.searchsorted(bounds, np.arange(n), side="right") - 1).astype(np.int32)
+    smart = partition.locality_owners(v2, f, fm2, world)
+    assert np.bincount(smart, minlength=world).max() <= n // world + 1
+    g_block = np.mean([partition.ghost_fraction(partition.extract_local_by_owner(w, v2, f, fm2, blocks, r)) for r in range(world)])
+    g_smart = np.mean([partition.ghost_fraction(partition.extract_local_by_owner(w, v2, f, fm2, smart, r)) for r in range(world)])
+    assert g_smart < 0.25 * g_block, (g_smart, g_block)
