@@ -359,8 +359,12 @@ def block_c4(args, local_rank):
     def sweeps(n):
         _lib.check(L.nb_gibbs_sweeps(dev.g, n, 0, 1, fg.seed))
     sweeps(3)
+    import torch
+    rt = torch.cuda.cudart()
     l0 = dev.launches()
+    rt.cudaProfilerStart()
     ms = dev.timed_blocks(sweeps, steps, 3)
+    rt.cudaProfilerStop()
     l1 = dev.launches()
     med = float(np.median(ms)) / steps
     bad = C.c_int64(-1)
@@ -415,8 +419,12 @@ def block_learn(args, local_rank):
         s = C.c_double(1e-4)
         _lib.check(L.nb_learn_sweeps(dev.g, n, C.byref(s), 1.0, 1, 0.01, 1.0, 1, fg.seed, 0))
     epochs(1)
+    import torch
+    rt = torch.cuda.cudart()
     l0 = dev.launches()
+    rt.cudaProfilerStart()
     ms = dev.timed_blocks(epochs, 3, 3)
+    rt.cudaProfilerStop()
     l1 = dev.launches()
     med = float(np.median(ms)) / 3
     fg._stale.add("weight_value")

@@ -435,7 +435,29 @@ __device__ __noinline__ void learn_tt_slices(const LearnArgs &a, const LearnCtx<
 }
 
 // Same algorithm, one WARP per row with the lanes striding over the row's quads: used when the
-// rows are long (data-programming models: a label variable with ~100 labelling functions).
+// rows are long (data-programming models: a label variable with ~100 labelling functions) or when
+// a cell has fewer rows than the grid has warps.  A cell is a chain of dependent memory round trips
+// (the work per cell is tiny), so the row is read ONCE: every lane issues all its loads up front
+// (four incidences per lane and group: quad, weight id, f(0) table, then the member values of both
+// chains), and keeps what the gradient needs -- f(0) and f(1) - f(0) under each chain, 10 bits --
+// in registers until both samples are drawn.  Rows of more than NB_ROW_STASH * 32 incidences re-read
+// their tail from memory.
+#define NB_ROW_GROUP 4                       /* incidences per lane whose loads are in flight together */
+#define NB_ROW_STASH (2 * NB_ROW_GROUP)      /* incidences per lane kept in registers */
+
+__device__ __forceinline__ uint32_t nb_pack_grad(uint32_t table, uint32_t base, int iF, int iE, bool live)
+{
+    // [1:0] f(0)+1 free  [4:2] f(1)-f(0)+2 free  [6:5] f(0)+1 evid  [9:7] diff evid  [10] contributes
+    return ((base >> (2 * iF)) & 3u) | (((table >> (3 * iF)) & 7u) << 2) | (((base >> (2 * iE)) & 3u) << 5) |
+           (((table >> (3 * iE)) & 7u) << 7) | ((live ? 1u : 0u) << 10);
+}
+__device__ __forceinline__ int nb_grad_of(uint32_t p, int prop, int ev)
+{
+    const int fF = ((int)(p & 3u) - 1) + prop * ((int)((p >> 2) & 7u) - 2);
+    const int fE = ((int)((p >> 5) & 3u) - 1) + ev * ((int)((p >> 7) & 7u) - 2);
+    return fF - fE;
+}
+
 template <bool SMEM>
 __device__ __noinline__ void learn_tt_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg0, int end0, int beg1, int end1,
                                            uint32_t kfree, uint32_t kevid, uint32_t ktrunc, int rot)
@@ -451,17 +473,52 @@ __device__ __noinline__ void learn_tt_rows(const LearnArgs &a, const LearnCtx<SM
     for (int64_t it = it_first; it < ntot; it += n_warps) {
         const int64_t nid = it < n0 ? beg0 + it : beg1 + (it - n0);
         const uint32_t meta = a.vmeta[nid];
-        const int evid = NB_META_EVID(meta);
-        if (!NB_META_VALID(meta) || evid == 4) continue;                         // learning.py:24-26
         const uint32_t rid = a.rng_id[nid];
+        const int vin = (int)a.vinit[nid];
         const int64_t s = nid >> 5;
         const int64_t q0 = a.tt_ptr[s];
         const int n = (int)((a.tt_ptr[s + 1] - q0) >> 5);
+        const int evid = NB_META_EVID(meta);
+        if (!NB_META_VALID(meta) || evid == 4) continue;                         // learning.py:24-26
         const uint4 *qp = a.tt + q0 + (nid & 31);
         const uint32_t *bp = a.tt_base + q0 + (nid & 31);
         const uint32_t *wp = a.tt_wid + q0 + (nid & 31);
+        uint32_t st_g[NB_ROW_STASH], st_w[NB_ROW_STASH];
+#pragma unroll
+        for (int u = 0; u < NB_ROW_STASH; u++) { st_g[u] = 0u; st_w[u] = 0u; }
         double dF = 0.0, dE = 0.0;
-        for (int j = lane; j < n; j += 32) {
+        // ---- the row, NB_ROW_GROUP * 32 incidences at a time: all loads first ----
+#pragma unroll
+        for (int grp = 0; grp < NB_ROW_STASH / NB_ROW_GROUP; grp++) {
+            if (grp * NB_ROW_GROUP * 32 < n) {
+                uint4 q[NB_ROW_GROUP];
+                uint32_t wid[NB_ROW_GROUP], b[NB_ROW_GROUP];
+#pragma unroll
+                for (int u = 0; u < NB_ROW_GROUP; u++) {
+                    const int j = lane + 32 * (grp * NB_ROW_GROUP + u);
+                    const bool in = j < n;
+                    q[u] = in ? __ldg(qp + (size_t)j * 32) : make_uint4((uint32_t)nid, (uint32_t)nid, NB_TT_NEUTRAL | NB_TT_FIXED_BIT, 0u);
+                    wid[u] = in ? __ldg(wp + (size_t)j * 32) : 0u;
+                    b[u] = in ? __ldg(bp + (size_t)j * 32) : NB_TT_BASE_NEUTRAL;
+                }
+                int xf[NB_ROW_GROUP][2], xe[NB_ROW_GROUP][2];
+#pragma unroll
+                for (int u = 0; u < NB_ROW_GROUP; u++) {
+                    xf[u][0] = nb_ldv(vF, q[u].x); xf[u][1] = nb_ldv(vF, q[u].y);
+                    xe[u][0] = nb_ldv(vE, q[u].x); xe[u][1] = nb_ldv(vE, q[u].y);
+                }
+#pragma unroll
+                for (int u = 0; u < NB_ROW_GROUP; u++) {
+                    const int iF = nb_tt_index(xf[u][0], xf[u][1]), iE = nb_tt_index(xe[u][0], xe[u][1]);
+                    const double w = ctx.weight(wid[u]);
+                    dF = fma(w, (double)nb_tt_diff(q[u].z, iF), dF);
+                    dE = fma(w, (double)nb_tt_diff(q[u].z, iE), dE);
+                    st_g[grp * NB_ROW_GROUP + u] = nb_pack_grad(q[u].z, b[u], iF, iE, !(q[u].z & NB_TT_FIXED_BIT));
+                    st_w[grp * NB_ROW_GROUP + u] = wid[u];
+                }
+            }
+        }
+        for (int j = lane + 32 * NB_ROW_STASH; j < n; j += 32) {                 // tail of a very long row
             const uint4 q = __ldg(qp + (size_t)j * 32);
             const double w = ctx.weight(__ldg(wp + (size_t)j * 32));
             dF = fma(w, (double)nb_tt_diff(q.z, nb_tt_index(nb_ldv(vF, q.x), nb_ldv(vF, q.y))), dF);
@@ -474,7 +531,7 @@ __device__ __noinline__ void learn_tt_rows(const LearnArgs &a, const LearnCtx<SM
             const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, kevid);
             ev = u <= (double)(1.0f / (1.0f + __expf((float)dE))) ? 0 : 1;
         } else {
-            ev = (int)a.vinit[nid];
+            ev = vin;
         }
         const double uf = nb_philox2x32_u53(rid, (uint32_t)a.epoch, kfree);
         const int prop = uf <= (double)(1.0f / (1.0f + __expf((float)dF))) ? 0 : 1;
@@ -485,19 +542,19 @@ __device__ __noinline__ void learn_tt_rows(const LearnArgs &a, const LearnCtx<SM
         if (a.regularization == 1)
             cinc = nb_philox2x32_u53(rid, (uint32_t)a.epoch, ktrunc) < 1.0 / a.truncation ? 1u : 0u;
         else if (a.regularization != 2) cinc = 0;
-        for (int j = lane; j < n; j += 32) {
+        // ---- integer gradients from the registers (:97-125) ----
+#pragma unroll
+        for (int u = 0; u < NB_ROW_STASH; u++)
+            if (st_g[u] & (1u << 10)) ctx.add_int(st_w[u], nb_grad_of(st_g[u], prop, ev), cinc);
+        for (int j = lane + 32 * NB_ROW_STASH; j < n; j += 32) {
             const uint4 q = __ldg(qp + (size_t)j * 32);
             if (q.z & NB_TT_FIXED_BIT) continue;
             const uint32_t b = __ldg(bp + (size_t)j * 32);
             // slots that point at the variable itself are ignored by the tables
             const int iF = nb_tt_index(nb_ldv(vF, q.x), nb_ldv(vF, q.y)), iE = nb_tt_index(nb_ldv(vE, q.x), nb_ldv(vE, q.y));
-            const int fF = ((int)((b >> (2 * iF)) & 3u) - 1) + prop * nb_tt_diff(q.z, iF);
-            const int fE = ((int)((b >> (2 * iE)) & 3u) - 1) + ev * nb_tt_diff(q.z, iE);
-            ctx.add_int(__ldg(wp + (size_t)j * 32), fF - fE, cinc);
+            ctx.add_int(__ldg(wp + (size_t)j * 32), nb_grad_of(nb_pack_grad(q.z, b, iF, iE, true), prop, ev), cinc);
         }
     }
-    // per-warp arrival at the end of the function, for the CTA at rotated position 0
-
 }
 
 // ---------------------------------------------------------------------------
@@ -531,7 +588,7 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
 {
     extern __shared__ unsigned char s_raw[];
     __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
-    __shared__ int s_rng[2 * NB_N_CLASSES];
+    __shared__ int s_rng[2][2 * NB_N_CLASSES];
     const int W = a.W;
     // shared layout (SMEM): weights f64 [W] | fixed-point sums i64 [W] | integer sums i32 [W] | counts u32 [W]
     double *s_w = (double *)s_raw;
@@ -553,14 +610,26 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
         const int color = only_color >= 0 ? only_color : cell % plan.n_colors;
         const bool tr = a.trace != nullptr && threadIdx.x == 0;
         unsigned long long t0 = tr ? nb_now() : 0ull, t1;
-        // five threads look the cell's id ranges up (64-bit divisions and dependent loads: not per thread)
+        // The cell's id ranges (64-bit divisions and dependent loads) come from shared memory: five
+        // threads of the LAST warp looked them up while the previous cell was being processed.
         __syncthreads();
-        if (threadIdx.x < NB_N_CLASSES) nb_plan_range(plan, (int)threadIdx.x, color, block, s_rng[2 * threadIdx.x], s_rng[2 * threadIdx.x + 1]);
-        __syncthreads();
-        const int pb = s_rng[2 * NB_CLASS_PAIR], pe = s_rng[2 * NB_CLASS_PAIR + 1], fb = s_rng[2 * NB_CLASS_FAST],
-                  fe = s_rng[2 * NB_CLASS_FAST + 1], cb = s_rng[2 * NB_CLASS_CAT], ce = s_rng[2 * NB_CLASS_CAT + 1],
-                  tb = s_rng[2 * NB_CLASS_GEN], te = s_rng[2 * NB_CLASS_GEN + 1];
-        int wb = s_rng[2 * NB_CLASS_WARP], we = s_rng[2 * NB_CLASS_WARP + 1];
+        if (cell == cell_beg) {
+            if (threadIdx.x < NB_N_CLASSES) nb_plan_range(plan, (int)threadIdx.x, color, block, s_rng[cell & 1][2 * threadIdx.x], s_rng[cell & 1][2 * threadIdx.x + 1]);
+            __syncthreads();
+        }
+        {
+            const int t = (int)threadIdx.x - (NB_LEARN_THREADS - 32);
+            if (t >= 0 && t < NB_N_CLASSES && cell + 1 < cell_end) {
+                const int nblock = only_color >= 0 ? cell + 1 : (cell + 1) / plan.n_colors;
+                const int ncolor = only_color >= 0 ? only_color : (cell + 1) % plan.n_colors;
+                nb_plan_range(plan, t, ncolor, nblock, s_rng[(cell + 1) & 1][2 * t], s_rng[(cell + 1) & 1][2 * t + 1]);
+            }
+        }
+        const int *rng = s_rng[cell & 1];
+        const int pb = rng[2 * NB_CLASS_PAIR], pe = rng[2 * NB_CLASS_PAIR + 1], fb = rng[2 * NB_CLASS_FAST],
+                  fe = rng[2 * NB_CLASS_FAST + 1], cb = rng[2 * NB_CLASS_CAT], ce = rng[2 * NB_CLASS_CAT + 1],
+                  tb = rng[2 * NB_CLASS_GEN], te = rng[2 * NB_CLASS_GEN + 1];
+        int wb = rng[2 * NB_CLASS_WARP], we = rng[2 * NB_CLASS_WARP + 1];
         wb -= (int)plan.n_trows;          // warp rows are addressed by their index
         we -= (int)plan.n_trows;
         if (pe <= pb && fe <= fb && ce <= cb && te <= tb && we <= wb) continue;   // uniform across the grid

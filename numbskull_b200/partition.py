@@ -419,6 +419,12 @@ class PartitionedGibbs(object):
             assert not (self.split and c % 2 == 1 and (sum(map(len, send)) or sum(map(len, recv))))
             self.halo.append(Exchange(send, recv, rank, world, torch.uint8, self.dev, group))
         self.halo_bytes_per_sweep = sum(h.n_send for h in self.halo)
+        # blocks without any ghost on any rank (independent sub-graphs that only share weights, e.g. the
+        # candidates of the labelling-function model): no exchange, whole epochs in single launches
+        t = torch.tensor([len(self.global_vid) - self.n_owned], device=self.dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t, group=group)
+        self.any_halo = int(t.item()) > 0
         self.p2p = False
         self.p2p_nowait = 16 if os.environ.get("NUMBSKULL_B200_P2P_NOWAIT", "1") != "0" else 0
         if (world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("NUMBSKULL_B200_P2P", "1") != "0"):
@@ -498,6 +504,10 @@ class PartitionedGibbs(object):
     def sweeps(self, n, burnin, sample_evidence):
         """n chromatic Gibbs sweeps; after each colour the owners' new values reach the ghosts."""
         L, g, lib = self.lib.lib(), self.fg._g, self.lib
+        if not self.any_halo:
+            if n > 0:
+                lib.check(L.nb_gibbs_sweeps(g, int(n), int(bool(burnin)), int(bool(sample_evidence)), self.fg.seed))
+            return
         if self.world > 1 and self.p2p:
             # the whole launch sequence (colour kernels + halo pushes) is issued from C
             mode = (1 if self.p2p_nowait else 0) | (2 if self.split and self.p2p_nowait else 0)
@@ -556,6 +566,24 @@ class PartitionedGibbs(object):
         w_prev = torch.from_numpy(fg._host("weight_value", expose=False)[0].copy()).to(self.dev)
         w_now = torch.empty_like(w_prev)      # the deltas never leave the devices (nb_get/set_weights_dev + NCCL)
         for _ in range(epochs):
+            if not self.any_halo:
+                # one persistent launch per epoch (nb_learn_sweeps), then the ranks' deltas are summed
+                s_ = C.c_double(float(stepsize))
+                lib.check(L.nb_learn_sweeps(g, 1, C.byref(s_), 1.0, int(regularization), float(reg_param), float(truncation),
+                                            int(bool(learn_non_evidence)), fg.seed, int(fg.batch_visits)))
+                if self.world > 1:
+                    lib.check(L.nb_get_weights_dev(g, C.c_void_p(w_now.data_ptr())))
+                    delta = w_now - w_prev
+                    if delta.is_cuda and self.dist.get_backend(self.group) == "gloo":
+                        d = delta.cpu()
+                        self.dist.all_reduce(d, group=self.group)
+                        delta = d.to(self.dev)
+                    else:
+                        self.dist.all_reduce(delta, group=self.group)
+                    w_prev = w_prev + delta
+                    lib.check(L.nb_set_weights_dev(g, C.c_void_p(w_prev.data_ptr())))
+                stepsize *= decay
+                continue
             ep = C.c_int64(0)
             lib.check(L.nb_begin_epoch(g, C.byref(ep)))
             nb = C.c_int(1)
@@ -608,6 +636,21 @@ def partition_graph(weight, variable, factor, fmap, rank, world, device, seed, g
     else:
         local = extract_local_by_owner(weight, variable, factor, fmap, owner, rank)
     return PartitionedGibbs(local, len(variable), rank, world, device, seed, color_seed, group)
+
+
+def lf_block(copies_total, n_lf, rank, world, seed=1003):
+    """Rank ``rank``'s candidates of the labelling-function model (BASELINE config 3; full size:
+    10 M candidates x 100 labelling functions = 1.01 B variables, beyond one GPU's 2^31 ids, so it
+    exists only in partitioned form).  Candidates are independent given the weights: the block has
+    no ghosts, the ranks only meet in the per-epoch weight-delta all-reduce.  Built locally; the
+    labelling-function accuracies are a function of ``seed`` alone, the votes of (seed, rank)."""
+    from . import synth
+    per = 1 + n_lf
+    c_lo, c_hi = copies_total * rank // world, copies_total * (rank + 1) // world
+    acc = np.random.default_rng(seed).uniform(0.55, 0.95, n_lf)
+    w, v, f, fm, dm, e = synth.lf_model(c_hi - c_lo, n_lf, np.random.default_rng([seed, rank]), accuracy=acc)
+    gv = np.arange(c_lo * per, c_hi * per, dtype=np.int64)
+    return dict(weight=w, variable=v, factor=f, fmap=fm, domain_mask=dm, global_vid=gv, n_owned=len(v)), copies_total * per
 
 
 def ising_strip_runner(rows, cols, rank, world, device, seed):

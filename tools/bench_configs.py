@@ -194,6 +194,55 @@ def c4_partitioned(scale):
     dist.destroy_process_group()
 
 
+def c3_partitioned(scale):
+    """C3 across the ranks of a torchrun launch: every rank builds its own candidates (no ghosts);
+    learning sums the ranks' weight deltas once per epoch (device-side all-reduce), then marginals."""
+    import torch
+    import torch.distributed as dist
+    from numbskull_b200 import partition
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=900))
+    copies, n_lf = max(1000, int(10_000_000 * scale)), 100
+    t0 = time.perf_counter()
+    loc, n_global = partition.lf_block(copies, n_lf, rank, world)
+    run = partition.PartitionedGibbs(loc, n_global, rank, world, local, seed=12345)
+    build_s = time.perf_counter() - t0
+    fg = run.fg
+    L, g = _lib.lib(), fg._g
+    run.learn(0, 1, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)            # warm-up epoch
+    torch.cuda.synchronize()
+    dist.barrier()
+    epochs = 3
+    t1 = time.perf_counter()
+    run.learn(0, epochs, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = (time.perf_counter() - t1) / epochs
+    t2 = time.perf_counter()
+    sweeps = 10
+    marg = run.inference(2, sweeps, sample_evidence=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dti = (time.perf_counter() - t2) / (sweeps + 2)
+    per = 1 + n_lf
+    y = np.asarray(marg)[::per] if len(marg) else np.zeros(0)
+    stats = torch.tensor([float(y.sum()), float(len(y))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(stats)
+    if rank == 0:
+        edges = copies * (1 + 2 * n_lf)
+        w = fg.weight_value[0]
+        print(json.dumps({"config": "c3_lf_%dx%d_partitioned" % (copies, n_lf), "n_gpus": world, "variables": n_global,
+                          "edges": edges, "colors": run.n_colors, "build_s": round(build_s, 1),
+                          "device_GB_rank0": round(fg.device_info()["device_bytes"] / 1e9, 2),
+                          "learn_ms_per_epoch": 1e3 * dt, "learn_edge_evals_per_s": edges / dt,
+                          "inference_ms_per_sweep_wall": 1e3 * dti, "mean_marginal_y": stats[0].item() / max(stats[1].item(), 1),
+                          "weights_head": [round(float(x), 4) for x in w[:6]], "weights_finite": bool(np.isfinite(w).all())}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def c5(scale):
     nvar = max(10000, int(50_000_000 * scale))
     g = synth.categorical(nvar, 16, 3, np.random.default_rng(1005))
@@ -214,7 +263,9 @@ if __name__ == "__main__":
     ap.add_argument("config", choices=["c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=0.1)
     a = ap.parse_args()
-    if a.config == "c4" and int(os.environ.get("WORLD_SIZE", 1)) > 1:
+    if a.config == "c3" and int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        c3_partitioned(a.scale)
+    elif a.config == "c4" and int(os.environ.get("WORLD_SIZE", 1)) > 1:
         c4_partitioned(a.scale)
     else:
         {"c3": c3, "c4": c4, "c5": c5}[a.config](a.scale)
