@@ -52,6 +52,11 @@ extern "C" void nb_graph_destroy(nb_graph *g)
     if (g->h_pinned) cudaFreeHost(g->h_pinned);
     for (cudaEvent_t e : g->xfer_events) cudaEventDestroy(e);
     nb_release_color_scratch(g);
+    for (int i = 0; i < NB_AUX_STREAMS; i++) {
+        if (g->aux[i]) { cudaStreamSynchronize(g->aux[i]); cudaStreamDestroy(g->aux[i]); }
+        if (g->ev_join[i]) cudaEventDestroy(g->ev_join[i]);
+    }
+    if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->stream && g->own_stream) cudaStreamDestroy(g->stream);
@@ -584,10 +589,15 @@ extern "C" int nb_gibbs_sweeps(nb_graph *g, int64_t n_epochs, int burnin, int sa
     NB_CUDA(cudaSetDevice(g->device));
     NB_TRY(check_runnable(g));
     NB_TRY(nb_refresh_inlined_weights(g));
-    for (int64_t ep = 0; ep < n_epochs; ep++) {
+    static const bool fan = [] { const char *e = getenv("NUMBSKULL_B200_FAN_OUT"); return !e || atoi(e) != 0; }();
+    g->fan_out = fan && g->p2p == nullptr;
+    int rc = NB_OK;
+    for (int64_t ep = 0; ep < n_epochs && rc == NB_OK; ep++) {
         uint64_t epoch = g->epoch_counter++;
-        for (int c = 0; c < g->n_colors; c++) NB_TRY(nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch));
+        for (int c = 0; c < g->n_colors && rc == NB_OK; c++) rc = nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch);
     }
+    g->fan_out = false;
+    NB_TRY(rc);
     NB_CUDA(cudaStreamSynchronize(g->stream));
     return NB_OK;
 }

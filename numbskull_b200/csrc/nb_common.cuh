@@ -187,6 +187,10 @@ struct nb_graph {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#define NB_AUX_STREAMS 4
+    cudaStream_t aux[NB_AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // concurrent row classes of one colour
+    cudaEvent_t ev_fork = nullptr, ev_join[NB_AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    bool fan_out = false;             // nb_gibbs_sweeps on a single-GPU graph: run a colour's row classes concurrently
 
     // sizes
     int64_t V = 0, F = 0, W = 0, NFMAP = 0, NVMAP = 0, NFI = 0;
@@ -321,6 +325,7 @@ struct nb_graph {
     bool halo_wait_off = false;        // launches of phases that never read a ghost skip the halo wait
     int64_t n_win = 0;                 // id windows (original id >> sigma_shift)
     std::vector<int32_t> win_start;    // [NB_N_CLASSES * (n_colors + 1)][n_win + 1] first new id of each window per group
+    std::vector<uint8_t> learn_long_rows;  // host copy of d_long_rows
     std::vector<int64_t> learn_vmax;   // per colour: max gradient visits of one weight
     int learn_vmax_flag = -1;
     std::vector<NbColorRange> colors;

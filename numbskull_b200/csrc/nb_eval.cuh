@@ -150,10 +150,15 @@ struct NbValsGlobal {
     const nb_val_t *__restrict__ v;
     __device__ __forceinline__ int operator()(uint32_t vid) const { return (int)v[vid]; }
 };
-// same, bypassing L1: a persistent kernel reads values other CTAs wrote earlier in the same launch
+// Same for the persistent learning kernel, which reads values other CTAs wrote earlier in the same
+// launch: a plain cached load (ld.global.ca, never the non-coherent path).  Inside a cell nobody
+// writes what another thread reads (colouring), and between cells every CTA passes the grid
+// barrier, whose fence invalidates the SM's L1 (CCTL.IVALL) before anybody reads again.  Bypassing
+// L1 altogether (ld.global.cg) cost the categorical rows a factor of four: their samplers re-read
+// the same few neighbours for every candidate value.
 struct NbValsCG {
     const nb_val_t *v;
-    __device__ __forceinline__ int operator()(uint32_t vid) const { return (int)__ldcg(v + vid); }
+    __device__ __forceinline__ int operator()(uint32_t vid) const { return (int)__ldca(v + vid); }
 };
 // weight accessors: global (read-only for the launch), global through L2, or a shared-memory copy
 struct NbWtsGlobal {
@@ -162,7 +167,7 @@ struct NbWtsGlobal {
 };
 struct NbWtsCG {
     const double *w;
-    __device__ __forceinline__ double operator()(uint32_t i) const { return __ldcg(w + i); }
+    __device__ __forceinline__ double operator()(uint32_t i) const { return __ldca(w + i); }
 };
 struct NbWtsShared {
     const double *w;
@@ -186,8 +191,13 @@ __device__ __forceinline__ int nb_member(const NbRow &r, int mpos, int step, int
 // learning kernel; inlined everywhere it blew the persistent learning kernel up to 855 KB of SASS
 // (k_gibbs_thread: 195 KB), and every mini-batch cell then ran out of a cold instruction cache
 // (ncu: 81 % i-cache hit rate, the slowest CTA 6x slower than the average one).
+#ifndef NB_EVAL_INLINE
+#define NB_EVAL_FN __noinline__
+#else
+#define NB_EVAL_FN inline
+#endif
 template <class Vals>
-__device__ __noinline__ double nb_eval_incidence_v(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
+__device__ NB_EVAL_FN double nb_eval_incidence_v(const NbRow &r, const NbHdr &h, int mpos, uint32_t self,
                                                    int k, const Vals &vals)
 {
     const int a = h.arity;
@@ -430,7 +440,7 @@ __device__ __forceinline__ int nb_draw_small(const double e[4], int card, double
 
 // Sample one variable whose row is `r` (thread path, or any row walked by one thread).
 template <bool WIDE, class Vals, class Wts>
-__device__ __noinline__ int nb_sample_row_v(const NbRow &r, int len, uint32_t self, uint32_t meta,
+__device__ NB_EVAL_FN int nb_sample_row_v(const NbRow &r, int len, uint32_t self, uint32_t meta,
                                             const Vals &vals, const Wts &weight, NbUniforms &rng)
 {
     const int card = NB_META_CARD(meta);

@@ -59,6 +59,11 @@ struct LearnArgs {
     const uint4 *tt;
     const uint32_t *tt_base;
     const uint32_t *tt_wid;   // weight id per quad (the quads themselves inline the weight VALUE for the Gibbs sweep)
+    // categorical record rows (new ids [cat_first, ...)): records + weight ids, see nb_cat_energies
+    const int64_t *cat_ptr;
+    const uint4 *cat;
+    const uint32_t *cat_wid;
+    int64_t cat_first;
     // reduction by weight id: three rotating global tables [3][W] (cell c uses c % 3)
     nb_fix_t *g_grad;
     uint32_t *g_cnt;
@@ -92,7 +97,7 @@ struct CellPlan {
     int64_t n_trows;
 };
 
-__device__ __forceinline__ int nb_plan_pos(const CellPlan &p, int group, int64_t unit)
+__host__ __device__ __forceinline__ int nb_plan_pos(const CellPlan &p, int group, int64_t unit)
 {
     const int32_t *ws = p.win_start + (size_t)group * (size_t)(p.n_win + 1);
     const int64_t w = unit / p.k_sub, j = unit % p.k_sub;
@@ -101,7 +106,7 @@ __device__ __forceinline__ int nb_plan_pos(const CellPlan &p, int group, int64_t
     return (int)(s + (e - s) * j / p.k_sub);
 }
 
-__device__ __forceinline__ void nb_plan_range(const CellPlan &p, int cls, int color, int block, int &beg, int &end)
+__host__ __device__ __forceinline__ void nb_plan_range(const CellPlan &p, int cls, int color, int block, int &beg, int &end)
 {
     const int64_t T = p.n_win * (int64_t)p.k_sub;
     const int group = cls * (p.n_colors + 1) + color;
@@ -141,7 +146,8 @@ struct LearnCtx {
     int32_t *gi;            // SMEM: shared integer gradient table (truth-table rows)
     nb_fix_t *gf;           // shared (SMEM) or global fixed-point gradient table
     uint32_t *cnt;          // shared or global visit counts
-    __device__ __forceinline__ double weight(uint32_t i) const { return SMEM ? w[i] : __ldcg(w + i); }
+    // (global table: cached in L1 like the values -- updated only between two grid barriers)
+    __device__ __forceinline__ double weight(uint32_t i) const { return SMEM ? w[i] : __ldca(w + i); }
     __device__ __forceinline__ void add_int(uint32_t wid, int g, uint32_t c) const
     {
         if (SMEM) { if (g) atomicAdd(gi + wid, g); }
@@ -173,7 +179,7 @@ __device__ __forceinline__ uint32_t nb_cnt_inc(const LearnArgs &a, uint32_t id)
 
 // second pass over a row: gradient of every visited incidence with a learnable weight
 template <bool WIDE, bool SMEM>
-__device__ __noinline__ void nb_row_gradient(const NbRow &r, int len, uint32_t self, uint32_t meta, int ev, int prop,
+__device__ NB_EVAL_FN void nb_row_gradient(const NbRow &r, int len, uint32_t self, uint32_t meta, int ev, int prop,
                                        const LearnArgs &a, uint32_t cnt_inc, const LearnCtx<SMEM> &ctx,
                                        int first_inc, int inc_stride, const uint2 *inc_list, int n_inc)
 {
@@ -240,6 +246,95 @@ __device__ __noinline__ void learn_thread_rows(const LearnArgs &a, const LearnCt
     }
 }
 
+__device__ __forceinline__ int nb_ldv(const nb_val_t *v, uint32_t i) { return (int)__ldca(v + i); }   // see NbValsCG
+// ---------------------------------------------------------------------------
+// categorical record rows (CAT class), one row per thread.  Same records as the Gibbs sweep
+// (nb_cat_energies: one 16-byte quad per incidence of an AND_CAT / EQUAL_CAT_CONST factor in its
+// value bucket), but the weights are read live through cat_wid -- they move every cell -- and both
+// chains are drawn.  Walking the generic words instead costs ~1000 instructions per card-16 row.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool nb_cat_sat(uint32_t m, int xa, int xb)
+{
+    const int no = (int)((m >> 24) & 3u);
+    return no < 3 && (no < 1 || xa == (int)((m >> 8) & 0xFFu)) && (no < 2 || xb == (int)((m >> 16) & 0xFFu));
+}
+
+// draw_sample (inference.py:36-52) from the per-value energies e[0..card), one uniform
+__device__ __forceinline__ int nb_cat_draw(float *e, int card, double u)
+{
+    float mx = e[0];
+    for (int k = 1; k < card; k++) mx = fmaxf(mx, e[k]);
+    float tot = 0.0f;
+    for (int k = 0; k < card; k++) { const float z = __expf(e[k] - mx); e[k] = z; tot += z; }
+    const float t = (float)u * tot;
+    float acc = 0.0f;
+    for (int k = 0; k < card; k++) {
+        acc += e[k];
+        if (acc >= t) return k;
+    }
+    return card - 1;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ int nb_cat_sample_l(const uint4 *qp, const uint32_t *wp, int n, int card, const nb_val_t *vals,
+                                               const LearnCtx<SMEM> &ctx, float *e, double u)
+{
+    for (int k = 0; k < card; k++) e[k] = 0.0f;
+    for (int j = 0; j < n; j += 2) {
+        uint4 q[2];
+        uint32_t wid[2];
+        int xa[2], xb[2];
+        const bool in1 = j + 1 < n;
+        q[0] = __ldg(qp + (size_t)j * 32);
+        wid[0] = __ldg(wp + (size_t)j * 32);
+        q[1] = in1 ? __ldg(qp + (size_t)(j + 1) * 32) : make_uint4(q[0].x, q[0].y, nb_pack_cat(0, 0, 0, 3, 1), 0u);
+        wid[1] = in1 ? __ldg(wp + (size_t)(j + 1) * 32) : wid[0];
+#pragma unroll
+        for (int t = 0; t < 2; t++) { xa[t] = nb_ldv(vals, q[t].x); xb[t] = nb_ldv(vals, q[t].y); }
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+            if (nb_cat_sat(q[t].z, xa[t], xb[t])) e[q[t].z & 0xFFu] += (float)ctx.weight(wid[t]);
+    }
+    return nb_cat_draw(e, card, u);
+}
+
+template <bool SMEM>
+__device__ __noinline__ void learn_cat_rows(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int beg, int end, uint32_t kf, uint32_t ke)
+{
+    float e[NB_CAT_MAX_CARD];
+    const nb_val_t *vF = a.val_free, *vE = a.val_evid;
+    for (int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; nid < end; nid += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t meta = __ldg(a.vmeta + nid);
+        const int evid = NB_META_EVID(meta);
+        if (!NB_META_VALID(meta) || evid == 4) continue;                   // learning.py:24-26
+        const int card = NB_META_CARD(meta);
+        const uint32_t id = __ldg(a.rng_id + nid);
+        const int64_t s = (nid - a.cat_first) >> 5;
+        const int64_t q0 = __ldg(a.cat_ptr + s), q1 = __ldg(a.cat_ptr + s + 1);
+        const int n = (int)((q1 - q0) >> 5);
+        const uint4 *qp = a.cat + q0 + (nid & 31);
+        const uint32_t *wp = a.cat_wid + q0 + (nid & 31);
+        int ev;
+        if (evid != 1) ev = nb_cat_sample_l<SMEM>(qp, wp, n, card, vE, ctx, e, nb_philox2x32_u53(id, (uint32_t)a.epoch, ke));   // :53-57
+        else ev = (int)a.vinit[nid];                                        // :60-61
+        a.val_evid[nid] = (nb_val_t)ev;                                     // :63
+        const int prop = nb_cat_sample_l<SMEM>(qp, wp, n, card, vF, ctx, e, nb_philox2x32_u53(id, (uint32_t)a.epoch, kf));   // :65-67
+        a.val_free[nid] = (nb_val_t)prop;                                   // :69
+        if (!a.learn_non_evidence && evid != 1) continue;                   // :70-71
+        // gradient (learning.py:73-108): the incidences of the buckets of the two chains' values
+        const uint32_t cinc = nb_cnt_inc(a, id);
+        for (int j = 0; j < n; j++) {
+            const uint4 q = __ldg(qp + (size_t)j * 32);
+            const uint32_t m = q.z;
+            const int k = (int)(m & 0xFFu);
+            if (((m >> 26) & 1u) || (k != ev && k != prop)) continue;
+            const int f1 = (k == prop && nb_cat_sat(m, nb_ldv(vF, q.x), nb_ldv(vF, q.y))) ? 1 : 0;
+            const int f0 = (k == ev && nb_cat_sat(m, nb_ldv(vE, q.x), nb_ldv(vE, q.y))) ? 1 : 0;
+            ctx.add_int(__ldg(wp + (size_t)j * 32), f1 - f0, cinc);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // warp path: one long row per warp
 // ---------------------------------------------------------------------------
@@ -280,7 +375,7 @@ __device__ inline void nb_warp_energies_l(const NbRow &r, const uint2 *inc, int 
 }
 
 template <bool WIDE, bool SMEM>
-__device__ __noinline__ int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
+__device__ NB_EVAL_FN int nb_warp_sample_l(const NbRow &r, const uint2 *inc, int n_inc, uint32_t self, uint32_t meta,
                                        const nb_val_t *vals, const LearnCtx<SMEM> &ctx, double *se, NbUniforms &rng)
 {
     const int card = NB_META_CARD(meta);
@@ -332,7 +427,6 @@ __device__ __noinline__ void learn_warp_rows(const LearnArgs &a, const LearnCtx<
 // SELL slice with a uniform trip count.  f(k) = f(0) + k (f(1) - f(0)) comes from
 // the two tables, so the gradient is an INTEGER.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int nb_ldv(const nb_val_t *v, uint32_t i) { return (int)__ldcg(v + i); }
 
 // (two id ranges per call: the cell's PAIR rows and its FAST rows -- one copy of the code)
 template <bool SMEM>
@@ -671,7 +765,8 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
             else learn_tt_slices<SMEM>(a, ctx, pb, pe, fb, fe, kf, ke, kt, rot);
         }
         NB_TRACE(1)
-        if (te > tb || ce > cb) learn_thread_rows<WIDE, SMEM>(a, ctx, cb, ce, tb, te);
+        if (ce > cb) learn_cat_rows<SMEM>(a, ctx, cb, ce, kf, ke);
+        if (te > tb) learn_thread_rows<WIDE, SMEM>(a, ctx, 0, 0, tb, te);
         NB_TRACE(2)
         if (we > wb) learn_warp_rows<WIDE, SMEM>(a, ctx, s_e[threadIdx.x >> 5], wb, we);
         NB_TRACE(3)
@@ -718,6 +813,105 @@ __global__ void __launch_bounds__(NB_LEARN_THREADS) k_learn_cells(LearnArgs a, C
         if (tr && blockIdx.x == 0) { atomicAdd(a.trace + 7, 1ull); atomicAdd(a.trace + 8, a.trace_cell[cell - cell_beg]); }
 #undef NB_TRACE
         k++;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Throughput mode.  When a cell holds far more rows than the persistent grid has threads (big graphs
+// with moderate tying: the KBC and categorical shapes), latency per cell does not matter and
+// occupancy does: the persistent kernel carries every row class and needs 128 registers (two CTAs
+// per SM).  Such cells are run as ordinary launches of one lean kernel per row class -- the same
+// device functions, 64-register budgets, full grids -- plus one apply kernel; a handful of launches
+// per cell is nothing against cells of hundreds of microseconds.
+// ---------------------------------------------------------------------------
+template <bool SMEM>
+__device__ __forceinline__ LearnCtx<SMEM> nb_lean_ctx(const LearnArgs &a, unsigned char *s_raw, int slot)
+{
+    const int W = a.W;
+    double *s_w = (double *)s_raw;
+    nb_fix_t *s_gf = (nb_fix_t *)(s_raw + (size_t)8 * (SMEM ? W : 0));
+    int32_t *s_gi = (int32_t *)(s_raw + (size_t)16 * (SMEM ? W : 0));
+    uint32_t *s_cnt = (uint32_t *)(s_raw + (size_t)20 * (SMEM ? W : 0));
+    if (SMEM) {
+        for (int w = threadIdx.x; w < W; w += blockDim.x) { s_w[w] = a.weight[w]; s_gf[w] = 0; s_gi[w] = 0; s_cnt[w] = 0u; }
+        __syncthreads();
+    }
+    LearnCtx<SMEM> ctx;
+    ctx.w = SMEM ? s_w : a.weight;
+    ctx.gi = s_gi;
+    ctx.gf = SMEM ? s_gf : a.g_grad + (size_t)slot * W;
+    ctx.cnt = SMEM ? s_cnt : a.g_cnt + (size_t)slot * W;
+    return ctx;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void nb_lean_flush(const LearnArgs &a, const LearnCtx<SMEM> &ctx, int slot)
+{
+    if (!SMEM) return;
+    __syncthreads();
+    nb_fix_t *g_gf = a.g_grad + (size_t)slot * a.W;
+    uint32_t *g_cn = a.g_cnt + (size_t)slot * a.W;
+    for (int w = threadIdx.x; w < a.W; w += blockDim.x) {
+        const nb_fix_t gsum = ctx.gf[w] + ((nb_fix_t)ctx.gi[w] << NB_GRAD_SHIFT);
+        const uint32_t c = ctx.cnt[w];
+        if (gsum) atomicAdd((unsigned long long *)(g_gf + w), (unsigned long long)gsum);
+        if (c) atomicAdd(g_cn + w, c);
+    }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS, 3) k_cell_tt(LearnArgs a, int pb, int pe, int fb, int fe, int by_row, int slot,
+                                                                 uint32_t kf, uint32_t ke, uint32_t kt)
+{
+    extern __shared__ unsigned char s_raw[];
+    const LearnCtx<SMEM> ctx = nb_lean_ctx<SMEM>(a, s_raw, slot);
+    if (by_row) learn_tt_rows<SMEM>(a, ctx, pb, pe, fb, fe, kf, ke, kt, 0);
+    else learn_tt_slices<SMEM>(a, ctx, pb, pe, fb, fe, kf, ke, kt, 0);
+    nb_lean_flush<SMEM>(a, ctx, slot);
+}
+
+template <bool WIDE, bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS, 4) k_cell_thread(LearnArgs a, int tb, int te, int slot)
+{
+    extern __shared__ unsigned char s_raw[];
+    const LearnCtx<SMEM> ctx = nb_lean_ctx<SMEM>(a, s_raw, slot);
+    learn_thread_rows<WIDE, SMEM>(a, ctx, 0, 0, tb, te);
+    nb_lean_flush<SMEM>(a, ctx, slot);
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS, 4) k_cell_cat(LearnArgs a, int cb, int ce, int slot, uint32_t kf, uint32_t ke)
+{
+    extern __shared__ unsigned char s_raw[];
+    const LearnCtx<SMEM> ctx = nb_lean_ctx<SMEM>(a, s_raw, slot);
+    learn_cat_rows<SMEM>(a, ctx, cb, ce, kf, ke);
+    nb_lean_flush<SMEM>(a, ctx, slot);
+}
+
+template <bool WIDE, bool SMEM>
+__global__ void __launch_bounds__(NB_LEARN_THREADS, 2) k_cell_warp(LearnArgs a, int wb, int we, int slot)
+{
+    extern __shared__ unsigned char s_raw[];
+    __shared__ double s_e[NB_LWARPS][NB_MAX_CARD + 1];
+    const LearnCtx<SMEM> ctx = nb_lean_ctx<SMEM>(a, s_raw, slot);
+    learn_warp_rows<WIDE, SMEM>(a, ctx, s_e[threadIdx.x >> 5], wb, we);
+    nb_lean_flush<SMEM>(a, ctx, slot);
+}
+
+// apply the cell's sums to the global weights and clear the table for its next use
+__global__ void k_cell_apply(LearnArgs a, int slot)
+{
+    nb_fix_t *g_gf = a.g_grad + (size_t)slot * a.W;
+    uint32_t *g_cn = a.g_cnt + (size_t)slot * a.W;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < a.W; w += (int64_t)gridDim.x * blockDim.x) {
+        const nb_fix_t Gi = g_gf[w];
+        const uint32_t n = g_cn[w];
+        if (Gi == 0 && n == 0u) continue;
+        g_gf[w] = 0;
+        g_cn[w] = 0u;
+        if (!a.wfixed[w])
+            a.weight[w] = nb_apply_update(a.weight[w], (double)Gi * (1.0 / NB_GRAD_UNIT), n, a.regularization, a.step,
+                                          a.reg_param, a.truncation);
     }
 }
 
@@ -777,6 +971,7 @@ static LearnArgs learn_args(nb_graph *g)
     a.weight = g->d_weight; a.wfixed = g->d_wfixed; a.n_trows = g->n_trows; a.W = (int)g->W;
     a.g_grad = g->d_grad; a.g_cnt = g->d_nvis; a.bar = g->d_learn_bar;
     a.tt_ptr = g->d_tt_ptr; a.tt = g->d_tt; a.tt_base = g->d_tt_base; a.tt_wid = g->d_tt_wid;
+    a.cat_ptr = g->d_cat_ptr; a.cat = g->d_cat; a.cat_wid = g->d_cat_wid; a.cat_first = g->n_frows;
     return a;
 }
 
@@ -843,6 +1038,7 @@ static int learn_prepare(nb_graph *g, LearnArgs &a, std::vector<int64_t> &vmax, 
             // truth-table rows of this colour average >= 16 incidences: spread each row over a warp
             lr[(size_t)c] = ((cr.p_end - cr.p_beg) + (cr.f_end - cr.f_beg)) > 0 && cr.edges >= 16 * rows;
         }
+        g->learn_long_rows = lr;
         NB_TRY(nb_alloc(g, &g->d_long_rows, lr.size(), false));
         NB_CUDA(cudaMemcpyAsync(g->d_long_rows, lr.data(), lr.size(), cudaMemcpyHostToDevice, g->stream));
         NB_CUDA(cudaStreamSynchronize(g->stream));
@@ -967,6 +1163,80 @@ static int launch_cells(nb_graph *g, const LearnArgs &a, const CellPlan &plan, i
                 : launch_cells_t<false, false>(g, a, plan, cell_beg, cell_end, only_color);
 }
 
+// one cell as ordinary launches (throughput mode)
+template <bool WIDE, bool SMEM>
+static int launch_cell_lean_t(nb_graph *g, const LearnArgs &a, const CellPlan &plan, int block, int color)
+{
+    CellPlan hp = plan;
+    hp.win_start = g->win_start.data();            // host copy of the window table
+    int rng[2 * NB_N_CLASSES];
+    for (int cls = 0; cls < NB_N_CLASSES; cls++) nb_plan_range(hp, cls, color, block, rng[2 * cls], rng[2 * cls + 1]);
+    const int pb = rng[2 * NB_CLASS_PAIR], pe = rng[2 * NB_CLASS_PAIR + 1], fb = rng[2 * NB_CLASS_FAST], fe = rng[2 * NB_CLASS_FAST + 1],
+              cb = rng[2 * NB_CLASS_CAT], ce = rng[2 * NB_CLASS_CAT + 1], tb = rng[2 * NB_CLASS_GEN], te = rng[2 * NB_CLASS_GEN + 1];
+    const int wb = rng[2 * NB_CLASS_WARP] - (int)g->n_trows, we = rng[2 * NB_CLASS_WARP + 1] - (int)g->n_trows;
+    if (pe <= pb && fe <= fb && ce <= cb && te <= tb && we <= wb) return NB_OK;
+    const size_t smem = SMEM ? (size_t)g->W * 24 : 0;
+    int sms = 0;
+    NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
+    // shared-memory tables are flushed once per CTA: fewer, longer-lived CTAs (the loops are grid-stride)
+    const int64_t cap = (int64_t)sms * (SMEM ? 8 : 32);
+    const uint32_t kf = nb_fold_key(a.seed, a.epoch, NB_TAG_FREE), ke = nb_fold_key(a.seed, a.epoch, NB_TAG_EVID),
+                   kt = nb_fold_key(a.seed, a.epoch, NB_TAG_TRUNC);
+    if (smem > 32 * 1024) {
+        NB_CUDA(cudaFuncSetAttribute(k_cell_tt<SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NB_CUDA(cudaFuncSetAttribute(k_cell_thread<WIDE, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NB_CUDA(cudaFuncSetAttribute(k_cell_cat<SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NB_CUDA(cudaFuncSetAttribute(k_cell_warp<WIDE, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (pe > pb || fe > fb) {
+        const int64_t rows = (int64_t)(pe - pb) + (fe - fb);
+        const int by_row = (g->learn_long_rows[(size_t)color] || rows <= 2 * cap * NB_LWARPS) ? 1 : 0;
+        const int64_t need = by_row ? (rows + NB_LWARPS - 1) / NB_LWARPS : (rows / 32 + 2 + NB_LWARPS - 1) / NB_LWARPS;
+        k_cell_tt<SMEM><<<(unsigned)std::max<int64_t>(1, std::min(need, cap)), NB_LEARN_THREADS, smem, g->stream>>>(
+            a, pb, pe, fb, fe, by_row, 0, kf, ke, kt);
+        g->launches++;
+    }
+    if (ce > cb) {
+        const int64_t need = ((int64_t)(ce - cb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
+        k_cell_cat<SMEM><<<(unsigned)std::max<int64_t>(1, std::min(need, cap)), NB_LEARN_THREADS, smem, g->stream>>>(a, cb, ce, 0, kf, ke);
+        g->launches++;
+    }
+    if (te > tb) {
+        const int64_t need = ((int64_t)(te - tb) + NB_LEARN_THREADS - 1) / NB_LEARN_THREADS;
+        k_cell_thread<WIDE, SMEM><<<(unsigned)std::max<int64_t>(1, std::min(need, cap)), NB_LEARN_THREADS, smem, g->stream>>>(a, tb, te, 0);
+        g->launches++;
+    }
+    if (we > wb) {
+        const int64_t need = ((int64_t)(we - wb) + NB_LWARPS - 1) / NB_LWARPS;
+        k_cell_warp<WIDE, SMEM><<<(unsigned)std::max<int64_t>(1, std::min(need, cap)), NB_LEARN_THREADS, smem, g->stream>>>(a, wb, we, 0);
+        g->launches++;
+    }
+    k_cell_apply<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((g->W + 255) / 256, cap)), 256, 0, g->stream>>>(a, 0);
+    g->launches++;
+    return NB_OK;
+}
+
+static int launch_cell_lean(nb_graph *g, const LearnArgs &a, const CellPlan &plan, int block, int color)
+{
+    const bool smem = g->W <= NB_LEARN_SMEM_W;
+    if (g->wide) return smem ? launch_cell_lean_t<true, true>(g, a, plan, block, color) : launch_cell_lean_t<true, false>(g, a, plan, block, color);
+    return smem ? launch_cell_lean_t<false, true>(g, a, plan, block, color) : launch_cell_lean_t<false, false>(g, a, plan, block, color);
+}
+
+// Latency mode (persistent kernel) or throughput mode (lean launches per cell)?  The persistent
+// grid has 2 x 256 threads per SM; beyond ~16 rows per thread and cell the cells are long enough
+// (hundreds of microseconds) for launch overhead not to matter and for occupancy to decide.
+static bool lean_mode(const nb_graph *g, int64_t cells)
+{
+    const char *e = getenv("NUMBSKULL_B200_LEARN_MODE");   // 1 persistent, 2 lean (tests compare the two)
+    const int force = e ? atoi(e) : 0;
+    if (force == 1) return false;
+    if (force == 2) return true;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+    return g->V / std::max<int64_t>(cells, 1) > (int64_t)sms * 2 * NB_LEARN_THREADS * 2;
+}
+
 // one (block, colour) cell: the partitioned runner exchanges halo values between the cells itself
 int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step, int regularization, double reg_param,
                    double truncation, int learn_non_evidence, uint64_t seed, uint64_t epoch)
@@ -978,7 +1248,13 @@ int nb_learn_color(nb_graph *g, int color, int block, int n_blocks, double step,
     NB_TRY(learn_prepare(g, a, vmax, learn_non_evidence));
     a.seed = seed; a.reg_param = reg_param; a.truncation = truncation; a.regularization = regularization;
     a.step = step; a.epoch = epoch;
-    NB_TRY(launch_cells(g, a, make_plan(g, n_blocks), block, block + 1, color));
+    if (lean_mode(g, (int64_t)n_blocks * g->n_colors)) {
+        NB_CUDA(cudaMemsetAsync(a.g_grad, 0, (size_t)g->W * sizeof(nb_fix_t), g->stream));
+        NB_CUDA(cudaMemsetAsync(a.g_cnt, 0, (size_t)g->W * sizeof(uint32_t), g->stream));
+        NB_TRY(launch_cell_lean(g, a, make_plan(g, n_blocks), block, color));
+    } else {
+        NB_TRY(launch_cells(g, a, make_plan(g, n_blocks), block, block + 1, color));
+    }
     g->weights_version++;
     NB_CUDA(cudaGetLastError());
     return NB_OK;
@@ -998,10 +1274,19 @@ int nb_run_learn(nb_graph *g, int64_t n_epochs, double *stepsize, double decay, 
         a.epoch = g->epoch_counter++;
         const int nb = block_count(g, vmax, default_batch_visits(step, batch_visits));
         const int64_t cells = (int64_t)nb * g->n_colors;
-        // one persistent launch per epoch (cell indices are 32-bit: split absurdly long epochs)
-        for (int64_t c0 = 0; c0 < cells; c0 += (1 << 30)) {
-            const int64_t c1 = std::min<int64_t>(cells, c0 + (1 << 30));
-            NB_TRY(launch_cells(g, a, make_plan(g, nb), (int)c0, (int)c1, -1));
+        if (lean_mode(g, cells)) {
+            // throughput mode: a few lean launches per cell (table 0 starts clear, k_cell_apply clears it again)
+            NB_CUDA(cudaMemsetAsync(a.g_grad, 0, (size_t)g->W * sizeof(nb_fix_t), g->stream));
+            NB_CUDA(cudaMemsetAsync(a.g_cnt, 0, (size_t)g->W * sizeof(uint32_t), g->stream));
+            const CellPlan plan = make_plan(g, nb);
+            for (int b = 0; b < nb; b++)
+                for (int c = 0; c < g->n_colors; c++) NB_TRY(launch_cell_lean(g, a, plan, b, c));
+        } else {
+            // latency mode: one persistent launch per epoch (cell indices are 32-bit: split absurdly long epochs)
+            for (int64_t c0 = 0; c0 < cells; c0 += (1 << 30)) {
+                const int64_t c1 = std::min<int64_t>(cells, c0 + (1 << 30));
+                NB_TRY(launch_cells(g, a, make_plan(g, nb), (int)c0, (int)c1, -1));
+            }
         }
         g->weights_version++;
         NB_CUDA(cudaGetLastError());

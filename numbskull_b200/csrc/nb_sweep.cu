@@ -317,6 +317,22 @@ __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_finish(S
     }
 }
 
+// The row classes of one colour are independent of each other (same colour: no shared factor), so
+// with g->fan_out their kernels run CONCURRENTLY: the class with the most rows stays on the graph's
+// stream, the others go to auxiliary streams forked and joined with events.  On the KBC shape a
+// colour is one big FAST launch plus a small PAIR launch and two tiny hub (warp-path) launches, which
+// used to run one after the other (launch gaps + under-filled tails: a few % of the sweep).
+static int fan_streams(nb_graph *g)
+{
+    if (g->aux[0]) return NB_OK;
+    for (int i = 0; i < NB_AUX_STREAMS; i++) {
+        NB_CUDA(cudaStreamCreateWithFlags(&g->aux[i], cudaStreamNonBlocking));
+        NB_CUDA(cudaEventCreateWithFlags(&g->ev_join[i], cudaEventDisableTiming));
+    }
+    NB_CUDA(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+    return NB_OK;
+}
+
 int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidence, uint64_t seed, uint64_t epoch)
 {
     if (color < 0) NB_FAIL(NB_ERR_INVALID, "negative colour %d", color);
@@ -325,34 +341,46 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     if (!burnin && epoch != g->last_tally_epoch) { g->tally_bound++; g->last_tally_epoch = epoch; }
     SweepArgs a = sweep_args(g, 0, burnin, sample_evidence, seed, epoch);
     if (c.f_end > c.f_beg || c.c_end > c.c_beg) NB_TRY(nb_refresh_inlined_weights(g));
+    // streams of the five row classes (PAIR, FAST, CAT, GEN, WARP)
+    const int64_t rows[5] = {c.p_end - c.p_beg, c.f_end - c.f_beg, c.c_end - c.c_beg, c.t_end - c.t_beg, c.w_end - c.w_beg};
+    cudaStream_t st[5] = {g->stream, g->stream, g->stream, g->stream, g->stream};
+    int n_aux = 0, aux_of[5] = {-1, -1, -1, -1, -1};
+    if (g->fan_out) {
+        int big = 0, n_live = 0;
+        for (int k = 0; k < 5; k++) { if (rows[k] > rows[big]) big = k; n_live += rows[k] > 0; }
+        if (n_live > 1) {
+            NB_TRY(fan_streams(g));
+            NB_CUDA(cudaEventRecord(g->ev_fork, g->stream));
+            for (int k = 0; k < 5; k++)
+                if (k != big && rows[k] > 0 && n_aux < NB_AUX_STREAMS) {
+                    aux_of[k] = n_aux;
+                    st[k] = g->aux[n_aux];
+                    NB_CUDA(cudaStreamWaitEvent(st[k], g->ev_fork, 0));
+                    n_aux++;
+                }
+        }
+    }
     if (c.p_end > c.p_beg) {
         unsigned grid = (unsigned)((c.p_end - c.p_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        k_gibbs_tt2<<<grid, 256, 0, g->stream>>>(a, g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, c.p_beg, c.p_end, key);
+        k_gibbs_tt2<<<grid, 256, 0, st[0]>>>(a, g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, c.p_beg, c.p_end, key);
         g->launches++;
     }
     if (c.f_end > c.f_beg) {
         unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        static const int variant = [] { const char *e = getenv("NUMBSKULL_B200_TT_VARIANT"); return e ? atoi(e) : 0; }();
-        switch (variant) {   // experiment knob: unroll depth / registers-for-occupancy trade-off
-        case 1: k_gibbs_tt<2, 8><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
-        case 2: k_gibbs_tt<4, 8><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
-        case 3: k_gibbs_tt<8, 4><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
-        case 4: k_gibbs_tt<8, 6><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
-        default: k_gibbs_tt<4, 1><<<grid, 256, 0, g->stream>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key); break;
-        }
+        k_gibbs_tt<4, 1><<<grid, 256, 0, st[1]>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
         g->launches++;
     }
     if (c.c_end > c.c_beg) {
         unsigned grid = (unsigned)((c.c_end - c.c_beg + 255) / 256);
-        k_gibbs_cat<<<grid, 256, 0, g->stream>>>(a, g->d_cat_ptr, g->d_cat, g->n_frows, c.c_beg, c.c_end);
+        k_gibbs_cat<<<grid, 256, 0, st[2]>>>(a, g->d_cat_ptr, g->d_cat, g->n_frows, c.c_beg, c.c_end);
         g->launches++;
     }
     if (c.t_end > c.t_beg) {
         unsigned grid = (unsigned)((c.t_end - c.t_beg + 255) / 256);
-        if (g->wide) k_gibbs_thread<true><<<grid, 256, 0, g->stream>>>(a, c.t_beg, c.t_end);
-        else k_gibbs_thread<false><<<grid, 256, 0, g->stream>>>(a, c.t_beg, c.t_end);
+        if (g->wide) k_gibbs_thread<true><<<grid, 256, 0, st[3]>>>(a, c.t_beg, c.t_end);
+        else k_gibbs_thread<false><<<grid, 256, 0, st[3]>>>(a, c.t_beg, c.t_end);
         g->launches++;
     }
     if (c.w_end > c.w_beg) {
@@ -360,14 +388,19 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
         unsigned grid1 = (unsigned)((c.k_end - c.k_beg + NB_WARPS_PER_BLOCK - 1) / NB_WARPS_PER_BLOCK);
         unsigned grid2 = (unsigned)((c.w_end - c.w_beg + NB_WARPS_PER_BLOCK - 1) / NB_WARPS_PER_BLOCK);
         if (g->wide) {
-            k_gibbs_warp_partial<true><<<grid1, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.k_beg, c.k_end);
-            k_gibbs_warp_finish<true><<<grid2, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.w_beg, c.w_end);
+            k_gibbs_warp_partial<true><<<grid1, 32 * NB_WARPS_PER_BLOCK, 0, st[4]>>>(a, t, c.k_beg, c.k_end);
+            k_gibbs_warp_finish<true><<<grid2, 32 * NB_WARPS_PER_BLOCK, 0, st[4]>>>(a, t, c.w_beg, c.w_end);
         } else {
-            k_gibbs_warp_partial<false><<<grid1, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.k_beg, c.k_end);
-            k_gibbs_warp_finish<false><<<grid2, 32 * NB_WARPS_PER_BLOCK, 0, g->stream>>>(a, t, c.w_beg, c.w_end);
+            k_gibbs_warp_partial<false><<<grid1, 32 * NB_WARPS_PER_BLOCK, 0, st[4]>>>(a, t, c.k_beg, c.k_end);
+            k_gibbs_warp_finish<false><<<grid2, 32 * NB_WARPS_PER_BLOCK, 0, st[4]>>>(a, t, c.w_beg, c.w_end);
         }
         g->launches += 2;
     }
+    for (int k = 0; k < 5; k++)
+        if (aux_of[k] >= 0) {                       // join: the next colour reads what these kernels wrote
+            NB_CUDA(cudaEventRecord(g->ev_join[aux_of[k]], st[k]));
+            NB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_join[aux_of[k]], 0));
+        }
     NB_CUDA(cudaGetLastError());
     return NB_OK;
 }

@@ -8,6 +8,8 @@ Bars (BASELINE.json north_star):
   * marginals: max-abs <= 0.01 against exact enumeration / the oracle;
   * learned weights: within 3 sigma of the oracle's spread over 5 seeds.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -439,6 +441,24 @@ def test_learning_is_deterministic(name):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("name", ["bool_l2", "cat", "lf", "allfuncs"])
+def test_learning_modes_agree_bit_for_bit(name, monkeypatch):
+    """The two execution strategies of an epoch -- one persistent launch over all cells (small
+    cells) and lean per-class launches per cell (large cells) -- run the same row functions over
+    the same cells with integer sums: identical weights and chains."""
+    z = golden("run_" + name)
+    o = golden_opts(z)
+    runs = []
+    for mode in ("1", "2"):
+        monkeypatch.setenv("NUMBSKULL_B200_LEARN_MODE", mode)
+        fg = _fg_from_golden(z, seed=77)
+        fg.learn(1, 25, 0.01, 0.97, o.get("regularization", 2), 0.01, o.get("truncation", 1),
+                 learn_non_evidence=o.get("learn_non_evidence", False))
+        runs.append((fg.weight_value.copy(), fg.var_value.copy(), fg.var_value_evid.copy()))
+    for a, b in zip(runs[0], runs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_learning_large_weight_table_path():
     """W > shared-memory table -> global accumulation path."""
     from numbskull_b200 import synth
@@ -456,6 +476,14 @@ def test_learning_large_weight_table_path():
     fg2 = _fg_from_synth((w2, v, f, fm, dm, e), seed=6)
     fg2.learn(0, 300, 0.001, 0.99, 2, 0.0001, 1)
     assert np.array_equal(fg2.weight_value, fg.weight_value)      # integer global table: deterministic
+    for mode in ("1", "2"):
+        os.environ["NUMBSKULL_B200_LEARN_MODE"] = mode
+        try:
+            fg3 = _fg_from_synth((w2, v, f, fm, dm, e), seed=6)
+            fg3.learn(0, 300, 0.001, 0.99, 2, 0.0001, 1)
+        finally:
+            del os.environ["NUMBSKULL_B200_LEARN_MODE"]
+        assert np.array_equal(fg3.weight_value, fg.weight_value), mode
 
 
 # --------------------------------------------------------------------------- API drop-in
