@@ -163,7 +163,10 @@ __host__ __device__ inline uint32_t nb_pack_meta(int card, int evid, int dtype, 
 #define NB_KEY_WINDOW(k) ((int64_t)(((k) >> 20) & ((1ull << 27) - 1)))
 #define NB_KEY_GROUP_BITS(k) ((k) >> 47)
 #define NB_PAIR_MAX_WID ((1u << 22) - 1)
-#define NB_WARP_TASK 1024   /* incidences per warp task */
+/* incidences per warp task: two per lane.  A task is a chain of dependent loads per incidence
+   (offset -> header -> members -> values); with 1024 incidences a warp walked 32 of them back to
+   back (230 us per colour on the KBC hubs, a tenth of the sweep) */
+#define NB_WARP_TASK 64
 
 typedef uint8_t nb_val_t;  // variable values on the device (cardinality <= 255)
 #define NB_MAX_CARD 255

@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int 
 // FAST rows: truth-table stream, one 16-byte quad per incidence (weight value inlined), uniform
 // trip count per warp.  The energy difference comes from nb_tt_delta (nb_eval.cuh), the same
 // function the parity hook nb_potentials_records evaluates.
+#ifndef NB_TT_MINB
+#define NB_TT_MINB 6      /* minimum CTAs per SM of k_gibbs_tt: 40 registers, 75 % occupancy (C4 50 M: 1.45 -> 1.35 ms per sweep) */
+#endif
+#ifndef NB_TT_UNROLL_SWEEP
+#define NB_TT_UNROLL_SWEEP 4
+#endif
 template <int UNROLL, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_gibbs_tt(SweepArgs a, const int64_t *__restrict__ tt_ptr,
                                                         const uint4 *__restrict__ tt, int beg, int end, uint32_t key)
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_partial(
     }
 }
 
-// Phase 2: one warp per row sums its tasks' partials in task order, samples, stores, tallies.
+// Phase 2: one warp per row sums its tasks' partials, samples, stores, tallies.
 template <bool WIDE>
 __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_finish(SweepArgs a, WarpTasks t, int wbeg, int wend)
 {
@@ -294,11 +300,14 @@ __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_finish(S
     const int evid = NB_META_EVID(meta), card = NB_META_CARD(meta);
     if (!NB_META_VALID(meta) || evid == 4) return;
     if (!(evid == 0 || a.sample_evidence)) return;
+    // fixed summation tree (lane l takes tasks l, l + 32, ..., then the warp butterfly): the result
+    // depends on the row's task list only, not on the launch or the partition
     const int64_t t0 = t.task_ptr[wr], t1 = t.task_ptr[wr + 1];
-    for (int k = lane; k < card; k += 32) {
+    for (int k = 0; k < card; k++) {
         double s = 0.0;
-        for (int64_t q = t0; q < t1; q++) s += t.part[(size_t)q * t.stride + k];
-        s_e[warp][k] = s;
+        for (int64_t q = t0 + lane; q < t1; q += 32) s += t.part[(size_t)q * t.stride + k];
+        s = nb_warp_sum(s);
+        if (lane == 0) s_e[warp][k] = s;
     }
     __syncwarp();
     NbUniforms rng(a.rng_id[nid], a.epoch, NB_TAG_FREE, a.seed);
@@ -369,7 +378,7 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     if (c.f_end > c.f_beg) {
         unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        k_gibbs_tt<4, 1><<<grid, 256, 0, st[1]>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
+        k_gibbs_tt<NB_TT_UNROLL_SWEEP, NB_TT_MINB><<<grid, 256, 0, st[1]>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
         g->launches++;
     }
     if (c.c_end > c.c_beg) {
