@@ -1348,6 +1348,9 @@ int nb_build_finalize(nb_graph *g)
     }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaStreamSynchronize(g->stream));
+    // bit mirror of the values (nb_common.cuh): all-Boolean graphs made of record rows and hub rows
+    g->bits_eligible = g->max_card <= 2 && g->n_crows == g->n_frows && g->n_trows == g->n_crows && g->n_frows > 0;
+    if (g->bits_eligible) NB_TRY(nb_alloc(g, &g->d_valbits, (size_t)((g->n_trows + g->n_wrows + 31) / 32 + 1)));
     nb_release_color_scratch(g);
     g->finalized = true;
     nb_set_l2_policy(g, g->stream);

@@ -193,6 +193,14 @@ struct nb_graph {
 #define NB_AUX_STREAMS 4
     cudaStream_t aux[NB_AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // concurrent row classes of one colour
     cudaEvent_t ev_fork = nullptr, ev_join[NB_AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    // Bit-packed mirror of the chain-0 values for the member gathers of the record kernels.  On an
+    // all-Boolean graph whose value array no longer fits in L2 (200 M variables = 200 MB against
+    // 126 MB) every second gather misses and costs a 32-byte DRAM sector for one byte; 1/8 of the
+    // size stays resident.  Rebuilt from d_val[0] on entry to nb_gibbs_sweeps, kept current by the
+    // kernels; the bytes stay authoritative for everything else.
+    uint32_t *d_valbits = nullptr;
+    bool bits_eligible = false;      // only PAIR / FAST / WARP rows, every variable Boolean
+    bool use_bits = false;           // inside nb_gibbs_sweeps
     bool fan_out = false;             // nb_gibbs_sweeps on a single-GPU graph: run a colour's row classes concurrently
 
     // sizes
@@ -350,6 +358,7 @@ void nb_p2p_wait_args(nb_graph *g, const volatile uint32_t **flags, const int32_
                       int **error);
 
 // build steps (nb_build.cu)
+int nb_pack_value_bits(nb_graph *g);
 int nb_build_device_graph(nb_graph *g, const nb_graph_desc *desc);
 int nb_build_color_round(nb_graph *g, int64_t *remaining);
 int nb_build_color_restart(nb_graph *g, int mode);

@@ -591,9 +591,19 @@ __device__ inline NbHdr nb_tabulate(const NbRow &r, int pos, uint32_t self, uint
 
 // e1 - e0 of a FAST row from its quads (lane-strided SELL layout: quad j at qp[j * 32]).
 #define NB_TT_UNROLL_DEFAULT 4
-template <int NB_TT_UNROLL = NB_TT_UNROLL_DEFAULT>
-__device__ __forceinline__ double nb_tt_delta(const uint4 *__restrict__ qp, int n, uint32_t self,
-                                              const nb_val_t *__restrict__ vals)
+// where the record kernels read member values from: the byte array, or (large all-Boolean graphs,
+// see nb_graph::d_valbits) a bit-packed mirror of it that stays L2-resident
+struct NbValsBytes {
+    const nb_val_t *__restrict__ v;
+    __device__ __forceinline__ int operator()(uint32_t id) const { return (int)v[id]; }
+};
+struct NbValsBits {
+    const uint32_t *__restrict__ b;
+    __device__ __forceinline__ int operator()(uint32_t id) const { return (int)((b[id >> 5] >> (id & 31u)) & 1u); }
+};
+
+template <int NB_TT_UNROLL = NB_TT_UNROLL_DEFAULT, class Vals>
+__device__ __forceinline__ double nb_tt_delta_v(const uint4 *__restrict__ qp, int n, uint32_t self, const Vals vals)
 {
     double d = 0.0;
     for (int j = 0; j < n; j += NB_TT_UNROLL) {
@@ -604,14 +614,20 @@ __device__ __forceinline__ double nb_tt_delta(const uint4 *__restrict__ qp, int 
         int xa[NB_TT_UNROLL], xb[NB_TT_UNROLL];
 #pragma unroll
         for (int t = 0; t < NB_TT_UNROLL; t++) {
-            xa[t] = (int)vals[q[t].x];
-            xb[t] = (int)vals[q[t].y];
+            xa[t] = vals(q[t].x);
+            xb[t] = vals(q[t].y);
         }
 #pragma unroll
         for (int t = 0; t < NB_TT_UNROLL; t++)
             d = fma((double)__uint_as_float(q[t].w), (double)nb_tt_diff(q[t].z, nb_tt_index(xa[t], xb[t])), d);
     }
     return d;
+}
+template <int NB_TT_UNROLL = NB_TT_UNROLL_DEFAULT>
+__device__ __forceinline__ double nb_tt_delta(const uint4 *__restrict__ qp, int n, uint32_t self,
+                                              const nb_val_t *__restrict__ vals)
+{
+    return nb_tt_delta_v<NB_TT_UNROLL>(qp, n, self, NbValsBytes{vals});
 }
 
 // Pair records (NB_CLASS_PAIR): incidences with at most ONE other member take 8 bytes,
@@ -631,8 +647,9 @@ __host__ __device__ inline uint32_t nb_pack_pair(uint32_t table9, int fixed, uin
 }
 
 #define NB_TT2_UNROLL 2
-__device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int n, uint32_t common, uint32_t self,
-                                               const nb_val_t *__restrict__ vals, const double *__restrict__ weight)
+template <class Vals>
+__device__ __forceinline__ double nb_tt2_delta_v(const uint4 *__restrict__ qp, int n, uint32_t common, uint32_t self,
+                                                 const Vals vals, const double *__restrict__ weight)
 {
     if (common != NB_PAIR_NONE) {
         const double w = __ldg(weight + (common >> 10));
@@ -642,7 +659,7 @@ __device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int
             const uint32_t o[4] = {q.x, q.y, q.z, q.w};
             int x[4];
 #pragma unroll
-            for (int t = 0; t < 4; t++) x[t] = (int)vals[o[t] == NB_PAIR_NONE ? self : o[t]];
+            for (int t = 0; t < 4; t++) x[t] = vals(o[t] == NB_PAIR_NONE ? self : o[t]);
 #pragma unroll
             for (int t = 0; t < 4; t++)
                 acc += o[t] == NB_PAIR_NONE ? 0 : (int)((common >> (3 * min(x[t], 2))) & 7u) - 2;
@@ -660,8 +677,8 @@ __device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int
         double w0[NB_TT2_UNROLL], w1[NB_TT2_UNROLL];
 #pragma unroll
         for (int t = 0; t < NB_TT2_UNROLL; t++) {
-            x0[t] = (int)vals[q[t].x];
-            x1[t] = (int)vals[q[t].z];
+            x0[t] = vals(q[t].x);
+            x1[t] = vals(q[t].z);
             w0[t] = __ldg(weight + (q[t].y >> 10));
             w1[t] = __ldg(weight + (q[t].w >> 10));
         }
@@ -672,6 +689,11 @@ __device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int
         }
     }
     return d;
+}
+__device__ __forceinline__ double nb_tt2_delta(const uint4 *__restrict__ qp, int n, uint32_t common, uint32_t self,
+                                               const nb_val_t *__restrict__ vals, const double *__restrict__ weight)
+{
+    return nb_tt2_delta_v(qp, n, common, self, NbValsBytes{vals}, weight);
 }
 
 // Categorical records (NB_CLASS_CAT): one quad per incidence of an AND_CAT / EQUAL_CAT_CONST factor

@@ -21,6 +21,7 @@ struct SweepArgs {
     int32_t *count;
     int32_t *count_b;
     nb_val_t *val;
+    uint32_t *valbits;       // bit-packed mirror of val (nullptr: not in use), see nb_graph::d_valbits
     const double *weight;
     int64_t n_trows;
     uint64_t seed, epoch;
@@ -57,6 +58,7 @@ static SweepArgs sweep_args(nb_graph *g, int chain, int burnin, int sample_evide
     a.vmeta = g->d_vmeta; a.slice_ptr = g->d_slice_ptr; a.twords = g->d_twords;
     a.wrow_ptr = g->d_wrow_ptr; a.wwords = g->d_wwords; a.inc_ptr = g->d_inc_ptr; a.inc = g->d_inc;
     a.rng_id = g->d_rng_id; a.cstart = g->d_cstart; a.count = g->d_count; a.count_b = g->d_count_b; a.val = g->d_val[chain];
+    a.valbits = (g->use_bits && chain == 0) ? g->d_valbits : nullptr;
     a.weight = g->d_weight; a.n_trows = g->n_trows; a.seed = seed; a.epoch = epoch;
     a.burnin = burnin; a.sample_evidence = sample_evidence;
     nb_p2p_wait_args(g, &a.w_flags, &a.w_neigh, &a.w_n, &a.w_phase, &a.w_error);
@@ -97,52 +99,91 @@ __global__ void __launch_bounds__(256) k_gibbs_thread(SweepArgs a, int beg, int 
 #ifndef NB_TT_UNROLL_SWEEP
 #define NB_TT_UNROLL_SWEEP 4
 #endif
-template <int UNROLL, int MINB>
+// Publishes the draws of one warp (32 consecutive ids = one word) in the bit mirror.
+__device__ __forceinline__ void nb_publish_bits(uint32_t *valbits, int64_t nid, bool sampled, int k)
+{
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, sampled), b = __ballot_sync(0xFFFFFFFFu, sampled && k);
+    if ((threadIdx.x & 31) == 0 && m) valbits[nid >> 5] = (valbits[nid >> 5] & ~m) | b;
+}
+
+template <int UNROLL, int MINB, bool BITS>
 __global__ void __launch_bounds__(256, MINB) k_gibbs_tt(SweepArgs a, const int64_t *__restrict__ tt_ptr,
                                                         const uint4 *__restrict__ tt, int beg, int end, uint32_t key)
 {
     nb_wait_halo(a);
-    const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (nid >= end) return;
+    const int64_t nid0 = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (!BITS && nid0 >= end) return;
+    const bool in = nid0 < end;
+    const int64_t nid = in ? nid0 : (int64_t)end - 1;         // (BITS: whole warps stay for the ballot)
     // independent loads first: they overlap with the stream
     const uint32_t meta = nb_lds(a.vmeta + nid);
     const uint32_t rid = nb_lds(a.rng_id + nid);
     const int64_t q0 = nb_lds(tt_ptr + (nid >> 5)), q1 = nb_lds(tt_ptr + (nid >> 5) + 1);
     const int n = (int)((q1 - q0) >> 5);                      // incidences of the longest row of this slice
-    const double d = nb_tt_delta<UNROLL>(tt + q0 + (nid & 31), n, (uint32_t)nid, a.val);   // e1 - e0
+    const double d = BITS ? nb_tt_delta_v<UNROLL>(tt + q0 + (nid & 31), n, (uint32_t)nid, NbValsBits{a.valbits})
+                          : nb_tt_delta_v<UNROLL>(tt + q0 + (nid & 31), n, (uint32_t)nid, NbValsBytes{a.val});   // e1 - e0
     const int evid = NB_META_EVID(meta);
-    if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
-    if (!(evid == 0 || a.sample_evidence)) return;          // :24
+    // inference.py:21-24
+    const bool sampled = in && NB_META_VALID(meta) && evid != 4 && (evid == 0 || a.sample_evidence);
+    if (!BITS && !sampled) return;
     const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, key);
     // P(0) = 1 / (1 + exp(e1 - e0)): draw_sample (inference.py:36-52) for cardinality 2
     const float p0 = 1.0f / (1.0f + __expf((float)d));
     const int k = u <= (double)p0 ? 0 : 1;
-    a.val[nid] = (nb_val_t)k;
-    if (!a.burnin && k) __stcs(a.count_b + nid, nb_lds(a.count_b + nid) + 1);   // inference.py:30-31
+    if (sampled) {
+        a.val[nid] = (nb_val_t)k;
+        if (!a.burnin && k) __stcs(a.count_b + nid, nb_lds(a.count_b + nid) + 1);   // inference.py:30-31
+    }
+    if (BITS) nb_publish_bits(a.valbits, nid0, sampled, k);
 }
 
 // PAIR rows: 8-byte records, two per quad -- or, in uniform slices, bare member ids, four per quad.
+template <bool BITS>
 __global__ void __launch_bounds__(256) k_gibbs_tt2(SweepArgs a, const int64_t *__restrict__ tt2_ptr,
                                                    const uint32_t *__restrict__ tt2_common,
                                                    const uint4 *__restrict__ tt2, int beg, int end, uint32_t key)
 {
     nb_wait_halo(a);
-    const int64_t nid = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (nid >= end) return;
+    const int64_t nid0 = (int64_t)beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (!BITS && nid0 >= end) return;
+    const bool in = nid0 < end;
+    const int64_t nid = in ? nid0 : (int64_t)end - 1;
     const uint32_t meta = nb_lds(a.vmeta + nid);
     const uint32_t rid = nb_lds(a.rng_id + nid);
     const int64_t q0 = nb_lds(tt2_ptr + (nid >> 5)), q1 = nb_lds(tt2_ptr + (nid >> 5) + 1);
     const uint32_t common = nb_lds(tt2_common + (nid >> 5));
     const int n = (int)((q1 - q0) >> 5);                      // quads of the longest row of this slice
-    const double d = nb_tt2_delta(tt2 + q0 + (nid & 31), n, common, (uint32_t)nid, a.val, a.weight);   // e1 - e0
+    const double d = BITS ? nb_tt2_delta_v(tt2 + q0 + (nid & 31), n, common, (uint32_t)nid, NbValsBits{a.valbits}, a.weight)
+                          : nb_tt2_delta_v(tt2 + q0 + (nid & 31), n, common, (uint32_t)nid, NbValsBytes{a.val}, a.weight);   // e1 - e0
     const int evid = NB_META_EVID(meta);
-    if (!NB_META_VALID(meta) || evid == 4) return;          // inference.py:21-23
-    if (!(evid == 0 || a.sample_evidence)) return;          // :24
+    const bool sampled = in && NB_META_VALID(meta) && evid != 4 && (evid == 0 || a.sample_evidence);   // inference.py:21-24
+    if (!BITS && !sampled) return;
     const double u = nb_philox2x32_u53(rid, (uint32_t)a.epoch, key);
     const float p0 = 1.0f / (1.0f + __expf((float)d));
     const int k = u <= (double)p0 ? 0 : 1;
-    a.val[nid] = (nb_val_t)k;
-    if (!a.burnin && k) __stcs(a.count_b + nid, nb_lds(a.count_b + nid) + 1);   // inference.py:30-31
+    if (sampled) {
+        a.val[nid] = (nb_val_t)k;
+        if (!a.burnin && k) __stcs(a.count_b + nid, nb_lds(a.count_b + nid) + 1);   // inference.py:30-31
+    }
+    if (BITS) nb_publish_bits(a.valbits, nid0, sampled, k);
+}
+
+// val -> bit mirror (all-Boolean graphs): one word per warp
+__global__ void k_pack_bits(const nb_val_t *__restrict__ val, uint32_t *__restrict__ bits, int64_t n)
+{
+    const int64_t n32 = (n + 31) & ~31ll;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, i < n && val[i] != 0);
+        if ((threadIdx.x & 31) == 0) bits[i >> 5] = b;
+    }
+}
+
+int nb_pack_value_bits(nb_graph *g)
+{
+    const int64_t n = g->n_trows + g->n_wrows;
+    k_pack_bits<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, g->stream>>>(g->d_val[0], g->d_valbits, n);
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
 }
 
 // CAT rows: categorical variable (cardinality <= 32) with AND_CAT / EQUAL_CAT_CONST factors.  One
@@ -321,6 +362,7 @@ __global__ void __launch_bounds__(32 * NB_WARPS_PER_BLOCK) k_gibbs_warp_finish(S
         k = nb_draw_shared(s_e[warp], card, rng);
     }
     if (lane == 0) {
+        if (a.valbits && (int)a.val[nid] != k) atomicXor(a.valbits + (nid >> 5), 1u << (nid & 31));   // (all-Boolean graph)
         a.val[nid] = (nb_val_t)k;
         nb_tally(a, nid, card, k);
     }
@@ -372,13 +414,15 @@ int nb_launch_gibbs_color(nb_graph *g, int color, int burnin, int sample_evidenc
     if (c.p_end > c.p_beg) {
         unsigned grid = (unsigned)((c.p_end - c.p_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        k_gibbs_tt2<<<grid, 256, 0, st[0]>>>(a, g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, c.p_beg, c.p_end, key);
+        if (a.valbits) k_gibbs_tt2<true><<<grid, 256, 0, st[0]>>>(a, g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, c.p_beg, c.p_end, key);
+        else k_gibbs_tt2<false><<<grid, 256, 0, st[0]>>>(a, g->d_tt2_ptr, g->d_tt2_common, g->d_tt2, c.p_beg, c.p_end, key);
         g->launches++;
     }
     if (c.f_end > c.f_beg) {
         unsigned grid = (unsigned)((c.f_end - c.f_beg + 255) / 256);
         uint32_t key = nb_fold_key(seed, epoch, NB_TAG_FREE);
-        k_gibbs_tt<NB_TT_UNROLL_SWEEP, NB_TT_MINB><<<grid, 256, 0, st[1]>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
+        if (a.valbits) k_gibbs_tt<NB_TT_UNROLL_SWEEP, NB_TT_MINB, true><<<grid, 256, 0, st[1]>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
+        else k_gibbs_tt<NB_TT_UNROLL_SWEEP, NB_TT_MINB, false><<<grid, 256, 0, st[1]>>>(a, g->d_tt_ptr, g->d_tt, c.f_beg, c.f_end, key);
         g->launches++;
     }
     if (c.c_end > c.c_beg) {

@@ -304,3 +304,32 @@ def test_categorical_10m_sampled_energies(oracle):
     seen = _sampled(fg, og, rng, expect=(CAT,))
     assert seen[CAT] > 9000
     fg.clear()
+
+
+def test_bit_mirror_gives_identical_chains(monkeypatch):
+    """Large all-Boolean graphs read member values from a bit-packed mirror of the value array
+    (nb_graph::d_valbits; on by default from 10^8 variables).  It only changes WHERE a value is read:
+    forced on, the chains, tallies and marginals are bit-identical to the byte path -- on a KBC graph
+    with evidence, PAIR and FAST rows and (row-length knob lowered) hub rows, with values written
+    from the host between the calls."""
+    import numbskull_b200 as nb
+    from numbskull_b200 import synth
+    g = synth.kbc_fast(200_000, seed=11, hub_frac=0.02)
+    runs = []
+    for mode in ("-1", "0"):
+        monkeypatch.setenv("NUMBSKULL_B200_BIT_MIRROR", mode)
+        ns = nb.NumbSkull(quiet=True)
+        ns.loadFactorGraph(*g)
+        fg = ns.factorGraphs[0]
+        fg.seed, fg.warp_row_words = 5, 96
+        fg.inference(2, 3, sample_evidence=False)
+        a = fg.var_value[0].copy()
+        m1 = fg.marginals.copy()
+        info = fg.device_info()
+        assert info["n_warp_rows"] > 0 and info["n_pair_rows"] > 0 and info["n_fast_rows"] > 0
+        fg.var_value[0][::3] = 1 - fg.var_value[0][::3]           # host edit: the mirror is rebuilt per call
+        fg.inference(0, 4, sample_evidence=True)
+        runs.append((a, m1, fg.var_value[0].copy(), fg.marginals.copy(), fg.count.copy()))
+        fg.clear()
+    for x, y in zip(runs[0], runs[1]):
+        assert np.array_equal(x, y)
