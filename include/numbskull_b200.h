@@ -137,6 +137,13 @@ int nb_synth_kbc_block(int64_t nvar, uint64_t seed, int64_t n_weights, int64_t w
                        double hub_frac, const double *mix3, int64_t lo, int64_t hi, nb_factor_rec *factor,
                        int64_t *n_factor, nb_ftv_rec *fmap, int64_t *n_fmap);
 
+/* Owner-block partitions (partition.extract_local, the role of the reference's per-minion graph
+ * views, salt/src/messages.py:175-179): the ghost variables of block [lo, hi) in ascending global
+ * id, and (rewrite != 0) fmap[].vid translated to local ids (owned v -> v - lo, ghost -> n_owned +
+ * rank).  Two calls: ghosts == NULL returns the count. */
+int nb_block_ghosts(nb_ftv_rec *fmap, int64_t n_fmap, int64_t nvar, int64_t lo, int64_t hi, int64_t *ghosts,
+                    int64_t *n_ghosts, int rewrite);
+
 /* -------------------------- graph lifecycle -------------------------- */
 
 /* FactorGraph.__init__ (factorgraph.py:30-73): builds the device-resident

@@ -65,6 +65,7 @@ SIGNATURES = {
     "nb_synth_kbc_variables": (C.c_int, [_U64, _DBL, _P, _I64, _P]),
     "nb_synth_kbc_block": (C.c_int, [_I64, _U64, _I64, _I64, _DBL, _DBL, _P, _I64, _I64, _P, C.POINTER(_I64), _P,
                                      C.POINTER(_I64)]),
+    "nb_block_ghosts": (C.c_int, [_P, _I64, _I64, _I64, _I64, _P, C.POINTER(_I64), C.c_int]),
     "nb_graph_create": (C.c_int, [C.POINTER(GraphDesc), C.POINTER(_P)]),
     "nb_graph_destroy": (None, [_P]),
     "nb_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),

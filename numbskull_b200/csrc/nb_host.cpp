@@ -719,3 +719,64 @@ extern "C" int nb_synth_kbc_block(int64_t nvar, uint64_t seed, int64_t n_weights
     });
     return NB_OK;
 }
+
+// Ghost set of an owner block [lo, hi) and the translation of a rank-local fmap to local ids
+// (owned variable v -> v - lo, ghost -> n_owned + its rank among the ghosts, ascending global id):
+// what partition.extract_local does with numpy's unique / searchsorted, which takes a minute and
+// a half on the 600 M members of a 2-GPU cut of the 1 B-edge graph.  A bitmap over the global ids
+// and per-word prefix counts instead of a sort.  Call with ghosts == NULL for the count, then with
+// a buffer of that size; rewrite != 0 also rewrites fmap[].vid.
+extern "C" int nb_block_ghosts(nb_ftv_rec *fmap, int64_t n_fmap, int64_t nvar, int64_t lo, int64_t hi, int64_t *ghosts,
+                               int64_t *n_ghosts, int rewrite)
+{
+    if (!fmap && n_fmap) NB_FAIL(NB_ERR_INVALID, "nb_block_ghosts: fmap is NULL");
+    if (lo < 0 || hi < lo || hi > nvar) NB_FAIL(NB_ERR_INVALID, "nb_block_ghosts: bad block [%lld, %lld) of %lld", (long long)lo, (long long)hi, (long long)nvar);
+    const int64_t words = (nvar + 63) / 64;
+    std::vector<std::atomic<uint64_t>> bits((size_t)words);
+    const int nt = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    std::atomic<int> bad{0};
+    run_threads(nt, [&](int t) {
+        for (int64_t w = words * t / nt; w < words * (t + 1) / nt; w++) bits[(size_t)w].store(0, std::memory_order_relaxed);
+    });
+    run_threads(nt, [&](int t) {
+        for (int64_t i = n_fmap * t / nt; i < n_fmap * (t + 1) / nt; i++) {
+            const int64_t v = fmap[i].vid;
+            if (v < 0 || v >= nvar) { bad.store(1); continue; }
+            if (v >= lo && v < hi) continue;
+            const uint64_t m = 1ull << (v & 63);
+            if (!(bits[(size_t)(v >> 6)].load(std::memory_order_relaxed) & m)) bits[(size_t)(v >> 6)].fetch_or(m, std::memory_order_relaxed);
+        }
+    });
+    if (bad.load()) NB_FAIL(NB_ERR_INVALID, "nb_block_ghosts: a member id is outside [0, %lld)", (long long)nvar);
+    std::vector<int64_t> pre((size_t)words + 1, 0);
+    std::vector<int64_t> part((size_t)nt + 1, 0);
+    run_threads(nt, [&](int t) {
+        int64_t c = 0;
+        for (int64_t w = words * t / nt; w < words * (t + 1) / nt; w++) c += __builtin_popcountll(bits[(size_t)w].load(std::memory_order_relaxed));
+        part[(size_t)t + 1] = c;
+    });
+    for (int t = 0; t < nt; t++) part[(size_t)t + 1] += part[(size_t)t];
+    const int64_t total = part[(size_t)nt];
+    if (!ghosts) { *n_ghosts = total; return NB_OK; }
+    if (*n_ghosts != total) NB_FAIL(NB_ERR_INVALID, "nb_block_ghosts: the ghost count changed between the calls");
+    run_threads(nt, [&](int t) {
+        int64_t c = part[(size_t)t];
+        for (int64_t w = words * t / nt; w < words * (t + 1) / nt; w++) {
+            pre[(size_t)w] = c;
+            uint64_t x = bits[(size_t)w].load(std::memory_order_relaxed);
+            while (x) { ghosts[c++] = w * 64 + __builtin_ctzll(x); x &= x - 1; }
+        }
+    });
+    if (rewrite) {
+        const int64_t n_owned = hi - lo;
+        run_threads(nt, [&](int t) {
+            for (int64_t i = n_fmap * t / nt; i < n_fmap * (t + 1) / nt; i++) {
+                const int64_t v = fmap[i].vid;
+                if (v >= lo && v < hi) { fmap[i].vid = v - lo; continue; }
+                const uint64_t x = bits[(size_t)(v >> 6)].load(std::memory_order_relaxed) & ((1ull << (v & 63)) - 1);
+                fmap[i].vid = n_owned + pre[(size_t)(v >> 6)] + __builtin_popcountll(x);
+            }
+        });
+    }
+    return NB_OK;
+}

@@ -238,15 +238,16 @@ def kbc_block(nvar, lo, hi, seed=1004, n_weights=1 << 20, evidence_frac=0.1, win
     fmap = np.zeros(ne.value, FactorToVar)
     _lib.check(L.nb_synth_kbc_block(nvar, seed, n_weights, window, far_frac, hub_frac, _lib.ptr(m3), lo, hi,
                                     _lib.ptr(factor), C.byref(nf), _lib.ptr(fmap), C.byref(ne)))
-    gvid = fmap["vid"]
-    owned = (gvid >= lo) & (gvid < hi)
-    ghosts = np.unique(gvid[~owned])
+    # ghosts (ascending global id) and local member ids, by host threads (nb_block_ghosts)
+    ng = C.c_int64(0)
+    _lib.check(L.nb_block_ghosts(_lib.ptr(fmap), len(fmap), nvar, lo, hi, None, C.byref(ng), 0))
+    ghosts = np.empty(ng.value, np.int64)
+    _lib.check(L.nb_block_ghosts(_lib.ptr(fmap), len(fmap), nvar, lo, hi, _lib.ptr(ghosts), C.byref(ng), 1))
     n_owned = hi - lo
     global_vid = np.concatenate((np.arange(lo, hi, dtype=np.int64), ghosts))
     variable = np.zeros(len(global_vid), Variable)
     _lib.check(L.nb_synth_kbc_variables(seed, evidence_frac, _lib.ptr(global_vid), len(global_vid), _lib.ptr(variable)))
     variable["isEvidence"][n_owned:] = 4
-    fmap["vid"] = np.where(owned, gvid - lo, n_owned + np.searchsorted(ghosts, gvid))
     weight = np.zeros(n_weights, Weight)
     _lib.check(L.nb_synth_kbc_weights(seed, n_weights, fixed_frac, _lib.ptr(weight)))
     return dict(weight=weight, variable=variable, factor=factor, fmap=fmap,
