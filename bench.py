@@ -383,7 +383,8 @@ def block_c4(args, local_rank):
            "gpu_launches": int(l1 - l0),
            "rows": {"pair": int(info["n_pair_rows"]), "fast": int(info["n_fast_rows"]), "warp": int(info["n_warp_rows"])},
            "roofline": roofline(bytes_sweep, med, "k_gibbs_tt (FAST rows: 16-byte truth-table quads with the weight "
-                                "inlined; one launch per colour)", "k_gibbs_tt_c4_bytes_per_sweep"),
+                                "inlined, member gathers from the bit-packed value mirror; one launch per colour; "
+                                "traffic = all launches of one sweep)", "k_gibbs_tt_c4_bytes_per_sweep"),
            "e2e_first_call_ms": e2e_ms, "mean_marginal": float(m.mean()),
            "build_s": {"generate": round(t1 - t0, 1), "host_index": round(t2 - t1, 1), "device": round(t3 - t2, 1)}}
     fg.clear()

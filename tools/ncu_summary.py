@@ -16,8 +16,23 @@ UNITS = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms":
          "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}
 
 
+def load_long(rows):
+    """`ncu --csv --metrics ...` log (one row per launch and metric) -> one dict per launch."""
+    hdr = rows[0]
+    ik, im, iu, iv, ii = (hdr.index(c) for c in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID"))
+    per = {}
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        d = per.setdefault(r[ii], {"Kernel Name": r[ik]})
+        d[r[im]] = float(r[iv].replace(",", "")) * UNITS.get(r[iu], 1.0)
+    return list(per.values())
+
+
 def load(path):
-    rows = list(csv.reader(open(path)))
+    rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("==")]
+    if "Metric Name" in rows[0]:
+        return load_long(rows)
     hdr, units, data = rows[0], rows[1], rows[2:]
     out = []
     for r in data:
