@@ -98,7 +98,7 @@ def main():
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json")
         cur = json.load(open(path)) if os.path.exists(path) else {}
         cur[args.traffic_key] = traffic
-        cur[args.traffic_key + "_source"] = "%s (ncu --set full, %d launches matching /%s/ over %.3g step(s); %.1f us per step under ncu)" \
+        cur[args.traffic_key + "_source"] = "%s (ncu, %d launches matching /%s/ over %.3g step(s); %.1f us per step under ncu)" \
             % (os.path.relpath(args.csv), len(launches), args.kernel, args.steps, t_us)
         json.dump(cur, open(path, "w"), indent=1)
         print("wrote", os.path.normpath(path))
