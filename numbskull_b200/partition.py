@@ -556,9 +556,19 @@ class PartitionedGibbs(object):
         return self.inference(0, epochs, True)
 
     def learn(self, burnin_epochs, epochs, stepsize, decay, regularization, reg_param, truncation,
-              learn_non_evidence=False):
+              learn_non_evidence=False, weight_sync="sum"):
         """FactorGraph.learn across the ranks: per colour both chains' boundary values are
-        exchanged; per epoch the weight deltas are summed (numbskull_master.py:223-224)."""
+        exchanged; per epoch the ranks' weight deltas are combined.  ``weight_sync="sum"`` is the
+        reference master's rule (numbskull_master.py:223-224: ``weight_value += dw`` for every
+        minion): to first order the move of one sequential pass over all ranks' variables, and right
+        when a weight's factors live mostly on one rank.  ``"mean"`` averages the deltas (parameter
+        averaging): the stable rule for data-parallel cuts of a model whose weights are tied across
+        ALL ranks (the labelling-function model cut by candidate) -- there every rank's epoch already
+        moves a weight most of the way to its optimum, and the sum of N such moves overshoots N-fold
+        and diverges (505 M variables on 8 GPUs: |w| ~ 460 after 4 epochs)."""
+        if weight_sync not in ("sum", "mean"):
+            raise ValueError("weight_sync must be 'sum' or 'mean'")
+        scale = 1.0 / self.world if weight_sync == "mean" else 1.0
         fg, L, lib, torch = self.fg, self.lib.lib(), self.lib, self.torch
         g = fg._device_graph()
         fg._sync_device(0, 0)
@@ -580,7 +590,7 @@ class PartitionedGibbs(object):
                         delta = d.to(self.dev)
                     else:
                         self.dist.all_reduce(delta, group=self.group)
-                    w_prev = w_prev + delta
+                    w_prev = w_prev + delta * scale
                     lib.check(L.nb_set_weights_dev(g, C.c_void_p(w_prev.data_ptr())))
                 stepsize *= decay
                 continue
@@ -614,7 +624,7 @@ class PartitionedGibbs(object):
                     delta = d.to(self.dev)
                 else:
                     self.dist.all_reduce(delta, group=self.group)
-                w_prev = w_prev + delta
+                w_prev = w_prev + delta * scale
                 lib.check(L.nb_set_weights_dev(g, C.c_void_p(w_prev.data_ptr())))
             stepsize *= decay
         torch.cuda.synchronize()

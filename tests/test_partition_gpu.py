@@ -144,3 +144,45 @@ def test_partitioned_learning_matches_single_gpu(tmp_path):
     assert np.array_equal(res[0]["weights"], res[1]["weights"])    # every rank holds the summed weights
     assert np.abs(res[0]["weights"] - fg.weight_value[0]).max() < 0.15
     assert np.abs(res[0]["weights"] - [1.0, 1.0, 0.5]).max() < 0.25
+
+
+def _lf_worker(rank, world, port, out_dir, copies, n_lf, sync):
+    import torch
+    import torch.distributed as dist
+    from numbskull_b200 import partition
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ngpu = torch.cuda.device_count()
+    device = rank if ngpu >= world else 0
+    torch.cuda.set_device(device)
+    dist.init_process_group("nccl" if ngpu >= world else "gloo", rank=rank, world_size=world)
+    loc, n_global = partition.lf_block(copies, n_lf, rank, world)
+    run = partition.PartitionedGibbs(loc, n_global, rank, world, device, seed=5)
+    assert not run.any_halo                      # cut by candidate: no ghosts, whole epochs per launch
+    run.learn(0, 30, 0.0005, 1.0, 1, 0.01, 1.0, learn_non_evidence=True, weight_sync=sync)
+    np.save(os.path.join(out_dir, "w%d.npy" % rank), run.fg.weight_value[0].copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_candidate_parallel_lf_learning_averages_the_deltas(tmp_path):
+    """The labelling-function model cut by candidate ties every weight across ALL ranks.  With the
+    ranks' per-epoch deltas AVERAGED (weight_sync="mean") the weights follow the single-GPU run on
+    the same model; the reference master's SUM (numbskull_master.py:223-224) multiplies every move by
+    the number of ranks (observed: |w| ~ 460 after 4 epochs on 8 GPUs, profiles/r2v_c3_n8_sum.json)."""
+    import torch.multiprocessing as mp
+    import numbskull_b200 as nb
+    from numbskull_b200 import synth
+    copies, n_lf, world = 8000, 10, 2
+    mp.spawn(_lf_worker, args=(world, _free_port(), str(tmp_path), copies, n_lf, "mean"), nprocs=world, join=True)
+    w = [np.load(str(tmp_path / ("w%d.npy" % r))) for r in range(world)]
+    assert np.array_equal(w[0], w[1]) and np.isfinite(w[0]).all()
+    acc = np.random.default_rng(1003).uniform(0.55, 0.95, n_lf)           # lf_block's accuracies
+    ns = nb.NumbSkull(quiet=True)
+    ns.loadFactorGraph(*synth.lf_model(copies, n_lf, np.random.default_rng(8), accuracy=acc))
+    fg = ns.factorGraphs[0]
+    fg.seed, fg.device = 5, 0
+    fg.learn(0, 30, 0.0005, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)
+    one = fg.weight_value[0]
+    assert np.abs(w[0] - one).max() < 0.12, (w[0], one)
+    assert np.corrcoef(w[0][1:], acc)[0, 1] > 0.9                          # weight = log-odds / 2 of the accuracy

@@ -211,12 +211,14 @@ def c3_partitioned(scale):
     build_s = time.perf_counter() - t0
     fg = run.fg
     L, g = _lib.lib(), fg._g
-    run.learn(0, 1, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)            # warm-up epoch
+    # weights tied across all ranks: the ranks' deltas are averaged (see PartitionedGibbs.learn)
+    sync = os.environ.get("NB_WEIGHT_SYNC", "mean")
+    run.learn(0, 1, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True, weight_sync=sync)            # warm-up epoch
     torch.cuda.synchronize()
     dist.barrier()
     epochs = 3
     t1 = time.perf_counter()
-    run.learn(0, epochs, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)
+    run.learn(0, epochs, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True, weight_sync=sync)
     torch.cuda.synchronize()
     dist.barrier()
     dt = (time.perf_counter() - t1) / epochs
@@ -234,7 +236,7 @@ def c3_partitioned(scale):
         edges = copies * (1 + 2 * n_lf)
         w = fg.weight_value[0]
         print(json.dumps({"config": "c3_lf_%dx%d_partitioned" % (copies, n_lf), "n_gpus": world, "variables": n_global,
-                          "edges": edges, "colors": run.n_colors, "build_s": round(build_s, 1),
+                          "edges": edges, "colors": run.n_colors, "build_s": round(build_s, 1), "weight_sync": sync,
                           "device_GB_rank0": round(fg.device_info()["device_bytes"] / 1e9, 2),
                           "learn_ms_per_epoch": 1e3 * dt, "learn_edge_evals_per_s": edges / dt,
                           "inference_ms_per_sweep_wall": 1e3 * dti, "mean_marginal_y": stats[0].item() / max(stats[1].item(), 1),
