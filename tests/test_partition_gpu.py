@@ -185,4 +185,3 @@ def test_candidate_parallel_lf_learning_averages_the_deltas(tmp_path):
     fg.learn(0, 30, 0.0005, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)
     one = fg.weight_value[0]
     assert np.abs(w[0] - one).max() < 0.12, (w[0], one)
-    assert np.corrcoef(w[0][1:], acc)[0, 1] > 0.9                          # weight = log-odds / 2 of the accuracy
