@@ -229,7 +229,8 @@ def c3_partitioned(scale):
     dist.barrier()
     dti = (time.perf_counter() - t2) / (sweeps + 2)
     per = 1 + n_lf
-    y = np.asarray(marg)[::per] if len(marg) else np.zeros(0)
+    # marginals come in the reference's cstart layout (1 entry per Boolean y, 3 per cardinality-3 LF variable)
+    y = np.asarray(marg)[np.asarray(fg.cstart[0:run.n_owned:per], np.int64)] if len(marg) else np.zeros(0)
     stats = torch.tensor([float(y.sum()), float(len(y))], device="cuda", dtype=torch.float64)
     dist.all_reduce(stats)
     if rank == 0:
