@@ -220,8 +220,50 @@ def reference_throughput(steps, warmup, grid=None, threads=None, budget_s=150.0)
             "grid": grid, "var_samples_per_sec": nvar * steps / dt, "ms_per_step": 1e3 * dt / steps}
 
 
+def reference_learning_throughput(copies=5000, n_lf=100, epochs=2, threads=None):
+    """fg.learn() of the unmodified numba reference on the labelling-function model (BASELINE config 3
+    shape, options of test_lf_learning.py:129-137), nthreads = all host cores, time = the reference's own
+    fg.learning_total_time (factorgraph.py:196-205).  A bounded sample: loadFactorGraph's Python loops
+    alone need ~8 us per variable."""
+    numbskull, types = _import_reference()
+    Weight, Variable, Factor, FactorToVar = types
+    threads = threads or os.cpu_count() or 1
+    sys.path.insert(0, REPO)
+    from numbskull_b200 import synth
+    w, v, f, fm, dm, e = synth.lf_model(copies, n_lf, np.random.default_rng(1003))
+    conv = lambda a, t: np.ascontiguousarray(a).view(t) if a.dtype.itemsize == np.dtype(t).itemsize else a.astype(t)  # noqa: E731
+    ns = numbskull.NumbSkull(nthreads=threads, quiet=True, learn_non_evidence=True)
+    ns.loadFactorGraph(conv(w, Weight), conv(v, Variable), conv(f, Factor), conv(fm, FactorToVar), dm, e)
+    fg = ns.factorGraphs[0]
+
+    def learn(n):
+        fg.learn(0, n, 1e-4, 1.0, 1, 0.01, 1.0, learn_non_evidence=True)
+    learn(1)                                                            # JIT compilation happens here
+    t0 = fg.learning_total_time
+    learn(epochs)
+    dt = (fg.learning_total_time - t0) / epochs
+    edges = copies * (1 + 2 * n_lf)
+    return {"value": edges / dt, "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_epoch": 1e3 * dt,
+            "sample": "lf_model %d x %d (%d variables), %d learning epochs of the unmodified numba reference "
+                      "(baseline/_ref, numba learnthread), nthreads=%d, time = fg.learning_total_time"
+                      % (copies, n_lf, copies * (1 + n_lf), epochs, threads)}
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
+        return
+    if args.ref_mode == "learn":
+        try:
+            OUT.emit(json.dumps(dict(reference_learning_throughput(), impl="reference")))
+        except Exception as exc:  # noqa: BLE001
+            OUT.emit(json.dumps({"impl": "reference", "unavailable": "%s: %s" % (type(exc).__name__, exc)}))
+        return
+    if args.ref_mode == "single":
+        try:
+            r = reference_throughput(3, 1, grid=512, threads=1)
+            OUT.emit(json.dumps(dict({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}, impl="reference")))
+        except Exception as exc:  # noqa: BLE001
+            OUT.emit(json.dumps({"impl": "reference", "unavailable": "%s: %s" % (type(exc).__name__, exc)}))
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     try:
@@ -244,6 +286,18 @@ def run_reference(args):
     OUT.emit(json.dumps(line))
 
 
+def reference_child(mode):
+    """One bounded run of the numba reference in a child process (--ref-mode single | learn)."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-mode", mode],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+        line.pop("impl", None)
+        return line
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": "numba reference: %s" % exc}
+
+
 def cpu_baselines(no_port=False):
     """cpu_baseline leg of our arm: the numba reference in a child process (it must not share a
     process with this repo's `numbskull` alias package) on a bounded 1024^2 grid, plus the C port."""
@@ -256,6 +310,7 @@ def cpu_baselines(no_port=False):
         out = dict(line.get("cpu_baseline") or {"unavailable": line.get("unavailable")})
     except Exception as exc:  # noqa: BLE001
         out = {"unavailable": "numba reference: %s" % exc}
+    out["single_thread"] = reference_child("single")
     if not no_port:
         try:
             out["port"] = cpu_port_throughput(steps=3, warmup=1)
@@ -714,6 +769,8 @@ def run_ours(args):
         line["learn"] = learn
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baselines()
+        if learn is not None and "unavailable" not in learn:
+            learn["cpu_baseline"] = reference_child("learn")       # the reference's learnthread on the same model shape
     OUT.emit(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -753,6 +810,8 @@ def main():
     ap.add_argument("--workloads", default=os.environ.get("NB_BENCH_WORKLOADS", "c2,c4,c3"),
                     help="N = 1 only: extra blocks next to the c2 headline")
     ap.add_argument("--ref-grid", type=int, default=0, help="reference arm: force the grid size")
+    ap.add_argument("--ref-mode", default="inference", choices=["inference", "single", "learn"],
+                    help="reference arm: the headline inference line, or a bounded single-thread / learning sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
