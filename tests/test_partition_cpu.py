@@ -212,3 +212,41 @@ def test_salt_partition_keys_and_locality_owners():
     g_block = np.mean([partition.ghost_fraction(partition.extract_local_by_owner(w, v2, f, fm2, blocks, r)) for r in range(world)])
     g_smart = np.mean([partition.ghost_fraction(partition.extract_local_by_owner(w, v2, f, fm2, smart, r)) for r in range(world)])
     assert g_smart < 0.25 * g_block, (g_smart, g_block)
+
+
+def test_block_ghosts_matches_numpy_and_rejects_bad_input():
+    """nb_block_ghosts (threaded bitmap + prefix counts) against numpy's unique / searchsorted, the
+    rule of partition.extract_local: ghosts ascending by global id, owned v -> v - lo, ghost -> n_owned
+    + rank; empty member lists, empty blocks and blocks at either end; ids outside the graph are an
+    error, not a crash."""
+    import ctypes as C
+    import numpy as np
+    from numbskull_b200 import _lib
+    from numbskull_b200.numbskulltypes import FactorToVar
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    nvar = 100_003
+    for lo, hi, n in ((0, 40_000, 300_000), (60_000, nvar, 300_000), (50_000, 50_000, 1000), (10, 20, 0), (0, nvar, 5000)):
+        fm = np.zeros(n, FactorToVar)
+        fm["vid"] = rng.integers(0, nvar, n)
+        fm["dense_equal_to"] = rng.integers(0, 7, n)
+        gv = fm["vid"].copy()
+        owned = (gv >= lo) & (gv < hi)
+        want_ghosts = np.unique(gv[~owned])
+        want_local = np.where(owned, gv - lo, (hi - lo) + np.searchsorted(want_ghosts, gv))
+        ng = C.c_int64(-1)
+        _lib.check(L.nb_block_ghosts(_lib.ptr(fm), n, nvar, lo, hi, None, C.byref(ng), 0))
+        assert ng.value == len(want_ghosts)
+        assert np.array_equal(fm["vid"], gv)                       # the counting call rewrites nothing
+        ghosts = np.empty(ng.value, np.int64)
+        _lib.check(L.nb_block_ghosts(_lib.ptr(fm), n, nvar, lo, hi, _lib.ptr(ghosts), C.byref(ng), 1))
+        assert np.array_equal(ghosts, want_ghosts)
+        assert np.array_equal(fm["vid"], want_local)
+        assert np.array_equal(fm["dense_equal_to"], fm["dense_equal_to"])
+    fm = np.zeros(4, FactorToVar)
+    fm["vid"] = [1, 2, nvar, 3]
+    ng = C.c_int64(0)
+    with pytest.raises(Exception):
+        _lib.check(L.nb_block_ghosts(_lib.ptr(fm), 4, nvar, 0, 2, None, C.byref(ng), 0))
+    with pytest.raises(Exception):
+        _lib.check(L.nb_block_ghosts(_lib.ptr(fm), 4, nvar, 5, 2, None, C.byref(ng), 0))
