@@ -596,8 +596,7 @@ extern "C" int nb_gibbs_sweeps(nb_graph *g, int64_t n_epochs, int burnin, int sa
     const char *bits_env = getenv("NUMBSKULL_B200_BIT_MIRROR");          // (read per call: the tests toggle it)
     const long long bits_min = bits_env ? atoll(bits_env) : 100000000ll;
     g->use_bits = g->bits_eligible && g->p2p == nullptr && bits_min >= 0 && g->V >= bits_min;
-    if (g->use_bits) NB_TRY(nb_pack_value_bits(g));
-    int rc = NB_OK;
+    int rc = g->use_bits ? nb_pack_value_bits(g) : NB_OK;     // (no early return: the flags below are always reset)
     for (int64_t ep = 0; ep < n_epochs && rc == NB_OK; ep++) {
         uint64_t epoch = g->epoch_counter++;
         for (int c = 0; c < g->n_colors && rc == NB_OK; c++) rc = nb_launch_gibbs_color(g, c, burnin, sample_evidence, seed, epoch);
