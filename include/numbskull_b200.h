@@ -144,6 +144,16 @@ int nb_synth_kbc_block(int64_t nvar, uint64_t seed, int64_t n_weights, int64_t w
 int nb_block_ghosts(nb_ftv_rec *fmap, int64_t n_fmap, int64_t nvar, int64_t lo, int64_t hi, int64_t *ghosts,
                     int64_t *n_ghosts, int rewrite);
 
+/* The same for an arbitrary placement owner[v] (partition.extract_local_by_owner: an imported
+ * partition -- salt/src/messages.py:175-179 -- or a locality-aware one): the factors with a member
+ * owned by `rank` (order kept, ftv_offset renumbered), their members as local ids (owned first,
+ * ghosts after, both in ascending global id) and global_vid[n_owned + n_ghost].  Two calls:
+ * loc_factor == NULL returns the four counts. */
+int nb_extract_local(const nb_factor_rec *factor, int64_t n_factor, const nb_ftv_rec *fmap, int64_t n_fmap,
+                     const int32_t *owner, int64_t nvar, int32_t rank, int64_t *n_loc_factor, int64_t *n_loc_fmap,
+                     int64_t *n_owned, int64_t *n_ghost, nb_factor_rec *loc_factor, nb_ftv_rec *loc_fmap,
+                     int64_t *global_vid);
+
 /* -------------------------- graph lifecycle -------------------------- */
 
 /* FactorGraph.__init__ (factorgraph.py:30-73): builds the device-resident

@@ -66,6 +66,8 @@ SIGNATURES = {
     "nb_synth_kbc_block": (C.c_int, [_I64, _U64, _I64, _I64, _DBL, _DBL, _P, _I64, _I64, _P, C.POINTER(_I64), _P,
                                      C.POINTER(_I64)]),
     "nb_block_ghosts": (C.c_int, [_P, _I64, _I64, _I64, _I64, _P, C.POINTER(_I64), C.c_int]),
+    "nb_extract_local": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, C.c_int32, C.POINTER(_I64), C.POINTER(_I64),
+                                   C.POINTER(_I64), C.POINTER(_I64), _P, _P, _P]),
     "nb_graph_create": (C.c_int, [C.POINTER(GraphDesc), C.POINTER(_P)]),
     "nb_graph_destroy": (None, [_P]),
     "nb_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),

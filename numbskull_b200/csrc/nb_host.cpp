@@ -780,3 +780,112 @@ extern "C" int nb_block_ghosts(nb_ftv_rec *fmap, int64_t n_fmap, int64_t nvar, i
     }
     return NB_OK;
 }
+
+// partition.extract_local_by_owner in host threads: the share of rank `rank` under the placement
+// owner[v] -- every factor with an owned member (factor order kept, ftv_offset renumbered), its
+// members as local ids (owned variables first in ascending global id, then the ghosts in ascending
+// global id), and the global id of every local variable.  Two calls: loc_factor == NULL returns the
+// four counts.  Bitmaps + prefix popcounts, no sort (the numpy version needs ~1 us per variable and
+// several 8-byte temporaries per fmap entry).
+extern "C" int nb_extract_local(const nb_factor_rec *factor, int64_t n_factor, const nb_ftv_rec *fmap, int64_t n_fmap,
+                                const int32_t *owner, int64_t nvar, int32_t rank, int64_t *n_loc_factor, int64_t *n_loc_fmap,
+                                int64_t *n_owned, int64_t *n_ghost, nb_factor_rec *loc_factor, nb_ftv_rec *loc_fmap,
+                                int64_t *global_vid)
+{
+    if ((!factor && n_factor) || (!fmap && n_fmap) || (!owner && nvar)) NB_FAIL(NB_ERR_INVALID, "nb_extract_local: NULL input");
+    const int nt = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    const int64_t words = (nvar + 63) / 64;
+    std::vector<std::atomic<uint64_t>> ghost((size_t)words);
+    std::vector<uint64_t> mine((size_t)words, 0);
+    std::vector<uint8_t> keep((size_t)n_factor, 0);
+    std::vector<int64_t> cf((size_t)nt + 1, 0), ce((size_t)nt + 1, 0);
+    std::atomic<int> bad{0};
+    run_threads(nt, [&](int t) {
+        for (int64_t w = words * t / nt; w < words * (t + 1) / nt; w++) {
+            ghost[(size_t)w].store(0, std::memory_order_relaxed);
+            uint64_t m = 0;
+            for (int64_t v = w * 64; v < std::min(nvar, w * 64 + 64); v++)
+                if (owner[v] == rank) m |= 1ull << (v & 63);
+            mine[(size_t)w] = m;
+        }
+    });
+    // kept factors and their ghost members
+    run_threads(nt, [&](int t) {
+        int64_t nf = 0, ne = 0;
+        for (int64_t f = n_factor * t / nt; f < n_factor * (t + 1) / nt; f++) {
+            const int64_t a = factor[f].arity, o = factor[f].ftv_offset;
+            if (a < 0 || o < 0 || o + a > n_fmap) { bad.store(1); continue; }
+            bool k = false;
+            for (int64_t j = 0; j < a; j++) {
+                const int64_t v = fmap[o + j].vid;
+                if (v < 0 || v >= nvar) { bad.store(1); k = false; break; }
+                if (owner[v] == rank) k = true;
+            }
+            if (!k) continue;
+            keep[(size_t)f] = 1;
+            nf++;
+            ne += a;
+            for (int64_t j = 0; j < a; j++) {
+                const int64_t v = fmap[o + j].vid;
+                if (owner[v] != rank) {
+                    const uint64_t m = 1ull << (v & 63);
+                    if (!(ghost[(size_t)(v >> 6)].load(std::memory_order_relaxed) & m)) ghost[(size_t)(v >> 6)].fetch_or(m, std::memory_order_relaxed);
+                }
+            }
+        }
+        cf[(size_t)t + 1] = nf;
+        ce[(size_t)t + 1] = ne;
+    });
+    if (bad.load()) NB_FAIL(NB_ERR_INVALID, "nb_extract_local: a factor's members lie outside fmap or a member id outside [0, %lld)", (long long)nvar);
+    for (int t = 0; t < nt; t++) { cf[(size_t)t + 1] += cf[(size_t)t]; ce[(size_t)t + 1] += ce[(size_t)t]; }
+    // prefix popcounts of both bitmaps
+    std::vector<int64_t> pm((size_t)words + 1, 0), pg((size_t)words + 1, 0), tm((size_t)nt + 1, 0), tg((size_t)nt + 1, 0);
+    run_threads(nt, [&](int t) {
+        int64_t a = 0, b = 0;
+        for (int64_t w = words * t / nt; w < words * (t + 1) / nt; w++) {
+            a += __builtin_popcountll(mine[(size_t)w]);
+            b += __builtin_popcountll(ghost[(size_t)w].load(std::memory_order_relaxed));
+        }
+        tm[(size_t)t + 1] = a;
+        tg[(size_t)t + 1] = b;
+    });
+    for (int t = 0; t < nt; t++) { tm[(size_t)t + 1] += tm[(size_t)t]; tg[(size_t)t + 1] += tg[(size_t)t]; }
+    const int64_t no = tm[(size_t)nt], ng = tg[(size_t)nt];
+    if (!loc_factor) {
+        *n_loc_factor = cf[(size_t)nt]; *n_loc_fmap = ce[(size_t)nt]; *n_owned = no; *n_ghost = ng;
+        return NB_OK;
+    }
+    if (*n_loc_factor != cf[(size_t)nt] || *n_loc_fmap != ce[(size_t)nt] || *n_owned != no || *n_ghost != ng)
+        NB_FAIL(NB_ERR_INVALID, "nb_extract_local: the counts changed between the calls");
+    run_threads(nt, [&](int t) {
+        int64_t a = tm[(size_t)t], b = tg[(size_t)t];
+        for (int64_t w = words * t / nt; w < words * (t + 1) / nt; w++) {
+            pm[(size_t)w] = a;
+            pg[(size_t)w] = b;
+            uint64_t x = mine[(size_t)w];
+            while (x) { global_vid[a++] = w * 64 + __builtin_ctzll(x); x &= x - 1; }
+            x = ghost[(size_t)w].load(std::memory_order_relaxed);
+            while (x) { global_vid[no + b++] = w * 64 + __builtin_ctzll(x); x &= x - 1; }
+        }
+    });
+    run_threads(nt, [&](int t) {
+        int64_t nf = cf[(size_t)t], ne = ce[(size_t)t];
+        for (int64_t f = n_factor * t / nt; f < n_factor * (t + 1) / nt; f++) {
+            if (!keep[(size_t)f]) continue;
+            const int64_t a = factor[f].arity, o = factor[f].ftv_offset;
+            loc_factor[nf] = factor[f];
+            loc_factor[nf].ftv_offset = ne;
+            for (int64_t j = 0; j < a; j++) {
+                const int64_t v = fmap[o + j].vid;
+                const uint64_t below = (1ull << (v & 63)) - 1;
+                loc_fmap[ne + j].vid = owner[v] == rank
+                    ? pm[(size_t)(v >> 6)] + __builtin_popcountll(mine[(size_t)(v >> 6)] & below)
+                    : no + pg[(size_t)(v >> 6)] + __builtin_popcountll(ghost[(size_t)(v >> 6)].load(std::memory_order_relaxed) & below);
+                loc_fmap[ne + j].dense_equal_to = fmap[o + j].dense_equal_to;
+            }
+            nf++;
+            ne += a;
+        }
+    });
+    return NB_OK;
+}

@@ -82,7 +82,34 @@ def extract_local_by_owner(weight, variable, factor, fmap, owner, rank):
     """:func:`extract_local` for an arbitrary placement: ``owner[v]`` is the rank that owns global
     variable ``v`` (an imported partition, e.g. :func:`owners_from_salt_keys`, or a locality-aware
     one, :func:`locality_owners`).  Owned variables keep their relative order; ghosts follow in
-    increasing global id with ``isEvidence = 4``."""
+    increasing global id with ``isEvidence = 4``.  Host threads in the library (nb_extract_local);
+    :func:`_extract_local_by_owner_numpy` is the same rule in numpy (the tests compare them)."""
+    import ctypes as C
+    from . import _lib
+    from .numbskulltypes import Factor
+    L = _lib.lib()
+    owner32 = np.ascontiguousarray(owner, np.int32)
+    assert len(owner32) == len(variable)
+    factor_c, fmap_c = np.ascontiguousarray(factor), np.ascontiguousarray(fmap)
+    nf, ne, no, ng = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    args = (_lib.ptr(factor_c), len(factor_c), _lib.ptr(fmap_c), len(fmap_c), _lib.ptr(owner32), len(owner32), int(rank),
+            C.byref(nf), C.byref(ne), C.byref(no), C.byref(ng))
+    _lib.check(L.nb_extract_local(*args, None, None, None))
+    loc_factor = np.zeros(nf.value, Factor)
+    loc_fmap = np.zeros(ne.value, FactorToVar)
+    global_vid = np.empty(no.value + ng.value, np.int64)
+    _lib.check(L.nb_extract_local(*args, _lib.ptr(loc_factor), _lib.ptr(loc_fmap), _lib.ptr(global_vid)))
+    n_owned = no.value
+    loc_variable = variable[global_vid].copy()
+    loc_variable["isEvidence"][n_owned:] = 4
+    loc_variable["vtf_offset"] = 0
+    return dict(weight=weight.copy(), variable=loc_variable, factor=loc_factor, fmap=loc_fmap,
+                domain_mask=np.zeros(len(loc_variable), np.bool_), global_vid=global_vid,
+                n_owned=int(n_owned), owner=np.asarray(owner))
+
+
+def _extract_local_by_owner_numpy(weight, variable, factor, fmap, owner, rank):
+    """The rule of :func:`extract_local_by_owner`, vectorised numpy (reference for the tests)."""
     owner = np.asarray(owner)
     assert len(owner) == len(variable)
     arity = factor["arity"].astype(np.int64)
