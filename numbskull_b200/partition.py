@@ -668,10 +668,10 @@ def partition_graph(weight, variable, factor, fmap, rank, world, device, seed, g
     keys) or :func:`locality_owners`.  Samples do not depend on the placement: colours and Philox
     streams are functions of the global ids."""
     if owner is None:
+        # contiguous blocks: the same cut as extract_local (the tests compare them), made by host threads
         bounds = block_bounds(len(variable), world)
-        local = extract_local(weight, variable, factor, fmap, int(bounds[rank]), int(bounds[rank + 1]))
-    else:
-        local = extract_local_by_owner(weight, variable, factor, fmap, owner, rank)
+        owner = (np.searchsorted(bounds, np.arange(len(variable), dtype=np.int64), side="right") - 1).astype(np.int32)
+    local = extract_local_by_owner(weight, variable, factor, fmap, owner, rank)
     return PartitionedGibbs(local, len(variable), rank, world, device, seed, color_seed, group)
 
 
